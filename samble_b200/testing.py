@@ -1,0 +1,138 @@
+"""Shared test/bench helpers: synthetic clouds, deterministic weights, tie-aware comparators.
+
+Nothing here touches the oracle or the reference; it only produces inputs and
+compares outputs, so both the product tests and the golden-vector generator use it.
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+Tensor = torch.Tensor
+
+
+def synthetic_clouds(B: int, N: int, seed: int = 0) -> Tuple[Tensor, Tensor]:
+    """ShapeNetPart-shaped input: xyz ~ U(-1,1)^3 as (B,3,N) fp32 and a
+    one-hot category (B,16,1) with class b mod 16.  CPU tensors."""
+    g = torch.Generator().manual_seed(seed)
+    xyz = torch.rand(B, 3, N, generator=g, dtype=torch.float32) * 2 - 1
+    cat = torch.zeros(B, 16, 1)
+    cat[torch.arange(B), torch.arange(B) % 16, 0] = 1.0
+    return xyz, cat
+
+
+def synthetic_features(B: int, C: int, N: int, seed: int = 0) -> Tensor:
+    """x ~ N(0,1) (B,C,N): the micro-bench / parity input for feature-space kernels."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, C, N, generator=g, dtype=torch.float32)
+
+
+def fill_state_dict_(sd: Dict[str, Tensor], seed: int = 0, sharpen: float = 1.0) -> Dict[str, Tensor]:
+    """Overwrite every entry of a state_dict in place with values that depend only on
+    (seed, entry name, shape), so two differently-constructed models (the reference's
+    nn.Modules here, ours on the GPU box) hold identical weights without shipping them.
+
+    weights ~ N(0, 1/fan_in) (x `sharpen` for the DownSample q/k projections: SURVEY 8d's
+    "sharpened" variant), BN weight ~ U(0.5,1.5), BN bias/running_mean ~ N(0,0.1),
+    running_var ~ U(0.5,1.5), so eval-mode BN is not the identity."""
+    for name, t in sd.items():
+        g = torch.Generator().manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+        if name.endswith("num_batches_tracked"):
+            t.fill_(1)
+            continue
+        if name.endswith("running_var"):
+            v = torch.rand(t.shape, generator=g) + 0.5
+        elif name.endswith("running_mean"):
+            v = torch.randn(t.shape, generator=g) * 0.1
+        elif t.dim() == 1 and name.endswith("weight"):          # BN scale
+            v = torch.rand(t.shape, generator=g) + 0.5
+        elif t.dim() == 1:                                       # biases
+            v = torch.randn(t.shape, generator=g) * 0.1
+        elif name.endswith("bin_tokens"):
+            v = torch.randn(t.shape, generator=g) / (t.shape[1] ** 0.5)
+        else:
+            fan_in = t[0].numel()
+            v = torch.randn(t.shape, generator=g) / (fan_in ** 0.5)
+            if sharpen != 1.0 and "downsample_list" in name and (".q_conv." in name or ".k_conv." in name):
+                v = v * sharpen
+        if name.endswith("transform.weight"):
+            v = v * 0.05          # keep the STN near identity like its zero-init (embedding.py:73-74)
+        if name.endswith("transform.bias"):
+            v = torch.eye(3).reshape(-1) + v * 0.05
+        t.copy_(v.to(t.dtype))
+    return sd
+
+
+# --------------------------------------------------------------------------
+# comparators (SURVEY 8c protocol step 5)
+# --------------------------------------------------------------------------
+
+
+def knn_parity(idx: Tensor, ref_idx: Tensor, a: Tensor, b: Tensor, rel_band: float = 2e-5) -> dict:
+    """Tie-aware kNN comparison.  a (B,Nq,C), b (B,Nr,C) are the RAW inputs.
+
+    Exact position-wise match rate is reported; every mismatching row must agree as
+    a SET except for members whose fp64 squared distance (raw units; the reference's
+    normalisation is a per-cloud similarity transform, so order is unaffected) lies
+    within `rel_band` (relative) of that row's k-th distance -- i.e. the swap is an
+    fp32 near-tie that no two fp32 implementations are obliged to order alike.
+    """
+    idx, ref_idx = idx.cpu().long(), ref_idx.cpu().long()
+    B, Nq, k = ref_idx.shape
+    exact = (idx == ref_idx)
+    bad_rows = (~exact.all(dim=-1)).nonzero()
+    a64, b64 = a.double().cpu(), b.double().cpu()
+    unexplained = 0
+    for bi, qi in bad_rows.tolist():
+        d = ((b64[bi] - a64[bi, qi]) ** 2).sum(-1)                  # (Nr,)
+        mine, ref = idx[bi, qi], ref_idx[bi, qi]
+        if len(set(mine.tolist())) != k:
+            unexplained += 1
+            continue
+        kth = torch.sort(d)[0][k - 1]
+        band = rel_band * max(float(kth), 1e-30)
+        # every element either side must be no worse than the k-th distance + band,
+        # and the sequence must be sorted up to the band
+        ok = bool((d[mine] <= kth + band).all()) and bool((d[ref] <= kth + band).all())
+        dm = d[mine]
+        ok = ok and bool((dm[1:] - dm[:-1] >= -band).all())
+        unexplained += 0 if ok else 1
+    return dict(exact_rate=float(exact.float().mean()), rows=B * Nq, mismatch_rows=len(bad_rows),
+                unexplained_rows=unexplained)
+
+
+def sampled_index_parity(idx: Tensor, ref_idx: Tensor, score: Tensor, k_per_bin: Tensor) -> dict:
+    """Tie-aware sampler comparison.  idx/ref_idx (B,1,M) int64, score (B,1,N) is the
+    REFERENCE score, k_per_bin (B,nb).  Indices must be equal except inside groups of
+    exactly equal reference score (sort order among equals is implementation-defined)."""
+    idx, ref_idx, score = idx.cpu(), ref_idx.cpu(), score.cpu()
+    B, _, M = ref_idx.shape
+    exact = idx == ref_idx
+    unexplained = 0
+    for b in range(B):
+        if bool(exact[b].all()):
+            continue
+        s = score[b, 0]
+        off = 0
+        for kb in k_per_bin[b].tolist():
+            seg_m, seg_r = idx[b, 0, off:off + kb], ref_idx[b, 0, off:off + kb]
+            off += kb
+            if torch.equal(seg_m, seg_r):
+                continue
+            # same multiset of scores in the same order == only ties were permuted
+            if not torch.equal(s[seg_m], s[seg_r]) or len(set(seg_m.tolist())) != kb:
+                unexplained += 1
+    return dict(exact_rate=float(exact.float().mean()), clouds=B, unexplained_bins=unexplained)
+
+
+def max_abs_rel(x: Tensor, ref: Tensor) -> Tuple[float, float]:
+    x, ref = x.detach().double().cpu(), ref.detach().double().cpu()
+    err = (x - ref).abs()
+    return float(err.max()), float((err / (ref.abs() + 1e-6)).max())
+
+
+def to_numpy_tree(d: dict) -> Dict[str, np.ndarray]:
+    return {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
