@@ -1,0 +1,166 @@
+/*
+ * samble_b200.h -- C ABI of the B200-native SAMBLE neighbourhood + sampling hot path.
+ *
+ * The reference (stevenczwu/SAMBLE) has no native code: its hot path is a Python
+ * namespace (utils/ops.py) plus four nn.Modules.  Each entry point below replaces the
+ * ATen call sequence of ONE reference function; the reference lines it replaces are
+ * cited as file:line (paths relative to the upstream repository root).  The Python
+ * binding a maintainer would add is shown in INTEGRATION.md (ctypes, no torch types
+ * in any signature).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers into caller-owned, contiguous buffers unless
+ *     a leading dimension (`ld*`, in elements) is given.  fp32 data, row-major.
+ *   - "channel-major" = (B, C, N) as the reference's models pass clouds around;
+ *     "point-major"   = (B, N, C).
+ *   - Index tensors are int64 (the reference's dtype, torch.topk) when idx_bits==64,
+ *     or int32 when idx_bits==32 (internal fast path; halves index traffic).
+ *   - `ws` is caller-owned scratch of at least the matching *_workspace_bytes();
+ *     the library never allocates, never synchronises, never touches the default
+ *     stream: every kernel goes to `stream`, so calls are CUDA-graph capturable.
+ *   - Return value: 0 on success, <0 on failure (SAMBLE_E_*).  Nothing throws.
+ *     samble_last_error() returns a thread-local description of the last failure.
+ */
+#ifndef SAMBLE_B200_H_
+#define SAMBLE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* samble_stream_t; /* cudaStream_t */
+
+enum {
+  SAMBLE_OK = 0,
+  SAMBLE_E_INVALID = -1,   /* bad argument (shape, k, alignment, null pointer) */
+  SAMBLE_E_WORKSPACE = -2, /* ws too small */
+  SAMBLE_E_CUDA = -3       /* launch failed; see samble_last_error() */
+};
+
+enum { SAMBLE_GROUP_NEIGHBOR = 0, SAMBLE_GROUP_DIFF = 1, SAMBLE_GROUP_CENTER_NEIGHBOR = 2, SAMBLE_GROUP_CENTER_DIFF = 3 };
+
+int samble_abi_version(void);
+const char* samble_last_error(void);
+/* number of kernel launches issued by this library on the calling thread since the
+ * last reset (bench.py's gpu_launches claim is read from here). */
+long long samble_launch_count(void);
+void samble_reset_launch_count(void);
+
+/* ---------------------------------------------------------------- kNN ----------
+ * utils/ops.py:17-44  knn(a, b, k) -> (distance, idx).
+ * a: queries, b: candidates; element (bi, n, c) lives at base + bi*a_sb + n*a_sn + c*a_sc
+ * (strides in elements), so both the (B,N,C) tensors of ops.knn and the (B,C,N)
+ * tensors of ops.select_neighbors (:50, a permute view) are passed without a copy.
+ * Both clouds are centred/scaled by a's statistics (:23-29).  Distances use the GEMM
+ * form of torch.cdist (:35) in fp32; selection is the k smallest, nearest first,
+ * ties broken by lower index.  b == a (same pointer+strides) is the self-kNN case.
+ * idx_out: (B,Nq,k) int32|int64.  dist_out: (B,Nq,k) fp32 NEGATIVE Euclidean
+ * distance in normalised units (what :43 returns), or NULL.
+ * Limits: 1 <= k <= 32, k <= Nr, C <= 512.
+ */
+size_t samble_knn_workspace_bytes(int B, int Nq, int Nr, int C);
+int samble_knn(const float* a, long long a_sb, long long a_sn, long long a_sc,
+               const float* b, long long b_sb, long long b_sn, long long b_sc,
+               int B, int Nq, int Nr, int C, int k,
+               void* idx_out, int idx_bits, float* dist_out,
+               void* ws, size_t ws_bytes, samble_stream_t stream);
+
+/* ------------------------------------------------------------- gathers ----------
+ * utils/ops.py:5-14  index_points(points (B,N,C), idx (B,M,K)) -> (B,M,K,C).
+ * R = M*K rows per cloud. */
+int samble_index_points(const float* points, const void* idx, int idx_bits, int B, int N, int C, int R,
+                        float* out, samble_stream_t stream);
+
+/* utils/ops.py:47-65,83-112  select_neighbors/group, AFTER the kNN.
+ * pcd (B,C,N) channel-major, idx (B,N,K).
+ * type NEIGHBOR|DIFF: out is (B,N,K,C) contiguous -- the reference returns exactly this
+ *   memory as a permuted (B,C,N,K) view (:57,:60).
+ * type CENTER_*: out is (B,2C,N,K) contiguous (torch.cat, :98-107). */
+int samble_group(const float* pcd, const void* idx, int idx_bits, int B, int C, int N, int K, int type,
+                 float* out, samble_stream_t stream);
+
+/* utils/ops.py:136-145  gather_by_idx(pcd (B,C,N), idx (B,1,M)) -> (B,C,M). */
+int samble_gather_by_idx(const float* pcd, const void* idx, int idx_bits, int B, int C, int N, int M,
+                         float* out, samble_stream_t stream);
+
+/* utils/ops.py:125-133  neighbor_mask: dense 0/1 (B,N,N) from idx (B,N,K) (zeros + scatter_). */
+int samble_neighbor_mask(const void* idx, int idx_bits, int B, int N, int K, float* out, samble_stream_t stream);
+
+/* ------------------------------------------------- Neighbor2Point attention -----
+ * models/attention.py:165-185,207-250 (scalar_dot, asm "dot"), with the bias-free
+ * k/v convolutions hoisted out of the neighbour dimension:
+ *   W(x_j - x_i) = W x_j - W x_i, and softmax over j is invariant to the -q.Wk x_i shift.
+ * q,k,v: point-major (B,N,C) with leading dimension ld (elements per point), i.e. the
+ * projections of the N points themselves; idx (B,N,K) from the kNN on x.
+ * out (B,N,C) point-major: sum_j softmax_j(q_i.k_j/sqrt(C/H)) v_j - v_i per head. */
+int samble_n2p_attend(const float* q, const float* k, const float* v, long long ld,
+                      const void* idx, int idx_bits, int B, int N, int C, int K, int heads,
+                      float* out, long long ld_out, samble_stream_t stream);
+
+/* --------------------------------------------------- DownSampleToken scoring ----
+ * models/downsample.py:124-153: energy = q @ [k | k_tok] / sqrt(D), row softmax over
+ * N+nb columns.  The N x (N+nb) map is never written: this pass leaves per-row
+ * max and sum-of-exp plus the PRE-softmax token columns (:149-152).
+ * q,k: point-major (B,N,D) with leading dims; k_tok: (nb,D) (tokens are shared by the
+ * batch, :116).  rowmax,rowsum: (B,N).  token_logits: (B,N,nb). */
+int samble_ds_row_stats(const float* q, long long ldq, const float* k, long long ldk, const float* k_tok,
+                        int B, int N, int D, int nb, float* rowmax, float* rowsum, float* token_logits,
+                        samble_stream_t stream);
+
+/* models/downsample.py:300-344 (idx_mode sparse_col_sqr) without the dense mask:
+ *   score[j] = sum_{i : j in kNN(i)} softmax_i[j] / indeg(j)^2,  NaN -> 0.
+ * Only the N*K edges are evaluated; accumulation order is fixed (deterministic). */
+size_t samble_ds_edge_score_workspace_bytes(int B, int N);
+int samble_ds_edge_score(const float* q, long long ldq, const float* k, long long ldk,
+                         const float* rowmax, const float* rowsum, const void* idx, int idx_bits,
+                         int B, int N, int D, int K, float* score, void* ws, size_t ws_bytes,
+                         samble_stream_t stream);
+
+/* ------------------------------------------------ bins, k per bin, sampling -----
+ * utils/ops.py:450-452  z = (s - mean) / std_population over the N points of each row. */
+int samble_zscore(const float* score, int rows, int N, float* z, samble_stream_t stream);
+
+/* utils/ops.py:460-462  mask[r,n,j] = z < upper[j] && z >= lower[j]  (uint8 0/1). */
+int samble_bin_mask(const float* z, const float* upper, const float* lower, int rows, int N, int nb,
+                    uint8_t* mask, samble_stream_t stream);
+
+/* utils/ops.py:385-432  calculate_num_points_to_choose. bin_prob (B,nb) fp32,
+ * max_num_points (B,nb) int64 -> k (B,nb) int32, op-for-op in fp32 (same summation
+ * order, truncation and first-argmax remainder rule). nb <= 8. */
+int samble_num_points_to_choose(const float* bin_prob, const long long* max_num_points, int B, int nb, int total,
+                                int* k_out, samble_stream_t stream);
+
+/* utils/ops.py:476-505  generating_downsampled_index, 'topk' branch.
+ * score (B,N), mask (B,N,nb) uint8, k (B,nb) int32 -> idx (B,M) int64:
+ * bins in order, inside a bin descending (score+1e-8)*mask, ties by lower index. */
+int samble_downsample_index_topk(const float* score, const uint8_t* mask, const int* k, int B, int N, int nb, int M,
+                                 long long* idx_out, samble_stream_t stream);
+
+/* models/downsample.py:205-240 fused for the shipped configuration (mean_relu,
+ * multi_token, topk): z-score -> bins by `cuts` (nb-1 descending thresholds, device) ->
+ * per-bin mean of token logits -> k per bin -> per-bin top-k.
+ * Outputs: idx (B,M) int64; bin_id (B,N) uint8 (255 = in no bin); counts (B,nb) int32;
+ * k_out (B,nb) int32; w_raw (B,nb) fp32 (bin_weights_beforerelu); z (B,N) or NULL. */
+int samble_ds_sample(const float* score, const float* token_logits, const float* cuts,
+                     int B, int N, int nb, int M,
+                     long long* idx_out, uint8_t* bin_id, int* counts, int* k_out, float* w_raw, float* z_out,
+                     samble_stream_t stream);
+
+/* ------------------------------------------------------------- UpSample ---------
+ * models/upsample.py:194-212 + utils/ops.py:68-80 fused: 3-NN of each of the N "up"
+ * points among the M selected points in xyz (normalised by the up cloud's statistics,
+ * ops.py:23-29), weights 1/(d+1e-8) normalised, weighted sum of the selected features.
+ * xyz_up (B,3,N), xyz_sel (B,3,M), feat (B,C,M) channel-major -> out (B,C,N).
+ * idx_out (B,N,3) int64 and dist_out (B,N,3) (positive) are optional (NULL). */
+size_t samble_interpolate3_workspace_bytes(int B, int N, int M);
+int samble_interpolate3(const float* xyz_up, const float* xyz_sel, const float* feat,
+                        int B, int N, int M, int C, float* out, long long* idx_out, float* dist_out,
+                        void* ws, size_t ws_bytes, samble_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAMBLE_B200_H_ */

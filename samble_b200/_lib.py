@@ -1,0 +1,125 @@
+"""ctypes binding of libsamble_b200.so (the C ABI declared in include/samble_b200.h).
+
+There is deliberately no fallback: if the library is missing, or a tensor is not on a
+CUDA device, every entry point raises.  PyTorch is used only to own device memory and
+to name the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Dict, Tuple
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libsamble_b200.so")
+HEADER = os.path.join(HERE, "..", "include", "samble_b200.h")
+
+_p, _i, _ll, _sz, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_float
+
+# name -> (restype, argtypes); mirrors include/samble_b200.h one to one (tests/test_abi.py
+# parses the header and checks that nothing is missing on either side).
+PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
+    "samble_abi_version": (_i, ()),
+    "samble_last_error": (C.c_char_p, ()),
+    "samble_launch_count": (_ll, ()),
+    "samble_reset_launch_count": (None, ()),
+    "samble_knn_workspace_bytes": (_sz, (_i, _i, _i, _i)),
+    "samble_knn": (_i, (_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _p, _i, _p, _p, _sz, _p)),
+    "samble_index_points": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
+    "samble_group": (_i, (_p, _p, _i, _i, _i, _i, _i, _i, _p, _p)),
+    "samble_gather_by_idx": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
+    "samble_neighbor_mask": (_i, (_p, _i, _i, _i, _i, _p, _p)),
+    "samble_n2p_attend": (_i, (_p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p)),
+    "samble_ds_row_stats": (_i, (_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p)),
+    "samble_ds_edge_score_workspace_bytes": (_sz, (_i, _i)),
+    "samble_ds_edge_score": (_i, (_p, _ll, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p)),
+    "samble_zscore": (_i, (_p, _i, _i, _p, _p)),
+    "samble_bin_mask": (_i, (_p, _p, _p, _i, _i, _i, _p, _p)),
+    "samble_num_points_to_choose": (_i, (_p, _p, _i, _i, _i, _p, _p)),
+    "samble_downsample_index_topk": (_i, (_p, _p, _p, _i, _i, _i, _i, _p, _p)),
+    "samble_ds_sample": (_i, (_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p)),
+    "samble_interpolate3_workspace_bytes": (_sz, (_i, _i, _i)),
+    "samble_interpolate3": (_i, (_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p)),
+}
+
+_lib = None
+
+
+def header_symbols() -> set:
+    with open(HEADER) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return set(re.findall(r"\b(samble_[a-z0-9_]+)\s*\(", text))
+
+
+def lib() -> C.CDLL:
+    """The loaded library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"samble_b200: native library {LIB_PATH} is missing. Build it with "
+                "`python -m samble_b200._build` (needs nvcc); there is no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, list(args)
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    msg = lib().samble_last_error().decode() or what
+    if rc == -1:
+        raise ValueError(msg)
+    raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def need_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("samble_b200 runs on CUDA tensors only (no CPU path); got a tensor on " + str(t.device))
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"samble_b200: tensors on different devices ({dev} vs {t.device})")
+    return dev
+
+
+def no_grad_check(*tensors: torch.Tensor) -> None:
+    """Forward-only (SURVEY 8b 'Autograd'): refuse rather than return silently wrong gradients."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise RuntimeError("samble_b200 native ops are forward-only: run under torch.no_grad() "
+                           "(backward is SURVEY 8f item f1)")
+
+
+def ptr(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Grow-only scratch per (device, stream): stream order makes reuse across calls safe, and a
+    stable pointer keeps CUDA-graph replays valid (size it by one eager warm-up first)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("samble_b200: workspace must be sized by an eager warm-up before graph capture")
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws

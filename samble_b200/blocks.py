@@ -1,0 +1,242 @@
+"""The four hot-path blocks as nn.Modules, state_dict-compatible with the reference's.
+
+Constructor signature `Cls(config_subtree, layer)`, forward signatures, parameter
+names/shapes and the public attributes callers read follow
+  models/embedding.py:7-39     EdgeConv
+  models/attention.py:130-250  Neighbor2PointAttention
+  models/downsample.py:15-378  DownSampleToken
+  models/upsample.py:136-213   UpSampleInterpolation
+so a reference checkpoint loads with load_state_dict and the reference's model wiring
+can construct these in place of its own (samble_b200.patch).
+
+Forward passes run the sm_100a kernels through samble_b200.ops; plain library GEMMs
+(1x1 convolutions on N points, BatchNorm) stay in PyTorch/cuBLAS.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+class EdgeConv(nn.Module):
+    """models/embedding.py:7-39: group -> (conv1x1+BN+LeakyReLU) x2 -> max over K."""
+
+    def __init__(self, config_embedding, layer):
+        super().__init__()
+        self.K = config_embedding.K[layer]
+        self.group_type = config_embedding.group_type[layer]
+        self.normal_channel = config_embedding.normal_channel
+
+        def cbl(cin, cout):
+            return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=1, bias=False), nn.BatchNorm2d(cout),
+                                 nn.LeakyReLU(negative_slope=0.2))
+
+        self.conv1 = cbl(config_embedding.conv1_in[layer], config_embedding.conv1_out[layer])
+        self.conv2 = cbl(config_embedding.conv2_in[layer], config_embedding.conv2_out[layer])
+
+    def forward(self, x: Tensor) -> Tensor:
+        x, _ = ops.group(x, self.K, self.group_type, self.normal_channel)
+        return self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0]
+
+
+class Neighbor2PointAttention(nn.Module):
+    """models/attention.py:130-250 (scalar_dot / asm 'dot' / group 'diff', the shipped setting).
+
+    The reference convolves the gathered (B,C,N,K) differences with k_conv/v_conv; both are
+    bias-free and linear, so the N points are projected ONCE ([q|k|v] in one GEMM) and the fused
+    kernel gathers projected rows (csrc/attention.cu): 32x fewer projection FLOPs, no (B,C,N,K)."""
+
+    def __init__(self, config_attention, layer):
+        super().__init__()
+        self.K = config_attention.K[layer]
+        self.group_type = config_attention.group_type[layer]
+        self.num_heads = config_attention.num_heads[layer]
+        self.attention_mode = config_attention.attention_mode[layer]
+        self.asm = config_attention.asm[layer]
+        q_in, q_out = config_attention.q_in[layer], config_attention.q_out[layer]
+        k_in, k_out = config_attention.k_in[layer], config_attention.k_out[layer]
+        v_in, v_out = config_attention.v_in[layer], config_attention.v_out[layer]
+        self.q_depth, self.k_depth, self.v_depth = (int(c / self.num_heads) for c in (q_out, k_out, v_out))
+        self.q_conv = nn.Conv2d(q_in, q_out, 1, bias=False)
+        self.k_conv = nn.Conv2d(k_in, k_out, 1, bias=False)
+        self.v_conv = nn.Conv2d(v_in, v_out, 1, bias=False)
+        self.softmax = nn.Softmax(dim=-1)
+        self.ff = nn.Sequential(
+            nn.Conv1d(config_attention.ff_conv1_channels_in[layer], config_attention.ff_conv1_channels_out[layer], 1, bias=False),
+            nn.LeakyReLU(negative_slope=0.2),
+            nn.Conv1d(config_attention.ff_conv2_channels_in[layer], config_attention.ff_conv2_channels_out[layer], 1, bias=False),
+        )
+        self.bn1 = nn.BatchNorm1d(v_out)
+        self.bn2 = nn.BatchNorm1d(v_out)
+
+    def forward(self, x: Tensor) -> Tensor:
+        if self.group_type != "diff" or self.attention_mode != "scalar_dot" or self.asm != "dot":
+            raise NotImplementedError("native Neighbor2PointAttention covers group_type='diff', "
+                                      "attention_mode='scalar_dot', asm='dot' (the shipped configs)")
+        B, C, N = x.shape
+        idx = ops.knn_indices(x, self.K)                                        # (B,N,K) int32
+        w = torch.cat([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C)
+        qkv = torch.matmul(x.transpose(1, 2), w.t())                            # (B,N,3C) point-major
+        y = ops.n2p_attend(qkv, idx, self.num_heads)                            # (B,N,C)
+        x = self.bn1(x + y.transpose(1, 2))
+        return self.bn2(x + self.ff(x))
+
+
+class DownSampleToken(nn.Module):
+    """models/downsample.py:15-378 for the shipped configuration: asm 'dot', one head, multi_token,
+    idx_mode sparse_col_sqr, mean_relu, res off, sample_mode 'topk'.
+
+    Pipeline (no N x N tensor is ever written):
+      [q|k|v] projection (cuBLAS) -> feature kNN (knn.cu) -> row softmax statistics (downsample.cu)
+      -> edge-only column score -> z-score / bins / k per bin / per-bin top-k (sampler.cu)
+      -> attention rows of the M selected points x V (cuBLAS on an M x (N+nb) slab).
+    """
+
+    def __init__(self, config_ds, layer):
+        super().__init__()
+        self.M = config_ds.M[layer]
+        self.K = config_ds.K
+        self.asm = config_ds.asm[layer]
+        self.res = config_ds.res.enable[layer]
+        self.ff = config_ds.res.ff[layer]
+        self.num_heads = config_ds.num_heads[layer]
+        self.idx_mode = config_ds.idx_mode[layer]
+        self.relu_mean_order = config_ds.bin.relu_mean_order[layer]
+        self.num_bins = config_ds.bin.num_bins[layer]
+        q_in, q_out = config_ds.q_in[layer], config_ds.q_out[layer]
+        k_in, k_out = config_ds.k_in[layer], config_ds.k_out[layer]
+        v_in, v_out = config_ds.v_in[layer], config_ds.v_out[layer]
+        self.q_depth, self.k_depth, self.v_depth = (int(c / self.num_heads) for c in (q_out, k_out, v_out))
+        self.q_conv = nn.Conv1d(q_in, q_out, 1, bias=False)
+        self.k_conv = nn.Conv1d(k_in, k_out, 1, bias=False)
+        self.v_conv = nn.Conv1d(v_in, v_out, 1, bias=False)
+        self.token_mode = config_ds.bin.token_mode[layer]
+        if self.token_mode != "multi_token":
+            raise NotImplementedError("only token_mode 'multi_token' (the shipped setting) is built")
+        self.bin_tokens = nn.Parameter(torch.normal(mean=0, std=1 / math.sqrt(q_in), size=(1, q_in, self.num_bins)))
+        self.softmax = nn.Softmax(dim=-1)
+        if self.res:
+            raise NotImplementedError("DownSampleToken residual link is off in every shipped config (default.yaml:188-190)")
+        self.scaling_factor = config_ds.bin.scaling_factor[layer]
+        self.bin_sample_mode = config_ds.bin.sample_mode[layer]
+        self.bin_norm_mode = config_ds.bin.norm_mode[layer]
+        self.momentum_update_factor = config_ds.bin.momentum_update_factor[layer]
+        self.dynamic_boundaries_enable = config_ds.bin.dynamic_boundaries_enable
+        if self.dynamic_boundaries_enable:
+            self.bin_boundaries = None
+        else:
+            cuts = [float(v) for v in config_ds.bin.bin_boundaries[layer]]     # not mutated (cf. downsample.py:98-99)
+            self.bin_boundaries = [torch.tensor([float("inf")] + cuts).reshape(1, 1, 1, self.num_bins),
+                                   torch.tensor(cuts + [float("-inf")]).reshape(1, 1, 1, self.num_bins)]
+        self.boltzmann_enable = config_ds.boltzmann.enable[layer]
+        self.boltzmann_T = config_ds.bin.boltzmann_T[layer]
+        self.boltzmann_norm_mode = config_ds.boltzmann.norm_mode[layer]
+        self.token_orthognonal_loss_factor = config_ds.bin.token_orthognonal_loss_factor
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _cuts(self, device) -> Tensor:
+        """the nb-1 finite thresholds of the [upper, lower] pair, checked non-increasing once per change."""
+        upper = self.bin_boundaries[0]
+        if upper.device != device:
+            self.bin_boundaries = [t.to(device) for t in self.bin_boundaries]
+            upper = self.bin_boundaries[0]
+        return upper.reshape(-1)[1:].to(torch.float32).contiguous()
+
+    def forward(self, x: Tensor, x_xyz=None):
+        if self.asm != "dot" or self.idx_mode != "sparse_col_sqr" or self.relu_mean_order != "mean_relu" or self.num_heads != 1:
+            raise NotImplementedError("native DownSampleToken covers asm='dot', idx_mode='sparse_col_sqr', "
+                                      "relu_mean_order='mean_relu', one head (the shipped configs)")
+        if self.bin_sample_mode != "topk":
+            raise NotImplementedError(f"bin sample_mode '{self.bin_sample_mode}' is SURVEY 8f item f3; use 'topk'")
+        B, C, N = x.shape
+        D, nb = self.q_depth, self.num_bins
+        # projections of the points and of the nb bin tokens (shared by the whole batch, :116-118)
+        w = torch.cat([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C)
+        qkv = torch.matmul(x.transpose(1, 2), w.t())                           # (B,N,3C)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        tok = self.bin_tokens[0].t()                                           # (nb,C)
+        k_tok = torch.matmul(tok, self.k_conv.weight.view(C, C).t()).contiguous()   # (nb,D)
+        v_tok = torch.matmul(tok, self.v_conv.weight.view(C, C).t())
+
+        idx = ops.knn_indices(x, self.K)                                       # neighbor_mask's kNN (:301)
+        rowmax, rowsum, tok_logits = ops.ds_row_stats(q, k, k_tok)
+        score = ops.ds_edge_score(q, k, rowmax, rowsum, idx)                   # (B,N)
+        self.attention_point_score = score.view(B, 1, N)
+
+        if self.dynamic_boundaries_enable:
+            z = ops.zscore(score)
+            self.bin_boundaries = ops.update_sampling_score_bin_boundary(
+                self.bin_boundaries, z.view(B, 1, N, 1), nb, self.momentum_update_factor)
+        s = ops.ds_sample(score, tok_logits, self._cuts(x.device), self.M)
+        index_down = s["idx"].view(B, 1, self.M)
+        self.bin_points_mask = (s["bin_id"].view(B, 1, N, 1) == torch.arange(nb, device=x.device, dtype=torch.uint8))
+        self.k_point_to_choose = s["k"]
+        self.bin_weights_beforerelu = s["w_raw"]
+
+        # attention rows of the selected points over all N+nb keys, times V (:242-252)
+        q_sel = torch.gather(q, 1, s["idx"].unsqueeze(-1).expand(-1, -1, D))   # (B,M,D)
+        scale = math.sqrt(D)
+        logits = torch.cat([torch.matmul(q_sel, k.transpose(1, 2)), torch.matmul(q_sel, k_tok.t())], dim=-1) / scale
+        att = torch.softmax(logits, dim=-1)
+        x_ds = torch.matmul(att[..., :N], v) + torch.matmul(att[..., N:], v_tok)   # (B,M,C)
+        x_ds = x_ds.transpose(1, 2)
+
+        self.idx = index_down
+        self.attention_bins_beforesoftmax = tok_logits.view(B, 1, N, nb)
+        return (x_ds, index_down), (None, None)
+
+    # reference API kept for callers (downsample.py:346-378)
+    def output_variable_calculatio(self):
+        B, _, _, num_bins = self.bin_points_mask.shape
+        index_batch, _, index_point, index_bin = torch.where(self.bin_points_mask)
+        self.idx_chunks = [[index_point[(index_bin == i) & (index_batch == j)].reshape(1, -1) for j in range(B)]
+                           for i in range(num_bins)]
+        self.bin_prob = self.bin_weights_beforerelu
+
+    def output_variables(self, *args):
+        vals = tuple(getattr(self, key) for key in args)
+        return vals[0] if len(vals) == 1 else (vals if vals else None)
+
+
+class UpSampleInterpolation(nn.Module):
+    """models/upsample.py:136-213: conv on the coarse features -> 3-NN inverse-distance interpolation
+    (fused kernel, csrc/upsample.cu) -> concat skip -> conv."""
+
+    def __init__(self, config_upsample, layer):
+        super().__init__()
+        q_in, v_out = config_upsample.q_in[layer], config_upsample.v_out[layer]
+        self.distance_type = config_upsample.interpolation.distance_type[layer]
+        self.K = config_upsample.interpolation.K[layer]
+
+        def cbl(cin, cout):
+            return nn.Sequential(nn.Conv1d(cin, cout, 1, bias=False), nn.BatchNorm1d(cout), nn.LeakyReLU(negative_slope=0.2))
+
+        self.conv = cbl(q_in, v_out)
+        self.res_conv = cbl(2 * v_out, v_out)
+
+    def forward(self, pcd_up, pcd_down, pcd_up_xyz):
+        (points_select, idx_select, points_select_xyz), (points_drop, idx_drop) = pcd_down
+        interpolated = self.interpolate(pcd_up, points_select, pcd_up_xyz, points_select_xyz,
+                                        distance_type=self.distance_type, K=self.K)
+        return self.res_conv(torch.cat([pcd_up, interpolated], dim=1))
+
+    def interpolate(self, pcd_up, points_select, pcd_up_xyz, points_select_xyz, distance_type="feature", K=3):
+        feat = self.conv(points_select)
+        if distance_type == "xyz" and K == 3:
+            return ops.interpolate3(pcd_up_xyz, points_select_xyz, feat)
+        if distance_type == "feature":
+            nbr, _, d = ops.select_neighbors_interpolate(pcd_up, points_select, feat, K=K)
+        elif distance_type == "xyz":
+            nbr, _, d = ops.select_neighbors_interpolate(pcd_up_xyz, points_select_xyz, feat, K=K)
+        else:
+            raise ValueError(f"upsample interpolation distance type can only be feature or xyz! Got: {distance_type}")
+        w = 1.0 / (d + 1e-8)
+        w = w / torch.sum(w, dim=-1, keepdim=True)
+        return torch.sum(nbr * w.unsqueeze(dim=1), dim=-1)

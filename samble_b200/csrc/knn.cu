@@ -1,0 +1,346 @@
+// kNN for SAMBLE clouds: replaces reference utils/ops.py:17-44 (mean/std normalisation, torch.cdist,
+// topk) with   stats -> normalise -> fused (distance tile + k-selection)   kernels.
+// The (B,Nq,Nr) distance matrix is never written to HBM.
+#include "common.cuh"
+#include "gemm_tile.cuh"
+
+namespace samble {
+
+// ------------------------------------------------------------------------------------------
+// per-cloud, per-channel mean and unbiased std of the QUERY cloud (ops.py:23,27).
+// one warp per channel; fp64 one-pass sums (exactly-rounded-quality results, order-independent
+// to well below fp32 resolution).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) knn_stats_kernel(const float* __restrict__ a, long long sb, long long sn,
+                                                        long long sc, int N, int C, float* __restrict__ mean,
+                                                        float* __restrict__ stdv) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp, b = blockIdx.y;
+  if (c >= C) return;
+  const float* p = a + b * sb + c * sc;
+  double s = 0.0, s2 = 0.0;
+  for (int n = lane; n < N; n += 32) {
+    double v = (double)p[n * sn];
+    s += v;
+    s2 += v * v;
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    double m = s / N;
+    double var = (s2 - s * m) / (double)(N - 1);
+    mean[b * C + c] = (float)m;
+    stdv[b * C + c] = (float)sqrt(var > 0.0 ? var : 0.0);
+  }
+}
+
+// sigma = mean over channels of the per-channel std (ops.py:27), summed in channel order.
+__device__ __forceinline__ float cloud_sigma(const float* stdv, int C) {
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s = __fadd_rn(s, stdv[c]);
+  return __fdiv_rn(s, (float)C);
+}
+
+// xyz path (C <= 3): one float4 per point = (x', y', z', |p'|^2), primes = normalised (ops.py:24-29).
+__global__ void __launch_bounds__(256) knn_prep_xyz_kernel(const float* __restrict__ x, long long sb, long long sn,
+                                                           long long sc, int N, int C, const float* __restrict__ mean,
+                                                           const float* __restrict__ stdv, float4* __restrict__ out) {
+  const int b = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float sigma = cloud_sigma(stdv + b * C, C);
+  float v[3] = {0.f, 0.f, 0.f};
+  for (int c = 0; c < C; ++c) v[c] = __fdiv_rn(__fsub_rn(x[b * sb + n * sn + c * sc], mean[b * C + c]), sigma);
+  // x.pow(2).sum(-1) of at::_euclidean_dist: products rounded separately, summed in channel order
+  float nn = __fmul_rn(v[0], v[0]);
+  nn = __fadd_rn(nn, __fmul_rn(v[1], v[1]));
+  nn = __fadd_rn(nn, __fmul_rn(v[2], v[2]));
+  out[(long long)b * N + n] = make_float4(v[0], v[1], v[2], nn);
+}
+
+// feature path: point-major normalised copy (B,N,Cp) (channels >= C zero) + squared norms (B,N).
+// 32x32 smem transpose so both the channel-major read and the point-major write coalesce.
+__global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restrict__ x, long long sb, long long sn,
+                                                            long long sc, int N, int C, int Cp,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ stdv, float* __restrict__ out,
+                                                            float* __restrict__ norms) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.y, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float sigma = cloud_sigma(stdv + b * C, C);
+  float nn = 0.f;
+  for (int c0 = 0; c0 < Cp; c0 += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int c = c0 + ty + 8 * r, n = n0 + tx;
+      float v = 0.f;
+      if (c < C && n < N) v = __fdiv_rn(__fsub_rn(x[b * sb + n * sn + c * sc], mean[b * C + c]), sigma);
+      tile[ty + 8 * r][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int n = n0 + ty + 8 * r, c = c0 + tx;
+      if (n < N && c < Cp) out[((long long)b * N + n) * Cp + c] = tile[tx][ty + 8 * r];
+    }
+    if (ty == 0) {
+      int cmax = min(32, Cp - c0);
+      for (int c = 0; c < cmax; ++c) nn = __fadd_rn(nn, __fmul_rn(tile[c][tx], tile[c][tx]));
+    }
+    __syncthreads();
+  }
+  if (ty == 0 && n0 + tx < N) norms[(long long)b * N + n0 + tx] = nn;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: xyz kNN.  One warp per query (QW queries per warp in flight), lanes across candidates
+// staged in shared memory; the running k-set lives one entry per lane (LaneTopK).
+// Squared distance follows the 5-term GEMM row of at::_euclidean_dist in k order:
+//   ((( (-2x)x' + (-2y)y' ) + (-2z)z' ) + |q|^2 ) + |p|^2 , clamp >= 0
+// which reproduces torch.cdist on CPU bit for bit (probed).
+// ------------------------------------------------------------------------------------------
+constexpr int kXyzChunk = 2048;
+constexpr int kXyzQW = 4;
+
+template <class I>
+__global__ void __launch_bounds__(256) knn_xyz_kernel(const float4* __restrict__ qp, const float4* __restrict__ rp,
+                                                      int Nq, int Nr, int k, I* __restrict__ idx_out,
+                                                      float* __restrict__ dist_out) {
+  __shared__ float4 cand[kXyzChunk];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
+  const int qbase = (blockIdx.x * 8 + warp) * kXyzQW;
+  float ax[kXyzQW], ay[kXyzQW], az[kXyzQW], aw[kXyzQW];
+  LaneTopK t[kXyzQW];
+#pragma unroll
+  for (int i = 0; i < kXyzQW; ++i) {
+    float4 q = qp[(long long)b * Nq + min(qbase + i, Nq - 1)];
+    ax[i] = -2.f * q.x, ay[i] = -2.f * q.y, az[i] = -2.f * q.z, aw[i] = q.w;
+    t[i].init(lane, k);
+  }
+  for (int c0 = 0; c0 < Nr; c0 += kXyzChunk) {
+    const int n = min(kXyzChunk, Nr - c0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) cand[j] = rp[(long long)b * Nr + c0 + j];
+    __syncthreads();
+    if (qbase >= Nq) continue;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      const bool valid = j < n;
+      const float4 p = cand[valid ? j : 0];
+#pragma unroll
+      for (int i = 0; i < kXyzQW; ++i) {
+        float acc = __fmul_rn(ax[i], p.x);
+        acc = __fmaf_rn(ay[i], p.y, acc);
+        acc = __fmaf_rn(az[i], p.z, acc);
+        acc = __fadd_rn(acc, aw[i]);
+        acc = __fadd_rn(acc, p.w);
+        t[i].offer(dist_bits(acc), c0 + j, valid);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kXyzQW; ++i) {
+    const int q = qbase + i;
+    if (q >= Nq) break;
+    const int r = t[i].rank();
+    if (t[i].active) {
+      long long o = ((long long)b * Nq + q) * k + r;
+      idx_out[o] = (I)t[i].i;
+      if (dist_out) dist_out[o] = -sqrtf(__uint_as_float(t[i].d));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 (exact fp32 form): feature-space kNN.  FFMA dot tiles + per-row k-selection epilogue.
+//   d2 = fma(-2, <a,b>, |a|^2 + |b|^2), clamp >= 0.
+// ------------------------------------------------------------------------------------------
+template <class Cfg>
+struct KnnEpilogue {
+  unsigned* listd;      // smem [TQ][32]
+  int* listi;           // smem [TQ][32]
+  const float* qq;      // smem [TQ]
+  const float* bnorm;   // global, this cloud's candidate norms
+  int q0, Nq, Nr, k;
+
+  __device__ __forceinline__ void tile(const float* S, int ldS, int n0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float bb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int j = n0 + lane + 32 * u;
+      bb[u] = j < Nr ? bnorm[j] : 0.f;
+    }
+    for (int rr = 0; rr < Cfg::RPW; ++rr) {
+      const int row = warp * Cfg::RPW + rr;
+      if (q0 + row >= Nq) break;
+      LaneTopK t;
+      t.active = lane < k;
+      t.d = listd[row * 32 + lane];
+      t.i = listi[row * 32 + lane];
+      t.refresh();
+      const float aa = qq[row];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = n0 + lane + 32 * u;
+        const float dot = S[row * ldS + lane + 32 * u];
+        const float d2 = __fmaf_rn(-2.f, dot, __fadd_rn(aa, bb[u]));
+        t.offer(dist_bits(d2), j, j < Nr);
+      }
+      listd[row * 32 + lane] = t.d;
+      listi[row * 32 + lane] = t.i;
+    }
+  }
+};
+
+template <class Cfg, class I>
+__global__ void __launch_bounds__(256, Cfg::MQ == 4 ? 2 : 1)
+    knn_feat_kernel(const float* __restrict__ an, const float* __restrict__ anorm, const float* __restrict__ bn,
+                    const float* __restrict__ bnorm, int Nq, int Nr, int C, int Cp, int k, I* __restrict__ idx_out,
+                    float* __restrict__ dist_out) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.y, q0 = blockIdx.x * Cfg::TQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tail = smem + Cfg::smem_floats(Cp);
+  unsigned* listd = reinterpret_cast<unsigned*>(tail);
+  int* listi = reinterpret_cast<int*>(tail + Cfg::TQ * 32);
+  float* qq = tail + 2 * Cfg::TQ * 32;
+  for (int r = warp; r < Cfg::TQ; r += 8) {
+    LaneTopK t;
+    t.init(lane, k);
+    listd[r * 32 + lane] = t.d;
+    listi[r * 32 + lane] = t.i;
+  }
+  for (int r = threadIdx.x; r < Cfg::TQ; r += blockDim.x) qq[r] = (q0 + r) < Nq ? anorm[(long long)b * Nq + q0 + r] : 0.f;
+  __syncthreads();
+  KnnEpilogue<Cfg> epi{listd, listi, qq, bnorm + (long long)b * Nr, q0, Nq, Nr, k};
+  dot_tiles<Cfg>(an + (long long)b * Nq * Cp, Cp, q0, Nq, bn + (long long)b * Nr * Cp, Cp, Nr, Cp, Cp, smem, epi);
+  __syncthreads();
+  for (int rr = 0; rr < Cfg::RPW; ++rr) {
+    const int row = warp * Cfg::RPW + rr, q = q0 + row;
+    if (q >= Nq) break;
+    LaneTopK t;
+    t.active = lane < k;
+    t.d = listd[row * 32 + lane];
+    t.i = listi[row * 32 + lane];
+    const int r = t.rank();
+    if (t.active) {
+      long long o = ((long long)b * Nq + q) * k + r;
+      idx_out[o] = (I)t.i;
+      if (dist_out) dist_out[o] = -sqrtf(__uint_as_float(t.d));
+    }
+  }
+}
+
+template <class Cfg>
+static size_t knn_feat_smem(int Cp) {
+  return (Cfg::smem_floats(Cp) + 2 * Cfg::TQ * 32 + Cfg::TQ) * sizeof(float);
+}
+
+template <class Cfg, class I>
+static int launch_knn_feat(const float* an, const float* anorm, const float* bn, const float* bnorm, int B, int Nq,
+                           int Nr, int C, int Cp, int k, I* idx, float* dist, cudaStream_t st) {
+  size_t smem = knn_feat_smem<Cfg>(Cp);
+  auto kern = knn_feat_kernel<Cfg, I>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("knn_feat smem attribute");
+  dim3 grid(ceil_div(Nq, Cfg::TQ), B);
+  kern<<<grid, 256, smem, st>>>(an, anorm, bn, bnorm, Nq, Nr, C, Cp, k, idx, dist);
+  SAMBLE_LAUNCHED("knn_feat_kernel");
+  return SAMBLE_OK;
+}
+
+// shared with upsample.cu
+int launch_knn_stats(const float* a, long long sb, long long sn, long long sc, int B, int N, int C, float* mean,
+                     float* stdv, cudaStream_t st) {
+  knn_stats_kernel<<<dim3(ceil_div(C, 8), B), 256, 0, st>>>(a, sb, sn, sc, N, C, mean, stdv);
+  SAMBLE_LAUNCHED("knn_stats_kernel");
+  return SAMBLE_OK;
+}
+int launch_knn_prep_xyz(const float* x, long long sb, long long sn, long long sc, int B, int N, int C,
+                        const float* mean, const float* stdv, float4* out, cudaStream_t st) {
+  knn_prep_xyz_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(x, sb, sn, sc, N, C, mean, stdv, out);
+  SAMBLE_LAUNCHED("knn_prep_xyz_kernel");
+  return SAMBLE_OK;
+}
+
+struct KnnPlan {
+  int Cp;
+  bool xyz;
+  size_t bytes;
+};
+static KnnPlan knn_plan(int B, int Nq, int Nr, int C) {
+  KnnPlan p;
+  p.xyz = C <= 3;
+  p.Cp = p.xyz ? 4 : (int)align_up(C, 16);
+  size_t per_pt = p.xyz ? sizeof(float4) : (size_t)(p.Cp + 1) * sizeof(float);
+  p.bytes = 2 * align_up((size_t)B * C * sizeof(float), 256) + align_up((size_t)B * Nq * per_pt, 256) +
+            align_up((size_t)B * Nr * per_pt, 256) + 4 * 256;
+  return p;
+}
+
+template <class I>
+static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_sc, const float* b, long long b_sb,
+                    long long b_sn, long long b_sc, int B, int Nq, int Nr, int C, int k, I* idx_out, float* dist_out,
+                    void* ws, size_t ws_bytes, cudaStream_t st) {
+  KnnPlan plan = knn_plan(B, Nq, Nr, C);
+  SAMBLE_REQUIRE(ws_bytes >= plan.bytes, "samble_knn: workspace %zu < %zu bytes", ws_bytes, plan.bytes);
+  const bool self = (a == b) && a_sb == b_sb && a_sn == b_sn && a_sc == b_sc && Nq == Nr;
+  Workspace w(ws, ws_bytes);
+  float* mean = w.take<float>((size_t)B * C);
+  float* stdv = w.take<float>((size_t)B * C);
+  if (int e = launch_knn_stats(a, a_sb, a_sn, a_sc, B, Nq, C, mean, stdv, st)) return e;
+  if (plan.xyz) {
+    float4* qa = w.take<float4>((size_t)B * Nq);
+    float4* qb = self ? qa : w.take<float4>((size_t)B * Nr);
+    if (int e = launch_knn_prep_xyz(a, a_sb, a_sn, a_sc, B, Nq, C, mean, stdv, qa, st)) return e;
+    if (!self)
+      if (int e = launch_knn_prep_xyz(b, b_sb, b_sn, b_sc, B, Nr, C, mean, stdv, qb, st)) return e;
+    dim3 grid(ceil_div(Nq, 8 * kXyzQW), B);
+    knn_xyz_kernel<I><<<grid, 256, 0, st>>>(qa, qb, Nq, Nr, k, idx_out, dist_out);
+    SAMBLE_LAUNCHED("knn_xyz_kernel");
+    return SAMBLE_OK;
+  }
+  const int Cp = plan.Cp;
+  float* an = w.take<float>((size_t)B * Nq * Cp);
+  float* anorm = w.take<float>((size_t)B * Nq);
+  float* bn = self ? an : w.take<float>((size_t)B * Nr * Cp);
+  float* bnorm = self ? anorm : w.take<float>((size_t)B * Nr);
+  knn_prep_feat_kernel<<<dim3(ceil_div(Nq, 32), B), 256, 0, st>>>(a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv, an, anorm);
+  SAMBLE_LAUNCHED("knn_prep_feat_kernel");
+  if (!self) {
+    knn_prep_feat_kernel<<<dim3(ceil_div(Nr, 32), B), 256, 0, st>>>(b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn, bnorm);
+    SAMBLE_LAUNCHED("knn_prep_feat_kernel");
+  }
+  // 128-row CTAs when they still give every SM at least ~2 CTAs of work, else 64-row CTAs
+  const bool big = (long long)ceil_div(Nq, 128) * B >= 2 * 148 && knn_feat_smem<DotTileCfg<8>>(Cp) <= 200 * 1024;
+  if (big) return launch_knn_feat<DotTileCfg<8>, I>(an, anorm, bn, bnorm, B, Nq, Nr, C, Cp, k, idx_out, dist_out, st);
+  return launch_knn_feat<DotTileCfg<4>, I>(an, anorm, bn, bnorm, B, Nq, Nr, C, Cp, k, idx_out, dist_out, st);
+}
+
+}  // namespace samble
+
+using namespace samble;
+
+extern "C" size_t samble_knn_workspace_bytes(int B, int Nq, int Nr, int C) {
+  if (B <= 0 || Nq <= 0 || Nr <= 0 || C <= 0) return 0;
+  return knn_plan(B, Nq, Nr, C).bytes;
+}
+
+extern "C" int samble_knn(const float* a, long long a_sb, long long a_sn, long long a_sc, const float* b,
+                          long long b_sb, long long b_sn, long long b_sc, int B, int Nq, int Nr, int C, int k,
+                          void* idx_out, int idx_bits, float* dist_out, void* ws, size_t ws_bytes,
+                          samble_stream_t stream) {
+  SAMBLE_REQUIRE(a && b && idx_out && ws, "samble_knn: null pointer");
+  SAMBLE_REQUIRE(B > 0 && Nq > 0 && Nr > 0 && C > 0, "samble_knn: empty shape B=%d Nq=%d Nr=%d C=%d", B, Nq, Nr, C);
+  SAMBLE_REQUIRE(C <= 512, "samble_knn: C=%d > 512", C);
+  SAMBLE_REQUIRE(k >= 1 && k <= 32, "samble_knn: k=%d outside [1,32]", k);
+  SAMBLE_REQUIRE(k <= Nr, "samble_knn: k=%d > number of candidates %d", k, Nr);
+  SAMBLE_REQUIRE(idx_bits == 32 || idx_bits == 64, "samble_knn: idx_bits must be 32 or 64");
+  SAMBLE_REQUIRE(B <= 65535, "samble_knn: B=%d > 65535", B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (idx_bits == 64)
+    return knn_impl<long long>(a, a_sb, a_sn, a_sc, b, b_sb, b_sn, b_sc, B, Nq, Nr, C, k, (long long*)idx_out,
+                               dist_out, ws, ws_bytes, st);
+  return knn_impl<int>(a, a_sb, a_sn, a_sc, b, b_sb, b_sn, b_sc, B, Nq, Nr, C, k, (int*)idx_out, dist_out, ws,
+                       ws_bytes, st);
+}

@@ -1,0 +1,114 @@
+// UpSampleInterpolation core (reference models/upsample.py:194-212 + utils/ops.py:68-80):
+// 3-NN of every "up" point among the selected points (xyz, normalised by the up cloud's statistics),
+// inverse-distance weights, weighted sum of the selected features -- one fused kernel, no (B,N,M)
+// distance matrix and no (B,C,N,3) gathered tensor.  HBM-bound: reads C*M + 3(N+M), writes C*N floats.
+#include "common.cuh"
+
+namespace samble {
+
+int launch_knn_stats(const float* a, long long sb, long long sn, long long sc, int B, int N, int C, float* mean,
+                     float* stdv, cudaStream_t st);
+int launch_knn_prep_xyz(const float* x, long long sb, long long sn, long long sc, int B, int N, int C,
+                        const float* mean, const float* stdv, float4* out, cudaStream_t st);
+
+constexpr int kUpChunk = 2048;
+
+__global__ void __launch_bounds__(128) interpolate3_kernel(const float4* __restrict__ up, const float4* __restrict__ sel,
+                                                           const float* __restrict__ feat, int N, int M, int C,
+                                                           float* __restrict__ out, long long* __restrict__ idx_out,
+                                                           float* __restrict__ dist_out) {
+  __shared__ float4 cand[kUpChunk];
+  const int b = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = n < N;
+  const float4 q = up[(long long)b * N + (live ? n : N - 1)];
+  const float ax = -2.f * q.x, ay = -2.f * q.y, az = -2.f * q.z;
+  float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY;
+  int i0 = 0, i1 = 0, i2 = 0;
+  for (int c0 = 0; c0 < M; c0 += kUpChunk) {
+    const int cn = min(kUpChunk, M - c0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cn; j += blockDim.x) cand[j] = sel[(long long)b * M + c0 + j];
+    __syncthreads();
+    for (int j = 0; j < cn; ++j) {
+      const float4 p = cand[j];
+      // same 5-term row as the xyz kNN (knn.cu), ascending j so ties keep the lower index
+      float acc = __fmul_rn(ax, p.x);
+      acc = __fmaf_rn(ay, p.y, acc);
+      acc = __fmaf_rn(az, p.z, acc);
+      acc = __fadd_rn(acc, q.w);
+      acc = __fadd_rn(acc, p.w);
+      const float d = acc > 0.f ? acc : 0.f;
+      if (d < d2) {
+        if (d < d1) {
+          d2 = d1, i2 = i1;
+          if (d < d0) d1 = d0, i1 = i0, d0 = d, i0 = c0 + j;
+          else d1 = d, i1 = c0 + j;
+        } else {
+          d2 = d, i2 = c0 + j;
+        }
+      }
+    }
+  }
+  if (!live) return;
+  const float e0 = sqrtf(d0), e1 = sqrtf(d1), e2 = sqrtf(d2);
+  // weights = 1/(d+1e-8), normalised by their left-to-right sum (upsample.py:206-209)
+  float w0 = __fdiv_rn(1.0f, __fadd_rn(e0, 1e-8f));
+  float w1 = __fdiv_rn(1.0f, __fadd_rn(e1, 1e-8f));
+  float w2 = __fdiv_rn(1.0f, __fadd_rn(e2, 1e-8f));
+  const float ws = __fadd_rn(__fadd_rn(w0, w1), w2);
+  w0 = __fdiv_rn(w0, ws), w1 = __fdiv_rn(w1, ws), w2 = __fdiv_rn(w2, ws);
+  if (idx_out) {
+    long long* o = idx_out + ((long long)b * N + n) * 3;
+    o[0] = i0, o[1] = i1, o[2] = i2;
+  }
+  if (dist_out) {
+    float* o = dist_out + ((long long)b * N + n) * 3;
+    o[0] = e0, o[1] = e1, o[2] = e2;
+  }
+  const float* f = feat + (long long)b * C * M;
+  float* y = out + (long long)b * C * N + n;
+  for (int c = 0; c < C; ++c) {
+    const float* fr = f + (long long)c * M;
+    // sum over the 3 neighbours of (feature * weight), products rounded separately (upsample.py:210-212)
+    float v = __fmul_rn(__ldg(fr + i0), w0);
+    v = __fadd_rn(v, __fmul_rn(__ldg(fr + i1), w1));
+    v = __fadd_rn(v, __fmul_rn(__ldg(fr + i2), w2));
+    y[(long long)c * N] = v;
+  }
+}
+
+static size_t interp_bytes(int B, int N, int M) {
+  return 2 * align_up((size_t)B * 3 * sizeof(float), 256) + align_up((size_t)B * N * sizeof(float4), 256) +
+         align_up((size_t)B * M * sizeof(float4), 256) + 1024;
+}
+
+}  // namespace samble
+
+using namespace samble;
+
+extern "C" size_t samble_interpolate3_workspace_bytes(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return 0;
+  return interp_bytes(B, N, M);
+}
+
+extern "C" int samble_interpolate3(const float* xyz_up, const float* xyz_sel, const float* feat, int B, int N, int M,
+                                   int C, float* out, long long* idx_out, float* dist_out, void* ws, size_t ws_bytes,
+                                   samble_stream_t stream) {
+  SAMBLE_REQUIRE(xyz_up && xyz_sel && feat && out && ws, "samble_interpolate3: null pointer");
+  SAMBLE_REQUIRE(B > 0 && N > 0 && C > 0 && B <= 65535, "samble_interpolate3: bad shape");
+  SAMBLE_REQUIRE(M >= 3, "samble_interpolate3: need at least 3 selected points, got %d", M);
+  SAMBLE_REQUIRE(ws_bytes >= interp_bytes(B, N, M), "samble_interpolate3: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w(ws, ws_bytes);
+  float* mean = w.take<float>((size_t)B * 3);
+  float* stdv = w.take<float>((size_t)B * 3);
+  float4* up = w.take<float4>((size_t)B * N);
+  float4* sel = w.take<float4>((size_t)B * M);
+  // channel-major (B,3,N): strides (3N, 1, N)
+  if (int e = launch_knn_stats(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, st)) return e;
+  if (int e = launch_knn_prep_xyz(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, up, st)) return e;
+  if (int e = launch_knn_prep_xyz(xyz_sel, 3LL * M, 1, M, B, M, 3, mean, stdv, sel, st)) return e;
+  interpolate3_kernel<<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(up, sel, feat, N, M, C, out, idx_out, dist_out);
+  SAMBLE_LAUNCHED("interpolate3_kernel");
+  return SAMBLE_OK;
+}

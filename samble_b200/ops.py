@@ -1,0 +1,346 @@
+"""Drop-in for the reference's `utils/ops.py` hot-path functions, backed by the sm_100a kernels.
+
+Same names, argument meaning, return layouts and error behaviour as reference
+utils/ops.py:5-145, 174-236, 385-505, so the reference's own models can use this
+module in place of `utils.ops` (see samble_b200.patch).  Every function runs through
+the C ABI (include/samble_b200.h); nothing falls back to PyTorch or the CPU.
+
+Functions with a leading underscore-free "fast" name (`knn_indices`, `n2p_attend`,
+`ds_*`, `interpolate3`) are the fused entry points our own blocks use; they have no
+reference counterpart because the reference materialises the intermediate instead.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+Tensor = torch.Tensor
+
+_GROUP_TYPES = {"neighbor": 0, "diff": 1, "center_neighbor": 2, "center_diff": 3}
+
+
+def _f32(t: Tensor, name: str) -> Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+def _idx_bits(idx: Tensor) -> int:
+    if idx.dtype == torch.int64:
+        return 64
+    if idx.dtype == torch.int32:
+        return 32
+    raise TypeError(f"index tensor must be int32 or int64, got {idx.dtype}")
+
+
+# ------------------------------------------------------------------ kNN
+
+
+def _knn_strided(a: Tensor, b: Tensor, k: int, layout: str, want_dist: bool, idx_dtype=torch.int64):
+    """a, b: 3-D fp32 CUDA tensors in 'bnc' (B,N,C) or 'bcn' (B,C,N) layout, any strides."""
+    dev = L.need_cuda(a, b)
+    L.no_grad_check(a, b)
+    _f32(a, "a"), _f32(b, "b")
+    if layout == "bnc":
+        (B, Nq, Cc), (Bb, Nr, Cb) = a.shape, b.shape
+        sa, sb_ = (a.stride(0), a.stride(1), a.stride(2)), (b.stride(0), b.stride(1), b.stride(2))
+    else:
+        (B, Cc, Nq), (Bb, Cb, Nr) = a.shape, b.shape
+        sa, sb_ = (a.stride(0), a.stride(2), a.stride(1)), (b.stride(0), b.stride(2), b.stride(1))
+    if B != Bb or Cc != Cb:
+        raise RuntimeError(f"knn: batch/channel mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+    if k > Nr:   # torch.topk's own complaint (utils/ops.py:43)
+        raise RuntimeError("selected index k out of range")
+    lib = L.lib()
+    idx = torch.empty(B, Nq, k, dtype=idx_dtype, device=dev)
+    dist = torch.empty(B, Nq, k, dtype=torch.float32, device=dev) if want_dist else None
+    nbytes = lib.samble_knn_workspace_bytes(B, Nq, Nr, Cc)
+    ws = L.workspace(nbytes, dev)
+    rc = lib.samble_knn(L.ptr(a), *sa, L.ptr(b), *sb_, B, Nq, Nr, Cc, k, L.ptr(idx), _idx_bits(idx), L.ptr(dist),
+                        L.ptr(ws), ws.numel(), L.stream())
+    L.check(rc, "samble_knn")
+    return dist, idx
+
+
+def knn(a: Tensor, b: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    """utils/ops.py:17-44.  a (B,N,C), b (B,M,C) -> (negative distance (B,N,k), idx (B,N,k) int64)."""
+    return _knn_strided(a, b, k, "bnc", True)
+
+
+def knn_indices(pcd: Tensor, K: int, idx_dtype=torch.int32) -> Tensor:
+    """Self-kNN of a channel-major cloud (B,C,N) -> idx (B,N,K); the internal fast path
+    (int32 indices, no distance output, no permute copy)."""
+    return _knn_strided(pcd, pcd, K, "bcn", False, idx_dtype)[1]
+
+
+# ------------------------------------------------------------------ gathers
+
+
+def index_points(points: Tensor, idx: Tensor) -> Tensor:
+    """utils/ops.py:5-14.  points (B,N,C), idx (B,M,K) -> (B,M,K,C)."""
+    dev = L.need_cuda(points, idx)
+    L.no_grad_check(points)
+    points = _f32(points, "points").contiguous()
+    idx = idx.contiguous()
+    B, N, Cc = points.shape
+    R = idx[0].numel()
+    out = torch.empty(*idx.shape, Cc, dtype=torch.float32, device=dev)
+    L.check(L.lib().samble_index_points(L.ptr(points), L.ptr(idx), _idx_bits(idx), B, N, Cc, R, L.ptr(out), L.stream()),
+            "samble_index_points")
+    return out
+
+
+def _group_from_idx(pcd: Tensor, idx: Tensor, group_type: str) -> Tensor:
+    B, Cc, N = pcd.shape
+    K = idx.shape[-1]
+    t = _GROUP_TYPES[group_type]
+    if t < 2:
+        buf = torch.empty(B, N, K, Cc, dtype=torch.float32, device=pcd.device)
+    else:
+        buf = torch.empty(B, 2 * Cc, N, K, dtype=torch.float32, device=pcd.device)
+    L.check(L.lib().samble_group(L.ptr(pcd), L.ptr(idx), _idx_bits(idx), B, Cc, N, K, t, L.ptr(buf), L.stream()),
+            "samble_group")
+    # neighbor/diff: the reference hands out this exact memory as a permuted view (utils/ops.py:57,60)
+    return buf.permute(0, 3, 1, 2) if t < 2 else buf
+
+
+def select_neighbors(pcd: Tensor, K: int, neighbor_type: str, normal_channel: bool = False):
+    """utils/ops.py:47-65.  pcd (B,C,N) -> ((B,C,N,K) view of (B,N,K,C), idx (B,N,K) int64)."""
+    if neighbor_type not in ("neighbor", "diff"):
+        raise ValueError(f'neighbor_type should be "neighbor" or "diff", but got {neighbor_type}')
+    L.need_cuda(pcd)
+    L.no_grad_check(pcd)
+    pcd = _f32(pcd, "pcd").contiguous()
+    key = pcd[:, :3, :] if (normal_channel and pcd.shape[1] == 6) else pcd
+    _, idx = _knn_strided(key, key, K, "bcn", False)
+    return _group_from_idx(pcd, idx, neighbor_type), idx
+
+
+def group(pcd: Tensor, K: int, group_type: str, normal_channel: bool = False):
+    """utils/ops.py:83-112."""
+    if group_type not in _GROUP_TYPES:
+        raise ValueError(
+            f"group_type should be neighbor, diff, center_neighbor or center_diff, but got {group_type}")
+    L.need_cuda(pcd)
+    L.no_grad_check(pcd)
+    pcd = _f32(pcd, "pcd").contiguous()
+    key = pcd[:, :3, :] if (normal_channel and pcd.shape[1] == 6) else pcd
+    _, idx = _knn_strided(key, key, K, "bcn", False)
+    return _group_from_idx(pcd, idx, group_type), idx
+
+
+def select_neighbors_interpolate(unknown: Tensor, known: Tensor, known_feature: Tensor, K: int = 3):
+    """utils/ops.py:68-80.  -> (neighbors (B,C,N,K) view, idx (B,N,K), distance (B,N,K) >= 0)."""
+    L.need_cuda(unknown, known, known_feature)
+    neg, idx = _knn_strided(unknown, known, K, "bcn", True)
+    nbr = index_points(known_feature.permute(0, 2, 1), idx)
+    return nbr.permute(0, 3, 1, 2), idx, -1 * neg
+
+
+def neighbor_mask(pcd: Tensor, K: int) -> Tensor:
+    """utils/ops.py:125-133.  dense 0/1 (B,N,N) float32."""
+    dev = L.need_cuda(pcd)
+    L.no_grad_check(pcd)
+    pcd = _f32(pcd, "pcd")
+    idx = knn_indices(pcd, K)
+    B, N, _ = idx.shape
+    out = torch.empty(B, N, N, dtype=torch.float32, device=dev)
+    L.check(L.lib().samble_neighbor_mask(L.ptr(idx), 32, B, N, K, L.ptr(out), L.stream()), "samble_neighbor_mask")
+    return out
+
+
+def gather_by_idx(pcd: Tensor, idx: Tensor) -> Tensor:
+    """utils/ops.py:136-145.  pcd (B,C,N), idx (B,1,M) -> (B,C,M)."""
+    dev = L.need_cuda(pcd, idx)
+    L.no_grad_check(pcd)
+    pcd = _f32(pcd, "pcd").contiguous()
+    B, Cc, N = pcd.shape
+    if idx.dim() != 3 or idx.shape[1] != 1:
+        raise RuntimeError(f"gather_by_idx expects idx of shape (B,1,M), got {tuple(idx.shape)}")
+    idx = idx.contiguous()
+    M = idx.shape[2]
+    out = torch.empty(B, Cc, M, dtype=torch.float32, device=dev)
+    L.check(L.lib().samble_gather_by_idx(L.ptr(pcd), L.ptr(idx), _idx_bits(idx), B, Cc, N, M, L.ptr(out), L.stream()),
+            "samble_gather_by_idx")
+    return out
+
+
+# ------------------------------------------------------------------ fused block cores
+
+
+def n2p_attend(qkv: Tensor, idx: Tensor, heads: int) -> Tensor:
+    """qkv (B,N,3C) point-major [q|k|v] projections of the points; idx (B,N,K) -> (B,N,C).
+    Core of models/attention.py:165-185,207-250 with the k/v convolutions hoisted (attention.cu)."""
+    dev = L.need_cuda(qkv, idx)
+    B, N, C3 = qkv.shape
+    Cc = C3 // 3
+    K = idx.shape[-1]
+    out = torch.empty(B, N, Cc, dtype=torch.float32, device=dev)
+    q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+    L.check(L.lib().samble_n2p_attend(L.ptr(q), L.ptr(k), L.ptr(v), C3, L.ptr(idx), _idx_bits(idx), B, N, Cc, K, heads,
+                                      L.ptr(out), Cc, L.stream()), "samble_n2p_attend")
+    return out
+
+
+def ds_row_stats(q: Tensor, k: Tensor, k_tok: Tensor):
+    """q,k: (B,N,D) point-major views (last stride 1, row stride ld); k_tok (nb,D).
+    -> rowmax (B,N), rowsum (B,N), token_logits (B,N,nb).  models/downsample.py:139-153."""
+    dev = L.need_cuda(q, k, k_tok)
+    B, N, D = q.shape
+    nb = k_tok.shape[0]
+    k_tok = k_tok.contiguous()
+    rowmax = torch.empty(B, N, dtype=torch.float32, device=dev)
+    rowsum = torch.empty(B, N, dtype=torch.float32, device=dev)
+    tok = torch.empty(B, N, nb, dtype=torch.float32, device=dev)
+    L.check(L.lib().samble_ds_row_stats(L.ptr(q), q.stride(1), L.ptr(k), k.stride(1), L.ptr(k_tok), B, N, D, nb,
+                                        L.ptr(rowmax), L.ptr(rowsum), L.ptr(tok), L.stream()), "samble_ds_row_stats")
+    return rowmax, rowsum, tok
+
+
+def ds_edge_score(q: Tensor, k: Tensor, rowmax: Tensor, rowsum: Tensor, idx: Tensor) -> Tensor:
+    """sparse_col_sqr point score (B,N) from the kNN edges only.  models/downsample.py:300-344."""
+    dev = L.need_cuda(q, k, idx)
+    B, N, D = q.shape
+    K = idx.shape[-1]
+    lib = L.lib()
+    score = torch.empty(B, N, dtype=torch.float32, device=dev)
+    ws = L.workspace(lib.samble_ds_edge_score_workspace_bytes(B, N), dev)
+    L.check(lib.samble_ds_edge_score(L.ptr(q), q.stride(1), L.ptr(k), k.stride(1), L.ptr(rowmax), L.ptr(rowsum),
+                                     L.ptr(idx), _idx_bits(idx), B, N, D, K, L.ptr(score), L.ptr(ws), ws.numel(),
+                                     L.stream()), "samble_ds_edge_score")
+    return score
+
+
+def zscore(score: Tensor) -> Tensor:
+    """(score - mean) / population std over the last dim (utils/ops.py:450-452)."""
+    L.need_cuda(score)
+    score = _f32(score, "score").contiguous()
+    N = score.shape[-1]
+    z = torch.empty_like(score)
+    L.check(L.lib().samble_zscore(L.ptr(score), score.numel() // N, N, L.ptr(z), L.stream()), "samble_zscore")
+    return z
+
+
+def ds_sample(score: Tensor, token_logits: Tensor, cuts: Tensor, M: int, want_z: bool = False):
+    """Fused bin stage (models/downsample.py:205-240): score (B,N), token_logits (B,N,nb), cuts (nb-1,)
+    descending thresholds on the z-score -> dict(idx (B,M) int64, bin_id (B,N) uint8, counts, k, w_raw, z)."""
+    dev = L.need_cuda(score, token_logits, cuts)
+    B, N = score.shape
+    nb = token_logits.shape[-1]
+    cuts = _f32(cuts, "cuts").contiguous()
+    if cuts.numel() != nb - 1:
+        raise ValueError(f"ds_sample: expected {nb - 1} cuts, got {cuts.numel()}")
+    out = dict(idx=torch.empty(B, M, dtype=torch.int64, device=dev),
+               bin_id=torch.empty(B, N, dtype=torch.uint8, device=dev),
+               counts=torch.empty(B, nb, dtype=torch.int32, device=dev),
+               k=torch.empty(B, nb, dtype=torch.int32, device=dev),
+               w_raw=torch.empty(B, nb, dtype=torch.float32, device=dev),
+               z=torch.empty(B, N, dtype=torch.float32, device=dev) if want_z else None)
+    L.check(L.lib().samble_ds_sample(L.ptr(score), L.ptr(token_logits), L.ptr(cuts), B, N, nb, M, L.ptr(out["idx"]),
+                                     L.ptr(out["bin_id"]), L.ptr(out["counts"]), L.ptr(out["k"]), L.ptr(out["w_raw"]),
+                                     L.ptr(out["z"]), L.stream()), "samble_ds_sample")
+    return out
+
+
+def interpolate3(xyz_up: Tensor, xyz_sel: Tensor, feat: Tensor, want_idx: bool = False):
+    """Fused 3-NN inverse-distance interpolation (models/upsample.py:194-212): xyz_up (B,3,N),
+    xyz_sel (B,3,M), feat (B,C,M) -> (B,C,N) [, idx (B,N,3) int64, dist (B,N,3)]."""
+    dev = L.need_cuda(xyz_up, xyz_sel, feat)
+    L.no_grad_check(xyz_up, xyz_sel, feat)
+    xyz_up, xyz_sel, feat = (_f32(t, "input").contiguous() for t in (xyz_up, xyz_sel, feat))
+    B, three, N = xyz_up.shape
+    M, Cc = xyz_sel.shape[2], feat.shape[1]
+    if three != 3 or xyz_sel.shape[1] != 3:
+        raise ValueError("interpolate3: xyz tensors must be (B,3,N)")
+    lib = L.lib()
+    out = torch.empty(B, Cc, N, dtype=torch.float32, device=dev)
+    idx = torch.empty(B, N, 3, dtype=torch.int64, device=dev) if want_idx else None
+    dist = torch.empty(B, N, 3, dtype=torch.float32, device=dev) if want_idx else None
+    ws = L.workspace(lib.samble_interpolate3_workspace_bytes(B, N, M), dev)
+    L.check(lib.samble_interpolate3(L.ptr(xyz_up), L.ptr(xyz_sel), L.ptr(feat), B, N, M, Cc, L.ptr(out), L.ptr(idx),
+                                    L.ptr(dist), L.ptr(ws), ws.numel(), L.stream()), "samble_interpolate3")
+    return (out, idx, dist) if want_idx else out
+
+
+# ------------------------------------------------------------------ bins (reference signatures)
+
+
+def update_sampling_score_bin_boundary(old_bin_boundaries, attention_point_score: Tensor, num_bins: int,
+                                       momentum_update_factor: float):
+    """utils/ops.py:174-236.  Batch quantiles of the z-scored point score -> [upper, lower] pair,
+    rank-averaged when a process group exists (:191-199) and EMA-blended into the old pair.
+    A training-time, latency-bound step (nb-1 floats): one device sort + NCCL all_reduce."""
+    z = attention_point_score
+    n = z.nelement()
+    pos = (torch.arange(1, num_bins) / num_bins * n).int().long().to(z.device)
+    ranked, _ = torch.sort(z.flatten(), dim=0, descending=True)
+    cut = ranked[pos]
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.all_reduce(cut)
+        cut = cut / torch.distributed.get_world_size()
+    if old_bin_boundaries is not None:
+        upper, lower = old_bin_boundaries[0].detach(), old_bin_boundaries[1].detach()
+        cut = upper[0, 0, 0, 1:] * momentum_update_factor + (1 - momentum_update_factor) * cut
+        upper[0, 0, 0, 1:] = cut
+        lower[0, 0, 0, :-1] = cut
+        return [upper, lower]
+    inf = torch.full((1,), float("inf"), device=z.device)
+    return [torch.cat([inf, cut]).reshape(1, 1, 1, num_bins), torch.cat([cut, -inf]).reshape(1, 1, 1, num_bins)]
+
+
+def bin_partition(attention_point_score: Tensor, bin_boundaries, dynamic_boundaries_enable: bool,
+                  momentum_update_factor: float, num_bins: int):
+    """utils/ops.py:435-464.  score (B,H,N) -> ([upper, lower], mask (B,H,N,num_bins) bool)."""
+    dev = L.need_cuda(attention_point_score)
+    L.no_grad_check(attention_point_score)
+    B, H, N = attention_point_score.shape
+    if bin_boundaries is not None:
+        bin_boundaries = [t.to(dev) for t in bin_boundaries]
+    z = zscore(attention_point_score)
+    if dynamic_boundaries_enable:
+        bin_boundaries = update_sampling_score_bin_boundary(bin_boundaries, z.reshape(B, H, N, 1), num_bins,
+                                                            momentum_update_factor)
+    upper = bin_boundaries[0].reshape(-1).to(torch.float32).contiguous()
+    lower = bin_boundaries[1].reshape(-1).to(torch.float32).contiguous()
+    mask = torch.empty(B, H, N, num_bins, dtype=torch.uint8, device=dev)
+    L.check(L.lib().samble_bin_mask(L.ptr(z), L.ptr(upper), L.ptr(lower), B * H, N, num_bins, L.ptr(mask), L.stream()),
+            "samble_bin_mask")
+    return bin_boundaries, mask.view(torch.bool)
+
+
+def calculate_num_points_to_choose(bin_prob: Tensor, max_num_points: Tensor, total_points_to_choose: int) -> Tensor:
+    """utils/ops.py:385-432.  (B,nb) fp32, (B,nb) int64, int -> (B,nb) int32."""
+    dev = L.need_cuda(bin_prob, max_num_points)
+    B, nb = bin_prob.shape
+    bin_prob = _f32(bin_prob, "bin_prob").contiguous()
+    cnt = max_num_points.to(torch.int64).contiguous()
+    k = torch.empty(B, nb, dtype=torch.int32, device=dev)
+    L.check(L.lib().samble_num_points_to_choose(L.ptr(bin_prob), L.ptr(cnt), B, nb, int(total_points_to_choose), L.ptr(k),
+                                                L.stream()), "samble_num_points_to_choose")
+    return k
+
+
+def generating_downsampled_index(M: int, attention_point_score: Tensor, bin_points_mask: Tensor, bin_sample_mode: str,
+                                 boltzmann_t, k_point_to_choose: Tensor) -> Tensor:
+    """utils/ops.py:467-619.  'topk' (:476-505) is native; 'uniform'/'random' (:507-613) draw from
+    torch.multinomial in the reference and are SURVEY 8f item f3 (not built yet)."""
+    if bin_sample_mode in ("uniform", "random"):
+        raise NotImplementedError(f"bin_sample_mode '{bin_sample_mode}' is not implemented natively yet "
+                                  "(SURVEY 8f f3); use 'topk'")
+    if bin_sample_mode != "topk":
+        raise ValueError("Please check the setting of bin sample mode. It must be topk, multinomial or random!")
+    dev = L.need_cuda(attention_point_score, bin_points_mask, k_point_to_choose)
+    B, H, N, nb = bin_points_mask.shape
+    if H != 1:
+        raise ValueError("generating_downsampled_index: one attention head expected (reference: 'has to be 1 head')")
+    score = _f32(attention_point_score, "score").reshape(B, N).contiguous()
+    mask = bin_points_mask.reshape(B, N, nb).to(torch.uint8).contiguous()
+    k = k_point_to_choose.to(torch.int32).contiguous()
+    idx = torch.empty(B, 1, M, dtype=torch.int64, device=dev)
+    L.check(L.lib().samble_downsample_index_topk(L.ptr(score), L.ptr(mask), L.ptr(k), B, N, nb, M, L.ptr(idx), L.stream()),
+            "samble_downsample_index_topk")
+    return idx

@@ -99,7 +99,7 @@ def _block_sd():
     from samble_b200.models import ShapeNetModel
 
     cfg = seg_config(M=(G.BLOCK_N // 2, G.BLOCK_N // 4))
-    m = ShapeNetModel(cfg, native=False)
+    m = ShapeNetModel(cfg)
     return cfg, fill_state_dict_(m.state_dict(), seed=5, sharpen=4.0)
 
 
@@ -137,7 +137,7 @@ def test_models(which):
     c = G.MODEL_CASES[which]
     gold = np.load(os.path.join(GOLD, f"{which}_small.npz"))
     cfg = (seg_config if which == "seg" else cls_config)(M=c["M"])
-    m = (models.ShapeNetModel if which == "seg" else models.ModelNetModel)(cfg, native=False)
+    m = (models.ShapeNetModel if which == "seg" else models.ModelNetModel)(cfg)
     sd = fill_state_dict_(m.state_dict(), seed=c["wseed"], sharpen=4.0)
     x, cat = synthetic_clouds(c["B"], c["N"], c["xseed"])
     states = [O.DSState(True), O.DSState(True)]
