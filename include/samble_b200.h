@@ -48,6 +48,10 @@ const char* samble_last_error(void);
  * last reset (bench.py's gpu_launches claim is read from here). */
 long long samble_launch_count(void);
 void samble_reset_launch_count(void);
+/* optional per-kernel device timing: while enabled every launch is bracketed by CUDA events on its
+ * stream; samble_profile_report() waits for them and writes "kernel,launches,total_ms" lines. */
+void samble_profile_enable(int on);
+int samble_profile_report(char* buf, size_t cap);
 
 /* ---------------------------------------------------------------- kNN ----------
  * utils/ops.py:17-44  knn(a, b, k) -> (distance, idx).

@@ -26,6 +26,8 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_last_error": (C.c_char_p, ()),
     "samble_launch_count": (_ll, ()),
     "samble_reset_launch_count": (None, ()),
+    "samble_profile_enable": (None, (_i,)),
+    "samble_profile_report": (_i, (C.c_char_p, _sz)),
     "samble_knn_workspace_bytes": (_sz, (_i, _i, _i, _i)),
     "samble_knn": (_i, (_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _p, _i, _p, _p, _sz, _p)),
     "samble_index_points": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
@@ -123,3 +125,18 @@ def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+def profile(enable: bool) -> None:
+    lib().samble_profile_enable(1 if enable else 0)
+
+
+def profile_report() -> dict:
+    """{kernel: (launches, total_ms)} of the launches recorded since profiling was enabled."""
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().samble_profile_report(buf, len(buf)), "samble_profile_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.rsplit(",", 2)
+        out[name] = (int(n), float(ms))
+    return out

@@ -97,6 +97,7 @@ extern "C" int samble_n2p_attend(const float* q, const float* k, const float* v,
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(ceil_div(N, 8), B);
   const float sqrt_d = sqrtf((float)(C / heads));
+  SAMBLE_PRE(st);
   if (idx_bits == 64)
     n2p_attend_kernel<long long, 32><<<grid, 256, 0, st>>>(q, k, v, ld, (const long long*)idx, N, C, K, lph, 0.f, sqrt_d, out, ld_out);
   else

@@ -15,6 +15,8 @@ constexpr unsigned kFull = 0xffffffffu;
 void set_error(const char* fmt, ...);
 void count_launch();
 int check_launch(const char* what);   // cudaGetLastError -> SAMBLE_E_CUDA + message
+void prof_pre(cudaStream_t st);       // no-ops unless samble_profile_enable(1)
+void prof_post(const char* what);
 
 #define SAMBLE_REQUIRE(cond, ...)                    \
   do {                                               \
@@ -24,8 +26,11 @@ int check_launch(const char* what);   // cudaGetLastError -> SAMBLE_E_CUDA + mes
     }                                                \
   } while (0)
 
+#define SAMBLE_PRE(st) ::samble::prof_pre(st)
+
 #define SAMBLE_LAUNCHED(what)                        \
   do {                                               \
+    ::samble::prof_post(what);                       \
     ::samble::count_launch();                        \
     int _e = ::samble::check_launch(what);           \
     if (_e) return _e;                               \

@@ -190,6 +190,7 @@ extern "C" int samble_ds_row_stats(const float* q, long long ldq, const float* k
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("ds_row_stats smem attribute");
   const float scale = sqrtf((float)D);
+  SAMBLE_PRE((cudaStream_t)stream);
   kern<<<dim3(ceil_div(N, Cfg::TQ), B), 256, smem, (cudaStream_t)stream>>>(q, ldq, k, ldk, k_tok, N, D, nb, scale, rowmax,
                                                                           rowsum, token_logits);
   SAMBLE_LAUNCHED("ds_row_stats_kernel");
@@ -223,13 +224,16 @@ extern "C" int samble_ds_edge_score(const float* q, long long ldq, const float* 
   if (idx_bits == 64) {
     auto kern = ds_edge_partial_kernel<long long>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SAMBLE_PRE(st);
     kern<<<dim3(e.P, B), e.W * 32, smem, st>>>(q, ldq, k, ldk, rowmax, rowsum, (const long long*)idx, N, D, K, e.RW, scale, part, indeg);
   } else {
     auto kern = ds_edge_partial_kernel<int>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SAMBLE_PRE(st);
     kern<<<dim3(e.P, B), e.W * 32, smem, st>>>(q, ldq, k, ldk, rowmax, rowsum, (const int*)idx, N, D, K, e.RW, scale, part, indeg);
   }
   SAMBLE_LAUNCHED("ds_edge_partial_kernel");
+  SAMBLE_PRE(st);
   ds_edge_finalize_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(part, indeg, N, e.P, score);
   SAMBLE_LAUNCHED("ds_edge_finalize_kernel");
   return SAMBLE_OK;

@@ -108,6 +108,7 @@ static int group_impl(const float* pcd, const I* idx, int B, int C, int N, int K
   const long long rows = (long long)N * K;
   if (type == SAMBLE_GROUP_NEIGHBOR || type == SAMBLE_GROUP_DIFF) {
     dim3 grid(grid_for(rows, 8), B);
+    SAMBLE_PRE(st);
     if (type == SAMBLE_GROUP_DIFF)
       group_rows_kernel<I, true><<<grid, 256, 0, st>>>(pcd, idx, C, N, K, out);
     else
@@ -127,6 +128,7 @@ static int group_impl(const float* pcd, const I* idx, int B, int C, int N, int K
     cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
+  SAMBLE_PRE(st);
   if (type == SAMBLE_GROUP_CENTER_DIFF)
     kd<<<grid, 256, smem, st>>>(pcd, idx, C, N, K, out);
   else
@@ -149,6 +151,7 @@ extern "C" int samble_index_points(const float* points, const void* idx, int idx
   if (R == 0) return SAMBLE_OK;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(grid_for((long long)R * (C % 4 == 0 ? C / 4 : C), 256), B);
+  SAMBLE_PRE(st);
   if (idx_bits == 64)
     index_points_kernel<long long><<<grid, 256, 0, st>>>(points, (const long long*)idx, N, C, R, out);
   else
@@ -175,6 +178,7 @@ extern "C" int samble_gather_by_idx(const float* pcd, const void* idx, int idx_b
   SAMBLE_REQUIRE(idx_bits == 32 || idx_bits == 64, "samble_gather_by_idx: idx_bits must be 32 or 64");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(grid_for((long long)C * M, 256), B);
+  SAMBLE_PRE(st);
   if (idx_bits == 64)
     gather_by_idx_kernel<long long><<<grid, 256, 0, st>>>(pcd, (const long long*)idx, C, N, M, out);
   else
@@ -192,6 +196,7 @@ extern "C" int samble_neighbor_mask(const void* idx, int idx_bits, int B, int N,
   if (cudaMemsetAsync(out, 0, (size_t)B * N * N * sizeof(float), st) != cudaSuccess) return check_launch("memset mask");
   count_launch();
   dim3 grid(grid_for((long long)N * K, 256), B);
+  SAMBLE_PRE(st);
   if (idx_bits == 64)
     mask_scatter_kernel<long long><<<grid, 256, 0, st>>>((const long long*)idx, N, (long long)N * K, out, K);
   else

@@ -244,6 +244,7 @@ static int launch_knn_feat(const float* an, const float* anorm, const float* bn,
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("knn_feat smem attribute");
   dim3 grid(ceil_div(Nq, Cfg::TQ), B);
+  SAMBLE_PRE(st);
   kern<<<grid, 256, smem, st>>>(an, anorm, bn, bnorm, Nq, Nr, C, Cp, k, idx, dist);
   SAMBLE_LAUNCHED("knn_feat_kernel");
   return SAMBLE_OK;
@@ -252,12 +253,14 @@ static int launch_knn_feat(const float* an, const float* anorm, const float* bn,
 // shared with upsample.cu
 int launch_knn_stats(const float* a, long long sb, long long sn, long long sc, int B, int N, int C, float* mean,
                      float* stdv, cudaStream_t st) {
+  SAMBLE_PRE(st);
   knn_stats_kernel<<<dim3(ceil_div(C, 8), B), 256, 0, st>>>(a, sb, sn, sc, N, C, mean, stdv);
   SAMBLE_LAUNCHED("knn_stats_kernel");
   return SAMBLE_OK;
 }
 int launch_knn_prep_xyz(const float* x, long long sb, long long sn, long long sc, int B, int N, int C,
                         const float* mean, const float* stdv, float4* out, cudaStream_t st) {
+  SAMBLE_PRE(st);
   knn_prep_xyz_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, st>>>(x, sb, sn, sc, N, C, mean, stdv, out);
   SAMBLE_LAUNCHED("knn_prep_xyz_kernel");
   return SAMBLE_OK;
@@ -296,6 +299,7 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
     if (!self)
       if (int e = launch_knn_prep_xyz(b, b_sb, b_sn, b_sc, B, Nr, C, mean, stdv, qb, st)) return e;
     dim3 grid(ceil_div(Nq, 8 * kXyzQW), B);
+    SAMBLE_PRE(st);
     knn_xyz_kernel<I><<<grid, 256, 0, st>>>(qa, qb, Nq, Nr, k, idx_out, dist_out);
     SAMBLE_LAUNCHED("knn_xyz_kernel");
     return SAMBLE_OK;
@@ -305,9 +309,11 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   float* anorm = w.take<float>((size_t)B * Nq);
   float* bn = self ? an : w.take<float>((size_t)B * Nr * Cp);
   float* bnorm = self ? anorm : w.take<float>((size_t)B * Nr);
+  SAMBLE_PRE(st);
   knn_prep_feat_kernel<<<dim3(ceil_div(Nq, 32), B), 256, 0, st>>>(a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv, an, anorm);
   SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   if (!self) {
+    SAMBLE_PRE(st);
     knn_prep_feat_kernel<<<dim3(ceil_div(Nr, 32), B), 256, 0, st>>>(b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn, bnorm);
     SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   }

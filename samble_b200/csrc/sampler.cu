@@ -214,6 +214,7 @@ using namespace samble;
 extern "C" int samble_zscore(const float* score, int rows, int N, float* z, samble_stream_t stream) {
   SAMBLE_REQUIRE(score && z, "samble_zscore: null pointer");
   SAMBLE_REQUIRE(rows > 0 && N > 0, "samble_zscore: bad shape");
+  SAMBLE_PRE((cudaStream_t)stream);
   zscore_kernel<<<rows, kSampThreads, 0, (cudaStream_t)stream>>>(score, N, z);
   SAMBLE_LAUNCHED("zscore_kernel");
   return SAMBLE_OK;
@@ -225,6 +226,7 @@ extern "C" int samble_bin_mask(const float* z, const float* upper, const float* 
   SAMBLE_REQUIRE(rows > 0 && N > 0 && nb > 0, "samble_bin_mask: bad shape");
   const long long total = (long long)rows * N;
   long long g = (total + 255) / 256;
+  SAMBLE_PRE((cudaStream_t)stream);
   bin_mask_kernel<<<(int)(g > 148 * 8 ? 148 * 8 : g), 256, 0, (cudaStream_t)stream>>>(z, upper, lower, total, nb, mask);
   SAMBLE_LAUNCHED("bin_mask_kernel");
   return SAMBLE_OK;
@@ -234,6 +236,7 @@ extern "C" int samble_num_points_to_choose(const float* bin_prob, const long lon
                                            int total, int* k_out, samble_stream_t stream) {
   SAMBLE_REQUIRE(bin_prob && max_num_points && k_out, "samble_num_points_to_choose: null pointer");
   SAMBLE_REQUIRE(B > 0 && nb > 0 && nb <= kMaxBins, "samble_num_points_to_choose: nb=%d outside [1,%d]", nb, kMaxBins);
+  SAMBLE_PRE((cudaStream_t)stream);
   num_points_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(bin_prob, max_num_points, B, nb, total, k_out);
   SAMBLE_LAUNCHED("num_points_kernel");
   return SAMBLE_OK;
@@ -248,6 +251,7 @@ extern "C" int samble_downsample_index_topk(const float* score, const uint8_t* m
   const size_t smem = (size_t)npad * sizeof(unsigned long long);
   SAMBLE_REQUIRE(smem <= 200 * 1024, "samble_downsample_index_topk: N=%d too large for the shared-memory sort", N);
   cudaFuncSetAttribute(index_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  SAMBLE_PRE((cudaStream_t)stream);
   index_topk_kernel<<<B, kSampThreads, smem, (cudaStream_t)stream>>>(score, mask, k, N, nb, M, npad, idx_out);
   SAMBLE_LAUNCHED("index_topk_kernel");
   return SAMBLE_OK;
@@ -265,6 +269,7 @@ extern "C" int samble_ds_sample(const float* score, const float* token_logits, c
   const size_t smem = (size_t)npad * sizeof(unsigned long long);
   SAMBLE_REQUIRE(smem <= 200 * 1024, "samble_ds_sample: N=%d too large for the shared-memory sort", N);
   cudaFuncSetAttribute(ds_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  SAMBLE_PRE((cudaStream_t)stream);
   ds_sample_kernel<<<B, kSampThreads, smem, (cudaStream_t)stream>>>(score, token_logits, cuts, N, nb, M, npad, idx_out,
                                                                      bin_id, counts, k_out, w_raw, z_out);
   SAMBLE_LAUNCHED("ds_sample_kernel");

@@ -108,6 +108,7 @@ extern "C" int samble_interpolate3(const float* xyz_up, const float* xyz_sel, co
   if (int e = launch_knn_stats(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, st)) return e;
   if (int e = launch_knn_prep_xyz(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, up, st)) return e;
   if (int e = launch_knn_prep_xyz(xyz_sel, 3LL * M, 1, M, B, M, 3, mean, stdv, sel, st)) return e;
+  SAMBLE_PRE(st);
   interpolate3_kernel<<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(up, sel, feat, N, M, C, out, idx_out, dist_out);
   SAMBLE_LAUNCHED("interpolate3_kernel");
   return SAMBLE_OK;
