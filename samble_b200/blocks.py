@@ -21,6 +21,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
+from ._precision import fp32_forward
 
 Tensor = torch.Tensor
 
@@ -41,6 +42,7 @@ class EdgeConv(nn.Module):
         self.conv1 = cbl(config_embedding.conv1_in[layer], config_embedding.conv1_out[layer])
         self.conv2 = cbl(config_embedding.conv2_in[layer], config_embedding.conv2_out[layer])
 
+    @fp32_forward
     def forward(self, x: Tensor) -> Tensor:
         x, _ = ops.group(x, self.K, self.group_type, self.normal_channel)
         return self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0]
@@ -76,6 +78,7 @@ class Neighbor2PointAttention(nn.Module):
         self.bn1 = nn.BatchNorm1d(v_out)
         self.bn2 = nn.BatchNorm1d(v_out)
 
+    @fp32_forward
     def forward(self, x: Tensor) -> Tensor:
         if self.group_type != "diff" or self.attention_mode != "scalar_dot" or self.asm != "dot":
             raise NotImplementedError("native Neighbor2PointAttention covers group_type='diff', "
@@ -149,6 +152,7 @@ class DownSampleToken(nn.Module):
             upper = self.bin_boundaries[0]
         return upper.reshape(-1)[1:].to(torch.float32).contiguous()
 
+    @fp32_forward
     def forward(self, x: Tensor, x_xyz=None):
         if self.asm != "dot" or self.idx_mode != "sparse_col_sqr" or self.relu_mean_order != "mean_relu" or self.num_heads != 1:
             raise NotImplementedError("native DownSampleToken covers asm='dot', idx_mode='sparse_col_sqr', "
@@ -221,6 +225,7 @@ class UpSampleInterpolation(nn.Module):
         self.conv = cbl(q_in, v_out)
         self.res_conv = cbl(2 * v_out, v_out)
 
+    @fp32_forward
     def forward(self, pcd_up, pcd_down, pcd_up_xyz):
         (points_select, idx_select, points_select_xyz), (points_drop, idx_drop) = pcd_down
         interpolated = self.interpolate(pcd_up, points_select, pcd_up_xyz, points_select_xyz,

@@ -14,6 +14,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import blocks, ops
+from ._precision import fp32_forward
 
 Tensor = torch.Tensor
 
@@ -43,6 +44,7 @@ class STN(nn.Module):
         nn.init.eye_(self.transform.bias.view(3, 3))
         self.dp1, self.dp2 = nn.Dropout(p=0.5), nn.Dropout(p=0.5)
 
+    @fp32_forward
     def forward(self, x: Tensor) -> Tensor:
         B = x.size(0)
         x = self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0]
@@ -80,6 +82,7 @@ class SegFeatureLearningBlock(_BlockBase):
             raise NotImplementedError("only us_which='interpolation' (seg.yaml:124) is on the hot path")
         self.upsample_list = nn.ModuleList([blocks.UpSampleInterpolation(cfg.upsample, l) for l in range(len(cfg.upsample.q_in))])
 
+    @fp32_forward
     def forward(self, x: Tensor) -> Tensor:
         x_xyz = x[:, :3, :]
         x = self._front(x)
@@ -120,6 +123,7 @@ class ShapeNetModel(nn.Module):
             self.STN = STN()
         self.stn_regularization_loss_factor = config.train.stn_regularization_loss_factor
 
+    @fp32_forward
     def forward(self, x: Tensor, category_id: Tensor):
         B, C, N = x.shape
         trans = None
@@ -157,6 +161,7 @@ class ClsFeatureLearningBlock(_BlockBase):
             self.conv = nn.Conv1d(outs[-1], 1024, kernel_size=1, bias=False)
         self.M_list = cfg.downsample.M
 
+    @fp32_forward
     def forward(self, x: Tensor):
         x_xyz = x.clone()
         x = self._front(x)
@@ -192,6 +197,7 @@ class ModelNetModel(nn.Module):
         self.linear2 = lbl(1024, 256)
         self.linear3 = nn.Linear(256, 40)
 
+    @fp32_forward
     def forward(self, x: Tensor) -> Tensor:
         if self.res_link_enable:
             x, _ = self.block(x)
