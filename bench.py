@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-sample-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -206,14 +207,25 @@ def run_native(args):
     with torch.no_grad():
         model(x, cat)                                       # calibration batch (dynamic boundaries)
         models.freeze_boundaries(model)
+        lib.samble_reset_launch_count()
+        model(x, cat)
+        launches_per_step = int(lib.samble_launch_count())
+        run = model
+        if not args.no_graph:
+            from samble_b200.runtime import GraphedForward
+
+            run = GraphedForward(model, x, cat)             # whole step = one graph launch
 
         def step_resident():
-            model(x, cat)
+            run(x, cat)
 
         def step_e2e():
-            xd = xh.to(dev, non_blocking=True)
-            cd = cath.to(dev, non_blocking=True)
-            y = model(xd, cd)
+            if args.no_graph:
+                y = model(xh.to(dev, non_blocking=True), cath.to(dev, non_blocking=True))
+            else:
+                run.static_in[0].copy_(xh, non_blocking=True)
+                run.static_in[1].copy_(cath, non_blocking=True)
+                y = run(run.static_in[0], run.static_in[1])
             out_h.copy_(y, non_blocking=True)
 
         for _ in range(max(3, args.warmup)):
@@ -269,7 +281,8 @@ def run_native(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": sampler.result(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(xh.numel() * 4 + cath.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
-            "gpu_launches": launches, "roofline": roof,
+            "gpu_launches": launches_per_step * args.steps, "launch_mode": "eager" if args.no_graph else "cuda_graph",
+            "roofline": roof,
             "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(native_ms.items(), key=lambda kv: -kv[1])},
             "native_share_of_step": sum(native_ms.values()) / prof_total_ms}
     if not args.no_cpu_baseline and world == 1:

@@ -93,6 +93,16 @@ int samble_gather_by_idx(const float* pcd, const void* idx, int idx_bits, int B,
 /* utils/ops.py:125-133  neighbor_mask: dense 0/1 (B,N,N) from idx (B,N,K) (zeros + scatter_). */
 int samble_neighbor_mask(const void* idx, int idx_bits, int B, int N, int K, float* out, samble_stream_t stream);
 
+/* ------------------------------------------------------------ EdgeConv ----------
+ * models/embedding.py:29-39 fused (eval mode): group -> conv1+BN+LeakyReLU(0.2) -> conv2+BN+LeakyReLU
+ * -> max over K.  conv1 is linear in [x_i ; x_j - x_i], so the caller projects the N points once:
+ *   pr (B,N,ld_pr) point-major = [P' | R'],  P'_i = a1*((W1a-W1b) x_i) + b1,  R'_j = a1*(W1b x_j)
+ * (a1,b1 = folded BN1), w2 (C2,C1) = diag(a2) W2, b2 (C2) = folded BN2 shift.  idx (B,N,K) from the kNN.
+ * out (B,C2,N) channel-major = lrelu(max_k (w2 . lrelu(P'_i + R'_idx[i,k]) + b2)).
+ * Limits: K <= 32, C1 % 4 == 0, C1 <= 128, C2 in {32,64,128}. */
+int samble_edge_mlp_max(const float* pr, long long ld_pr, const void* idx, int idx_bits, const float* w2,
+                        const float* b2, int B, int N, int K, int C1, int C2, float* out, samble_stream_t stream);
+
 /* ------------------------------------------------- Neighbor2Point attention -----
  * models/attention.py:165-185,207-250 (scalar_dot, asm "dot"), with the bias-free
  * k/v convolutions hoisted out of the neighbour dimension:

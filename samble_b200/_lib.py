@@ -34,6 +34,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_group": (_i, (_p, _p, _i, _i, _i, _i, _i, _i, _p, _p)),
     "samble_gather_by_idx": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
     "samble_neighbor_mask": (_i, (_p, _i, _i, _i, _i, _p, _p)),
+    "samble_edge_mlp_max": (_i, (_p, _ll, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p)),
     "samble_n2p_attend": (_i, (_p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p)),
     "samble_ds_row_stats": (_i, (_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p)),
     "samble_ds_edge_score_workspace_bytes": (_sz, (_i, _i)),
@@ -120,8 +121,8 @@ def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
            torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        if torch.cuda.is_current_stream_capturing():
-            raise RuntimeError("samble_b200: workspace must be sized by an eager warm-up before graph capture")
+        # (during CUDA-graph capture this allocation comes from the graph's private pool and stays
+        # valid for every replay as long as this cache holds the tensor)
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws

@@ -26,8 +26,60 @@ from ._precision import fp32_forward
 Tensor = torch.Tensor
 
 
+def fold_bn(bn: nn.modules.batchnorm._BatchNorm):
+    """eval-mode BatchNorm as y = a*x + b."""
+    a = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    return a, bn.bias - bn.running_mean * a
+
+
+class _FoldCache:
+    """Folded weights of an edge MLP, recomputed only when a parameter/buffer was modified in place
+    (tensor._version) or moved."""
+
+    def __init__(self):
+        self.key, self.val = None, None
+
+    def get(self, tensors, build):
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if key != self.key:
+            with torch.no_grad():
+                self.val = build()
+            self.key = key
+        return self.val
+
+
+def edge_mlp_weights(conv1, bn1, conv2, bn2, group_type: str):
+    """Fold conv1+BN1 into per-point projections and BN2 into conv2 (csrc/edgeconv.cu header)."""
+    w1 = conv1.weight.flatten(1)                         # (C1, Cin_total)
+    c1 = w1.shape[0]
+    if group_type.startswith("center"):
+        cin = w1.shape[1] // 2
+        wa, wb = w1[:, :cin], w1[:, cin:]
+        a_mat = wa - wb if group_type == "center_diff" else wa
+        b_mat = wb
+    else:
+        a_mat = -w1 if group_type == "diff" else torch.zeros_like(w1)
+        b_mat = w1
+    a1, b1 = fold_bn(bn1)
+    a2, b2 = fold_bn(bn2)
+    w_pr = torch.cat([a1[:, None] * a_mat, a1[:, None] * b_mat], dim=0).contiguous()          # (2*C1, Cin)
+    bias_pr = torch.cat([b1, torch.zeros_like(b1)]).contiguous()                               # shift rides on P
+    w2 = (a2[:, None] * conv2.weight.flatten(1)).contiguous()                                  # (C2, C1)
+    return w_pr, bias_pr, w2, b2.contiguous()
+
+
+def fused_edge_mlp(x: Tensor, idx: Tensor, weights) -> Tensor:
+    """x (B,Cin,N), idx (B,N,K) -> (B,C2,N): one library GEMM over the N points + the fused kernel."""
+    w_pr, bias_pr, w2, b2 = weights
+    pr = torch.matmul(x.transpose(1, 2), w_pr.t()) + bias_pr                                    # (B,N,2*C1)
+    return ops.edge_mlp_max(pr, idx, w2, b2)
+
+
 class EdgeConv(nn.Module):
-    """models/embedding.py:7-39: group -> (conv1x1+BN+LeakyReLU) x2 -> max over K."""
+    """models/embedding.py:7-39: group -> (conv1x1+BN+LeakyReLU) x2 -> max over K.
+
+    eval mode: fused (csrc/edgeconv.cu), nothing of size N*K touches HBM.  train mode (BatchNorm batch
+    statistics cannot be folded): native group kernel + library convolutions, as the reference computes it."""
 
     def __init__(self, config_embedding, layer):
         super().__init__()
@@ -41,11 +93,24 @@ class EdgeConv(nn.Module):
 
         self.conv1 = cbl(config_embedding.conv1_in[layer], config_embedding.conv1_out[layer])
         self.conv2 = cbl(config_embedding.conv2_in[layer], config_embedding.conv2_out[layer])
+        self._fold = _FoldCache()
 
     @fp32_forward
     def forward(self, x: Tensor) -> Tensor:
-        x, _ = ops.group(x, self.K, self.group_type, self.normal_channel)
-        return self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0]
+        if self.group_type not in ("neighbor", "diff", "center_neighbor", "center_diff"):
+            raise ValueError(
+                f"group_type should be neighbor, diff, center_neighbor or center_diff, but got {self.group_type}")
+        c2 = self.conv2[0].out_channels
+        if self.training or self.K > 32 or c2 not in (32, 64, 128) or self.conv1[0].out_channels % 4:
+            x, _ = ops.group(x, self.K, self.group_type, self.normal_channel)
+            return self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0]
+        key = x[:, :3, :] if (self.normal_channel and x.shape[1] == 6) else x
+        idx = ops.knn_indices(key, self.K)
+        params = [self.conv1[0].weight, self.conv2[0].weight, *self.conv1[1].parameters(), *self.conv1[1].buffers(),
+                  *self.conv2[1].parameters(), *self.conv2[1].buffers()]
+        weights = self._fold.get(params, lambda: edge_mlp_weights(self.conv1[0], self.conv1[1], self.conv2[0],
+                                                                  self.conv2[1], self.group_type))
+        return fused_edge_mlp(x, idx, weights)
 
 
 class Neighbor2PointAttention(nn.Module):

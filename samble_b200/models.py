@@ -43,14 +43,31 @@ class STN(nn.Module):
         nn.init.constant_(self.transform.weight, 0)
         nn.init.eye_(self.transform.bias.view(3, 3))
         self.dp1, self.dp2 = nn.Dropout(p=0.5), nn.Dropout(p=0.5)
+        self._fold = blocks._FoldCache()
 
-    @fp32_forward
-    def forward(self, x: Tensor) -> Tensor:
+    def _tail(self, x: Tensor) -> Tensor:
         B = x.size(0)
-        x = self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0]
         x = self.conv3(x).max(dim=-1, keepdim=False)[0]
         x = self.dp2(self.linear2(self.dp1(self.linear1(x))))
         return self.transform(x).view(B, 3, 3)
+
+    @fp32_forward
+    def forward(self, x: Tensor) -> Tensor:
+        """reference signature: x is the grouped (B,6,N,K) tensor of ops.group(x,32,'center_diff')."""
+        return self._tail(self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0])
+
+    @fp32_forward
+    def forward_cloud(self, x: Tensor, K: int = 32) -> Tensor:
+        """same result from the raw (B,3,N) cloud: conv1 -> conv2 -> max over K is the EdgeConv pattern
+        (seg_model.py:182-184 + embedding.py:81-85), so eval mode reuses the fused edge-MLP kernel."""
+        if self.training:
+            return self.forward(ops.group(x, K, "center_diff")[0])
+        idx = ops.knn_indices(x, K)
+        params = [self.conv1[0].weight, self.conv2[0].weight, *self.conv1[1].parameters(), *self.conv1[1].buffers(),
+                  *self.conv2[1].parameters(), *self.conv2[1].buffers()]
+        weights = self._fold.get(params, lambda: blocks.edge_mlp_weights(self.conv1[0], self.conv1[1], self.conv2[0],
+                                                                         self.conv2[1], "center_diff"))
+        return self._tail(blocks.fused_edge_mlp(x, idx, weights))
 
 
 class _BlockBase(nn.Module):
@@ -128,8 +145,7 @@ class ShapeNetModel(nn.Module):
         B, C, N = x.shape
         trans = None
         if self.STN_enable:
-            x0, _ = ops.group(x, 32, "center_diff")
-            trans = self.STN(x0)
+            trans = self.STN.forward_cloud(x, 32)
             x = torch.bmm(x.transpose(2, 1), trans).transpose(2, 1).contiguous()
         f = self.block(x)                                                     # (B,C,N)
         g = self.conv(f)

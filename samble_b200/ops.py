@@ -172,6 +172,19 @@ def gather_by_idx(pcd: Tensor, idx: Tensor) -> Tensor:
 # ------------------------------------------------------------------ fused block cores
 
 
+def edge_mlp_max(pr: Tensor, idx: Tensor, w2: Tensor, b2: Tensor) -> Tensor:
+    """Fused EdgeConv core (csrc/edgeconv.cu): pr (B,N,2*C1) = [P'|R'] point projections, idx (B,N,K),
+    w2 (C2,C1), b2 (C2) -> (B,C2,N).  models/embedding.py:29-39 after folding eval-mode BatchNorm."""
+    dev = L.need_cuda(pr, idx, w2, b2)
+    B, N, two_c1 = pr.shape
+    C1, C2, K = two_c1 // 2, w2.shape[0], idx.shape[-1]
+    w2, b2 = w2.contiguous(), b2.contiguous()
+    out = torch.empty(B, C2, N, dtype=torch.float32, device=dev)
+    L.check(L.lib().samble_edge_mlp_max(L.ptr(pr), pr.stride(1), L.ptr(idx), _idx_bits(idx), L.ptr(w2), L.ptr(b2), B, N, K,
+                                        C1, C2, L.ptr(out), L.stream()), "samble_edge_mlp_max")
+    return out
+
+
 def n2p_attend(qkv: Tensor, idx: Tensor, heads: int) -> Tensor:
     """qkv (B,N,3C) point-major [q|k|v] projections of the points; idx (B,N,K) -> (B,N,C).
     Core of models/attention.py:165-185,207-250 with the k/v convolutions hoisted (attention.cu)."""

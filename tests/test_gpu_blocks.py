@@ -176,6 +176,58 @@ def test_blocks_vs_oracle(N):
         assert close_frac(up, O.upsample_interpolation(sd, "block.upsample_list.0.", x128, dn, xyz_up, xyz_dn, 3)) == 1.0
 
 
+@pytest.mark.parametrize("B,N,K,Cin,C1,C2,gt", [(2, 300, 32, 3, 64, 64, "center_diff"), (1, 515, 16, 64, 64, 128, "center_diff"),
+                                                (2, 128, 7, 8, 32, 32, "diff"), (1, 200, 20, 16, 64, 64, "center_neighbor"),
+                                                (1, 64, 32, 6, 16, 32, "neighbor")])
+def test_fused_edge_mlp_vs_unfused(B, N, K, Cin, C1, C2, gt):
+    """csrc/edgeconv.cu against the literal group -> conv -> BN -> LeakyReLU -> conv -> BN -> LeakyReLU -> max
+    (models/embedding.py:29-39) on CPU, teacher-forced with the same neighbour indices."""
+    from torch import nn
+
+    g = torch.Generator().manual_seed(N + K)
+    x = torch.randn(B, Cin, N, generator=g)
+    cin_t = 2 * Cin if gt.startswith("center") else Cin
+    conv1, bn1, conv2, bn2 = nn.Conv2d(cin_t, C1, 1, bias=False), nn.BatchNorm2d(C1), nn.Conv2d(C1, C2, 1, bias=False), nn.BatchNorm2d(C2)
+    sd = {f"{n}.{k}": v for n, mod in (("conv1", conv1), ("bn1", bn1), ("conv2", conv2), ("bn2", bn2)) for k, v in mod.state_dict().items()}
+    fill_state_dict_(sd, seed=N)
+    for mod in (conv1, bn1, conv2, bn2):
+        mod.eval()
+    _, idx = O.knn(x.transpose(1, 2), x.transpose(1, 2), K)
+    pts = x.transpose(1, 2)
+    nbr = O.index_points(pts, idx)
+    if gt.endswith("diff"):
+        nbr = nbr - pts.unsqueeze(2)
+    grouped = nbr.permute(0, 3, 1, 2)
+    if gt.startswith("center"):
+        grouped = torch.cat([x.unsqueeze(-1).repeat(1, 1, 1, K), grouped], dim=1)
+    with torch.no_grad():
+        lrelu = torch.nn.functional.leaky_relu
+        ref = lrelu(bn2(conv2(lrelu(bn1(conv1(grouped)), 0.2))), 0.2).max(dim=-1)[0]
+        w = [t.to(DEV) for t in blocks.edge_mlp_weights(conv1, bn1, conv2, bn2, gt)]
+        for dt in (torch.int32, torch.int64):
+            out = blocks.fused_edge_mlp(cu(x), cu(idx.to(dt)), w)
+            assert close_frac(out, ref, atol=1e-4, rtol=1e-4) == 1.0
+
+
+def test_cuda_graph_replay_matches_eager():
+    from samble_b200.runtime import GraphedForward
+
+    cfg, m, _ = _sd(512, seed=4)
+    x, cat = synthetic_clouds(3, 512, 8)
+    x2, cat2 = synthetic_clouds(3, 512, 9)
+    with torch.no_grad():
+        m(cu(x), cu(cat))
+        with pytest.raises(RuntimeError, match="frozen"):
+            GraphedForward(m, cu(x), cu(cat))
+        models.freeze_boundaries(m)
+        y_eager, y2_eager = m(cu(x), cu(cat)).clone(), m(cu(x2), cu(cat2)).clone()
+        idx2 = [ds.idx.clone() for ds in m.block.downsample_list]
+        g = GraphedForward(m, cu(x), cu(cat))
+        assert torch.equal(g(cu(x), cu(cat)), y_eager)
+        assert torch.equal(g(cu(x2), cu(cat2)), y2_eager)            # new inputs through the same graph
+        assert all(torch.equal(a, ds.idx) for a, ds in zip(idx2, m.block.downsample_list))
+
+
 def test_grad_is_refused_not_wrong():
     cfg, m, sd = _sd(128)
     x = cu(synthetic_features(1, 128, 128, 1)).requires_grad_(True)
