@@ -53,6 +53,10 @@ void samble_reset_launch_count(void);
 void samble_profile_enable(int on);
 int samble_profile_report(char* buf, size_t cap);
 
+/* hardware self-test of the tcgen05 path (descriptors, 128B swizzle, TMEM mapping): D (128x128) =
+ * A (128xK) * B(128xK)^T with kind::tf32, fp32 accumulate.  K % 32 == 0, K <= 192. */
+int samble_selftest_tc_gemm(const float* A, const float* B, int K, float* D, samble_stream_t stream);
+
 /* ---------------------------------------------------------------- kNN ----------
  * utils/ops.py:17-44  knn(a, b, k) -> (distance, idx).
  * a: queries, b: candidates; element (bi, n, c) lives at base + bi*a_sb + n*a_sn + c*a_sc

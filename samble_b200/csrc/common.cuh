@@ -85,39 +85,55 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ---- running "k smallest" set held one entry per lane (k <= 32) ----
-// Entry order is the total order (distance bits, index): distances are clamped to >= +0 so
-// their IEEE bit patterns order like unsigned ints; ties go to the lower index.
+// Entry order is the total order (distance bits, index): distances are clamped to >= +0 so their IEEE
+// bit patterns order like unsigned ints; ties go to the lower index.
+// CONTRACT: candidates are offered in ASCENDING index order (lane order inside a call, calls in index
+// order).  A candidate that ties the current worst distance therefore has the higher index and loses,
+// so the hot path is a single 32-bit compare; only eviction among equal worst distances looks at indices.
 struct LaneTopK {
-  unsigned d;   // distance bits of this lane's entry (0xffffffff = empty)
+  unsigned d;   // distance bits of this lane's entry (0xffffffff = empty, 0 on inactive lanes)
   int i;        // candidate index of this lane's entry
-  unsigned td;  // warp-uniform: bits of the current worst (largest) entry
-  int ti;       //               and its index
+  unsigned td;  // warp-uniform: distance bits of the current worst (largest) entry
+  int tl;       // warp-uniform: lane holding the entry to evict next
+  int lane;
   bool active;  // lane < k
 
-  __device__ __forceinline__ void init(int lane, int k) {
+  __device__ __forceinline__ void init(int lane_, int k) {
+    lane = lane_;
     active = lane < k;
-    d = 0xffffffffu;
-    i = 0x7ffffff0 - lane;   // distinct per lane so "the worst entry" is always unique
+    d = active ? 0xffffffffu : 0u;
+    i = 0x7ffffff0 - lane;   // distinct per lane
+    td = 0xffffffffu;
+    tl = 0;                  // lane 0 holds the largest placeholder index
+  }
+  __device__ __forceinline__ void load(int lane_, int k, unsigned d_, int i_) {
+    lane = lane_;
+    active = lane < k;
+    d = d_;
+    i = i_;
     refresh();
   }
   __device__ __forceinline__ void refresh() {
-    td = __reduce_max_sync(kFull, active ? d : 0u);
-    ti = (int)__reduce_max_sync(kFull, (active && d == td) ? (unsigned)(i + 1) : 0u) - 1;
+    td = __reduce_max_sync(kFull, d);
+    const unsigned m = __ballot_sync(kFull, active && d == td);
+    tl = __ffs(m) - 1;
+    if (m & (m - 1)) {       // several entries share the worst distance: evict the highest index
+      const int mi = __reduce_max_sync(kFull, (active && d == td) ? i : (int)0x80000000);
+      tl = __ffs(__ballot_sync(kFull, active && d == td && i == mi)) - 1;
+    }
   }
-  __device__ __forceinline__ bool beats_worst(unsigned cd, int ci) const {
-    return cd < td || (cd == td && ci < ti);
-  }
-  // All 32 lanes call this with their own candidate (cd, ci); `want` says whether the
-  // lane's candidate is real.  Candidates are offered in ascending lane order.
+  // All 32 lanes call this with their own candidate (cd, ci); `want` says whether it is real.
   __device__ __forceinline__ void offer(unsigned cd, int ci, bool want) {
-    unsigned pass = __ballot_sync(kFull, want && beats_worst(cd, ci));
+    unsigned pass = __ballot_sync(kFull, want && cd < td);
     while (pass) {
-      int src = __ffs(pass) - 1;
+      const int src = __ffs(pass) - 1;
       pass &= pass - 1;
-      unsigned sd = __shfl_sync(kFull, cd, src);
-      int si = __shfl_sync(kFull, ci, src);
-      if (beats_worst(sd, si)) {            // warp-uniform: the worst may have improved meanwhile
-        if (active && d == td && i == ti) { d = sd; i = si; }
+      const unsigned sd = __shfl_sync(kFull, cd, src);
+      if (sd < td) {                        // warp-uniform: the worst may have improved meanwhile
+        const int si = __shfl_sync(kFull, ci, src);
+        const bool hit = lane == tl;
+        d = hit ? sd : d;
+        i = hit ? si : i;
         refresh();
       }
     }
@@ -127,10 +143,9 @@ struct LaneTopK {
     int r = 0;
 #pragma unroll
     for (int l = 0; l < kWarp; ++l) {
-      unsigned od = __shfl_sync(kFull, d, l);
-      int oi = __shfl_sync(kFull, i, l);
-      bool oact = __shfl_sync(kFull, (int)active, l);
-      r += (oact && (od < d || (od == d && oi < i))) ? 1 : 0;
+      const unsigned od = __shfl_sync(kFull, active ? d : 0xffffffffu, l);
+      const int oi = __shfl_sync(kFull, active ? i : 0x7fffffff, l);
+      r += (od < d || (od == d && oi < i)) ? 1 : 0;
     }
     return r;
   }

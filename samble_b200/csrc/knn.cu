@@ -174,10 +174,7 @@ struct KnnEpilogue {
       const int row = warp * Cfg::RPW + rr;
       if (q0 + row >= Nq) break;
       LaneTopK t;
-      t.active = lane < k;
-      t.d = listd[row * 32 + lane];
-      t.i = listi[row * 32 + lane];
-      t.refresh();
+      t.load(lane, k, listd[row * 32 + lane], listi[row * 32 + lane]);
       const float aa = qq[row];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -219,9 +216,7 @@ __global__ void __launch_bounds__(256, Cfg::MQ == 4 ? 2 : 1)
     const int row = warp * Cfg::RPW + rr, q = q0 + row;
     if (q >= Nq) break;
     LaneTopK t;
-    t.active = lane < k;
-    t.d = listd[row * 32 + lane];
-    t.i = listi[row * 32 + lane];
+    t.load(lane, k, listd[row * 32 + lane], listi[row * 32 + lane]);
     const int r = t.rank();
     if (t.active) {
       long long o = ((long long)b * Nq + q) * k + r;

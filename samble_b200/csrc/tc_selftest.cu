@@ -1,0 +1,76 @@
+// Hardware self-test of the tcgen05 plumbing in tc_common.cuh: one CTA computes D = A * B^T
+// (A, B: 128 x K fp32, K-major; kind::tf32; fp32 accumulate in TMEM) and writes D (128 x 128).
+// It exercises exactly what the production kernels rely on: the 128-byte-swizzled operand layout,
+// the shared-memory and instruction descriptors, K-advance inside a swizzle atom, commit -> mbarrier,
+// and the TMEM lane/column mapping of tcgen05.ld.32x32b.
+#include "tc_common.cuh"
+
+namespace samble {
+
+__global__ void __launch_bounds__(128) tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                               int K, float* __restrict__ D) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = K / 32;
+  uint8_t* sA = base;
+  uint8_t* sB = base + (size_t)nkb * 16384;
+  for (int kb = 0; kb < nkb; ++kb)
+    for (int p = tid; p < 1024; p += 128) {
+      const int row = p >> 3, ch = p & 7;
+      const float4 a = *reinterpret_cast<const float4*>(A + (size_t)row * K + kb * 32 + ch * 4);
+      const float4 b = *reinterpret_cast<const float4*>(B + (size_t)row * K + kb * 32 + ch * 4);
+      *reinterpret_cast<float4*>(sA + (size_t)kb * 16384 + tc::sw128_offset(row, ch)) = a;
+      *reinterpret_cast<float4*>(sB + (size_t)kb * 16384 + tc::sw128_offset(row, ch)) = b;
+    }
+  tc::fence_proxy_async();
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 128);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = tc::instr_desc(2, 128, 128);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const uint64_t ad = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)kb * 16384));
+      const uint64_t bd = tc::smem_desc_sw128(tc::smem_u32(sB + (size_t)kb * 16384));
+      for (int k8 = 0; k8 < 4; ++k8) tc::mma_tf32(tmem, ad + 2 * k8, bd + 2 * k8, idesc, (kb | k8) != 0);
+    }
+    tc::mma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    float v[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) D[(size_t)row * 128 + c0 + i] = v[i];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 128);
+}
+
+}  // namespace samble
+
+using namespace samble;
+
+extern "C" int samble_selftest_tc_gemm(const float* A, const float* B, int K, float* D, samble_stream_t stream) {
+  SAMBLE_REQUIRE(A && B && D, "samble_selftest_tc_gemm: null pointer");
+  SAMBLE_REQUIRE(K > 0 && K % 32 == 0 && K <= 192, "samble_selftest_tc_gemm: K=%d must be a multiple of 32, <= 192", K);
+  size_t smem = (size_t)(K / 32) * 2 * 16384 + 1024;
+  if (cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("tc_gemm_selftest smem attribute");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAMBLE_PRE(st);
+  tc_gemm_selftest_kernel<<<1, 128, smem, st>>>(A, B, K, D);
+  SAMBLE_LAUNCHED("tc_gemm_selftest_kernel");
+  return SAMBLE_OK;
+}

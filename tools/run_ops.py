@@ -1,0 +1,50 @@
+"""Run the hot-path ops in isolation at the BASELINE seg shapes (ncu target / micro-bench)."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from samble_b200 import _lib as L
+from samble_b200 import ops  # noqa: E402
+from samble_b200.testing import synthetic_features  # noqa: E402
+
+B, N = int(os.environ.get("B", 16)), int(os.environ.get("N", 2048))
+which = sys.argv[1:] or ["xyz", "feat128", "feat64", "rowstats"]
+dev = torch.device("cuda:0")
+x3 = synthetic_features(B, 3, N, 1).to(dev)
+x64 = synthetic_features(B, 64, N, 2).to(dev)
+x128 = synthetic_features(B, 128, N, 3).to(dev)
+q = torch.randn(B, N, 128, device=dev)
+k = torch.randn(B, N, 128, device=dev)
+ktok = torch.randn(4, 128, device=dev)
+
+
+def bench(name, fn, flops=None, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    extra = f"  {flops / ms / 1e9:.1f} TFLOP/s" if flops else ""
+    print(f"{name:12s} {ms * 1e3:9.1f} us{extra}   pairs/s {B * N * N / ms / 1e6:.1f} G", flush=True)
+
+
+L.profile(os.environ.get("PROFILE", "0") == "1")
+if "xyz" in which:
+    bench("knn xyz", lambda: ops.knn_indices(x3, 32))
+if "feat64" in which:
+    bench("knn C=64", lambda: ops.knn_indices(x64, 32), 2.0 * B * N * N * 64)
+if "feat128" in which:
+    bench("knn C=128", lambda: ops.knn_indices(x128, 32), 2.0 * B * N * N * 128)
+if "rowstats" in which:
+    bench("ds rowstats", lambda: ops.ds_row_stats(q, k, ktok), 2.0 * B * N * N * 128)
+if os.environ.get("PROFILE", "0") == "1":
+    for kname, (n, ms) in sorted(L.profile_report().items(), key=lambda kv: -kv[1][1]):
+        print(f"  {kname:28s} {n:5d} launches  {ms / n * 1e3:9.1f} us avg")
