@@ -68,7 +68,11 @@ int samble_selftest_tc_gemm(const float* A, const float* B, int K, float* D, sam
  * idx_out: (B,Nq,k) int32|int64.  dist_out: (B,Nq,k) fp32 NEGATIVE Euclidean
  * distance in normalised units (what :43 returns), or NULL.
  * Limits: 1 <= k <= 32, k <= Nr, C <= 512.
- */
+ *
+ * C <= 3 runs the FFMA xyz kernel.  4 <= C <= 128 runs the tcgen05 path (tf32 contraction -> candidate set ->
+ * exact fp32 re-rank; output identical to the exact kernel); larger C runs the exact FFMA tile kernel.
+ * samble_set_knn_mode: 0 = auto (default), 1 = exact FFMA kernels only (used by the tests as the cross-check). */
+void samble_set_knn_mode(int mode);
 size_t samble_knn_workspace_bytes(int B, int Nq, int Nr, int C);
 int samble_knn(const float* a, long long a_sb, long long a_sn, long long a_sc,
                const float* b, long long b_sb, long long b_sn, long long b_sc,

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restr
                                                             long long sc, int N, int C, int Cp,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ stdv, float* __restrict__ out,
-                                                            float* __restrict__ norms) {
+                                                            float* __restrict__ norms, unsigned* __restrict__ maxnorm) {
   __shared__ float tile[32][33];
   const int b = blockIdx.y, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const float sigma = cloud_sigma(stdv + b * C, C);
@@ -88,7 +88,13 @@ __global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restr
     }
     __syncthreads();
   }
-  if (ty == 0 && n0 + tx < N) norms[(long long)b * N + n0 + tx] = nn;
+  if (ty == 0) {
+    if (n0 + tx < N) norms[(long long)b * N + n0 + tx] = nn;
+    if (maxnorm) {                                    // per-cloud max |p'|^2 (>= 0: uint order == float order)
+      const unsigned m = __reduce_max_sync(kFull, n0 + tx < N ? __float_as_uint(nn) : 0u);
+      if (tx == 0) atomicMax(maxnorm + b, m);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -193,10 +199,15 @@ template <class Cfg, class I>
 __global__ void __launch_bounds__(256, Cfg::MQ == 4 ? 2 : 1)
     knn_feat_kernel(const float* __restrict__ an, const float* __restrict__ anorm, const float* __restrict__ bn,
                     const float* __restrict__ bnorm, int Nq, int Nr, int C, int Cp, int k, I* __restrict__ idx_out,
-                    float* __restrict__ dist_out) {
+                    float* __restrict__ dist_out, const int* __restrict__ row_flags) {
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.y, q0 = blockIdx.x * Cfg::TQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (row_flags) {   // repair mode: only tiles holding a row the tensor-core path could not finish
+    int any = 0;
+    for (int r = threadIdx.x; r < Cfg::TQ; r += blockDim.x) any |= (q0 + r < Nq) ? row_flags[(long long)b * Nq + q0 + r] : 0;
+    if (!__syncthreads_or(any)) return;
+  }
   float* tail = smem + Cfg::smem_floats(Cp);
   unsigned* listd = reinterpret_cast<unsigned*>(tail);
   int* listi = reinterpret_cast<int*>(tail + Cfg::TQ * 32);
@@ -215,6 +226,7 @@ __global__ void __launch_bounds__(256, Cfg::MQ == 4 ? 2 : 1)
   for (int rr = 0; rr < Cfg::RPW; ++rr) {
     const int row = warp * Cfg::RPW + rr, q = q0 + row;
     if (q >= Nq) break;
+    if (row_flags && !row_flags[(long long)b * Nq + q]) continue;
     LaneTopK t;
     t.load(lane, k, listd[row * 32 + lane], listi[row * 32 + lane]);
     const int r = t.rank();
@@ -233,15 +245,15 @@ static size_t knn_feat_smem(int Cp) {
 
 template <class Cfg, class I>
 static int launch_knn_feat(const float* an, const float* anorm, const float* bn, const float* bnorm, int B, int Nq,
-                           int Nr, int C, int Cp, int k, I* idx, float* dist, cudaStream_t st) {
+                           int Nr, int C, int Cp, int k, I* idx, float* dist, const int* row_flags, cudaStream_t st) {
   size_t smem = knn_feat_smem<Cfg>(Cp);
   auto kern = knn_feat_kernel<Cfg, I>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("knn_feat smem attribute");
   dim3 grid(ceil_div(Nq, Cfg::TQ), B);
   SAMBLE_PRE(st);
-  kern<<<grid, 256, smem, st>>>(an, anorm, bn, bnorm, Nq, Nr, C, Cp, k, idx, dist);
-  SAMBLE_LAUNCHED("knn_feat_kernel");
+  kern<<<grid, 256, smem, st>>>(an, anorm, bn, bnorm, Nq, Nr, C, Cp, k, idx, dist, row_flags);
+  SAMBLE_LAUNCHED(row_flags ? "knn_feat_repair_kernel" : "knn_feat_kernel");
   return SAMBLE_OK;
 }
 
@@ -261,6 +273,14 @@ int launch_knn_prep_xyz(const float* x, long long sb, long long sn, long long sc
   return SAMBLE_OK;
 }
 
+// tensor-core path (knn_tc.cu)
+bool knn_tc_eligible(int Nq, int Nr, int C, int k);
+template <class I>
+int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const unsigned* bbmax, int B,
+                  int Nq, int Nr, int Cp, int k, float* thr, I* idx, float* dist, int* row_flags, cudaStream_t st);
+
+static int g_knn_mode = 0;   // 0 auto, 1 exact FFMA kernel only, 2 tensor-core path wherever eligible
+
 struct KnnPlan {
   int Cp;
   bool xyz;
@@ -269,10 +289,11 @@ struct KnnPlan {
 static KnnPlan knn_plan(int B, int Nq, int Nr, int C) {
   KnnPlan p;
   p.xyz = C <= 3;
-  p.Cp = p.xyz ? 4 : (int)align_up(C, 16);
+  p.Cp = p.xyz ? 4 : (int)align_up(C, 32);   // 32-channel K-blocks for the tensor-core path
   size_t per_pt = p.xyz ? sizeof(float4) : (size_t)(p.Cp + 1) * sizeof(float);
   p.bytes = 2 * align_up((size_t)B * C * sizeof(float), 256) + align_up((size_t)B * Nq * per_pt, 256) +
-            align_up((size_t)B * Nr * per_pt, 256) + 4 * 256;
+            align_up((size_t)B * Nr * per_pt, 256) + 2 * align_up((size_t)B * Nq * sizeof(float), 256) +
+            align_up((size_t)B * sizeof(unsigned), 256) + 8 * 256;
   return p;
 }
 
@@ -305,22 +326,41 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   float* bn = self ? an : w.take<float>((size_t)B * Nr * Cp);
   float* bnorm = self ? anorm : w.take<float>((size_t)B * Nr);
   SAMBLE_PRE(st);
-  knn_prep_feat_kernel<<<dim3(ceil_div(Nq, 32), B), 256, 0, st>>>(a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv, an, anorm);
+  float* thr = w.take<float>((size_t)B * Nq);
+  int* row_flags = w.take<int>((size_t)B * Nq);
+  unsigned* bbmax = w.take<unsigned>((size_t)B);
+  const bool use_tc = g_knn_mode != 1 && knn_tc_eligible(Nq, Nr, C, k);
+  if (use_tc) {   // row_flags and bbmax are adjacent (256-byte granules): one memset node
+    const size_t span = (size_t)((char*)(bbmax + B) - (char*)row_flags);
+    if (cudaMemsetAsync(row_flags, 0, span, st) != cudaSuccess) return check_launch("memset knn flags");
+    count_launch();
+  }
+  SAMBLE_PRE(st);
+  knn_prep_feat_kernel<<<dim3(ceil_div(Nq, 32), B), 256, 0, st>>>(a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv, an, anorm,
+                                                                    (use_tc && self) ? bbmax : nullptr);
   SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   if (!self) {
     SAMBLE_PRE(st);
-    knn_prep_feat_kernel<<<dim3(ceil_div(Nr, 32), B), 256, 0, st>>>(b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn, bnorm);
+    knn_prep_feat_kernel<<<dim3(ceil_div(Nr, 32), B), 256, 0, st>>>(b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn, bnorm,
+                                                                      use_tc ? bbmax : nullptr);
     SAMBLE_LAUNCHED("knn_prep_feat_kernel");
+  }
+  if (use_tc) {
+    if (int e = launch_knn_tc<I>(an, anorm, bn, bnorm, bbmax, B, Nq, Nr, Cp, k, thr, idx_out, dist_out, row_flags, st)) return e;
+    // rows whose candidate buffer overflowed are redone by the exact kernel (normally none: every tile exits at once)
+    return launch_knn_feat<DotTileCfg<4>, I>(an, anorm, bn, bnorm, B, Nq, Nr, C, Cp, k, idx_out, dist_out, row_flags, st);
   }
   // 128-row CTAs when they still give every SM at least ~2 CTAs of work, else 64-row CTAs
   const bool big = (long long)ceil_div(Nq, 128) * B >= 2 * 148 && knn_feat_smem<DotTileCfg<8>>(Cp) <= 200 * 1024;
-  if (big) return launch_knn_feat<DotTileCfg<8>, I>(an, anorm, bn, bnorm, B, Nq, Nr, C, Cp, k, idx_out, dist_out, st);
-  return launch_knn_feat<DotTileCfg<4>, I>(an, anorm, bn, bnorm, B, Nq, Nr, C, Cp, k, idx_out, dist_out, st);
+  if (big) return launch_knn_feat<DotTileCfg<8>, I>(an, anorm, bn, bnorm, B, Nq, Nr, C, Cp, k, idx_out, dist_out, nullptr, st);
+  return launch_knn_feat<DotTileCfg<4>, I>(an, anorm, bn, bnorm, B, Nq, Nr, C, Cp, k, idx_out, dist_out, nullptr, st);
 }
 
 }  // namespace samble
 
 using namespace samble;
+
+extern "C" void samble_set_knn_mode(int mode) { g_knn_mode = mode; }
 
 extern "C" size_t samble_knn_workspace_bytes(int B, int Nq, int Nr, int C) {
   if (B <= 0 || Nq <= 0 || Nr <= 0 || C <= 0) return 0;

@@ -214,3 +214,57 @@ def test_bin_golden():
     w = torch.rand(3, 4, generator=torch.Generator().manual_seed(53))
     np.testing.assert_array_equal(ops.calculate_num_points_to_choose(cu(w), cu(mask3.squeeze(1).sum(1)), 100).cpu().numpy(),
                                   gold["bin.static.k"])
+
+
+# ---------------------------------------------------------------- tensor-core kNN == exact kNN
+
+
+def _knn_both(a, b, k):
+    from samble_b200 import _lib as L
+
+    lib = L.lib()
+    try:
+        lib.samble_set_knn_mode(1)
+        d1, i1 = ops.knn(a, b, k)
+        torch.cuda.synchronize()
+    finally:
+        lib.samble_set_knn_mode(0)
+    d0, i0 = ops.knn(a, b, k)
+    torch.cuda.synchronize()
+    return (d0, i0), (d1, i1)
+
+
+TC_SHAPES = [(2, 2048, 0, 128, 32), (2, 2048, 0, 64, 32), (3, 1000, 0, 128, 32), (2, 512, 0, 128, 16), (1, 700, 260, 20, 5),
+             (2, 130, 0, 8, 32), (1, 64, 0, 128, 32), (1, 40, 33, 64, 32), (1, 4096, 0, 128, 32), (4, 300, 1200, 96, 3)]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES, ids=[f"B{s[0]}_N{s[1]}x{s[2] or s[1]}_C{s[3]}_k{s[4]}" for s in TC_SHAPES])
+def test_tensor_core_knn_is_bit_identical_to_exact_kernel(shape):
+    """csrc/knn_tc.cu (tcgen05 tf32 candidates + fp32 re-rank) must reproduce csrc/knn.cu's exact FFMA kernel
+    bit for bit: same indices in the same order, same distances."""
+    B, Nq, Nr, C, k = shape
+    a = cu(synthetic_features(B, Nq, C, 100 + Nq))
+    b = a if Nr == 0 else cu(synthetic_features(B, Nr, C, 200 + Nr))
+    (d0, i0), (d1, i1) = _knn_both(a, b, k)
+    assert torch.equal(i0, i1)
+    assert torch.equal(d0, d1)
+
+
+def test_tensor_core_knn_hard_cases():
+    g = torch.Generator().manual_seed(5)
+    # (1) tight clusters + duplicated points: near-zero distances, exact ties, candidate-buffer overflow -> repair kernel
+    centers = torch.randn(1, 8, 128, generator=g) * 4
+    a = (centers[:, torch.randint(0, 8, (1024,), generator=g)] + 1e-3 * torch.randn(1, 1024, 128, generator=g))
+    a[:, 512:768] = a[:, 256:512]
+    a = cu(a.contiguous())
+    (d0, i0), (d1, i1) = _knn_both(a, a, 32)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    # (2) wildly different norms (margin driven by the largest candidate norm)
+    s = cu(synthetic_features(2, 600, 64, 7) * (1 + 50 * (torch.rand(2, 600, 1, generator=g) > 0.97).float()))
+    (d0, i0), (d1, i1) = _knn_both(s, s, 32)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    # (3) low intrinsic dimension (a curve embedded in 128-d): many candidates near the threshold
+    tt = torch.linspace(0, 1, 2048).view(1, 2048, 1)
+    curve = cu(torch.cat([torch.sin(tt * (i + 1)) for i in range(128)], dim=-1).contiguous())
+    (d0, i0), (d1, i1) = _knn_both(curve, curve, 32)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
