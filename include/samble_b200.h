@@ -55,7 +55,9 @@ int samble_profile_report(char* buf, size_t cap);
 
 /* hardware self-test of the tcgen05 path (descriptors, 128B swizzle, TMEM mapping): D (128x128) =
  * A (128xK) * B(128xK)^T with kind::tf32, fp32 accumulate.  K % 32 == 0, K <= 192. */
-int samble_selftest_tc_gemm(const float* A, const float* B, int K, float* D, samble_stream_t stream);
+int samble_selftest_tc_gemm(const float* A, const float* B, int K, float* D, const float* Ax /* 128x8 or NULL */,
+                            const float* Bx /* 128x8 or NULL: adds Ax*Bx^T from a non-swizzled slice */,
+                            samble_stream_t stream);
 
 /* ---------------------------------------------------------------- kNN ----------
  * utils/ops.py:17-44  knn(a, b, k) -> (distance, idx).

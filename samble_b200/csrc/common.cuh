@@ -113,6 +113,12 @@ struct LaneTopK {
     i = i_;
     refresh();
   }
+  // seed the set directly (no serial inserts): lanes with `take` adopt their own candidate.
+  // Only valid while every taken slot is still empty; candidates must be in ascending index order by lane.
+  __device__ __forceinline__ void fill(unsigned cd, int ci, bool take) {
+    if (take && active) { d = cd; i = ci; }
+    refresh();
+  }
   __device__ __forceinline__ void refresh() {
     td = __reduce_max_sync(kFull, d);
     const unsigned m = __ballot_sync(kFull, active && d == td);

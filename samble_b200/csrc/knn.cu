@@ -18,14 +18,26 @@ __global__ void __launch_bounds__(256) knn_stats_kernel(const float* __restrict_
   const int c = blockIdx.x * 8 + warp, b = blockIdx.y;
   if (c >= C) return;
   const float* p = a + b * sb + c * sc;
-  double s = 0.0, s2 = 0.0;
-  for (int n = lane; n < N; n += 32) {
-    double v = (double)p[n * sn];
-    s += v;
-    s2 += v * v;
+  // 4 independent accumulator pairs: the loads of one trip do not wait on the previous trip's adds
+  double sa[4] = {0.0, 0.0, 0.0, 0.0}, qa[4] = {0.0, 0.0, 0.0, 0.0};
+  int n = lane;
+  for (; n + 96 < N; n += 128) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = p[(long long)(n + 32 * u) * sn];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      sa[u] += (double)v[u];
+      qa[u] += (double)v[u] * (double)v[u];
+    }
   }
-  s = warp_sum(s);
-  s2 = warp_sum(s2);
+  for (; n < N; n += 32) {
+    const double v = (double)p[(long long)n * sn];
+    sa[0] += v;
+    qa[0] += v * v;
+  }
+  double s = warp_sum((sa[0] + sa[1]) + (sa[2] + sa[3]));
+  double s2 = warp_sum((qa[0] + qa[1]) + (qa[2] + qa[3]));
   if (lane == 0) {
     double m = s / N;
     double var = (s2 - s * m) / (double)(N - 1);
@@ -275,9 +287,11 @@ int launch_knn_prep_xyz(const float* x, long long sb, long long sn, long long sc
 
 // tensor-core path (knn_tc.cu)
 bool knn_tc_eligible(int Nq, int Nr, int C, int k);
+size_t knn_tc_workspace_bytes(int B, int Nq);
 template <class I>
 int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const unsigned* bbmax, int B,
-                  int Nq, int Nr, int Cp, int k, float* thr, I* idx, float* dist, int* row_flags, cudaStream_t st);
+                  int Nq, int Nr, int Cp, int k, float* thr, unsigned short* cand, int* cnt, I* idx, float* dist,
+                  int* row_flags, cudaStream_t st);
 
 static int g_knn_mode = 0;   // 0 auto, 1 exact FFMA kernel only, 2 tensor-core path wherever eligible
 
@@ -293,7 +307,7 @@ static KnnPlan knn_plan(int B, int Nq, int Nr, int C) {
   size_t per_pt = p.xyz ? sizeof(float4) : (size_t)(p.Cp + 1) * sizeof(float);
   p.bytes = 2 * align_up((size_t)B * C * sizeof(float), 256) + align_up((size_t)B * Nq * per_pt, 256) +
             align_up((size_t)B * Nr * per_pt, 256) + 2 * align_up((size_t)B * Nq * sizeof(float), 256) +
-            align_up((size_t)B * sizeof(unsigned), 256) + 8 * 256;
+            align_up((size_t)B * sizeof(unsigned), 256) + (p.xyz ? 0 : knn_tc_workspace_bytes(B, Nq)) + 10 * 256;
   return p;
 }
 
@@ -329,6 +343,8 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   float* thr = w.take<float>((size_t)B * Nq);
   int* row_flags = w.take<int>((size_t)B * Nq);
   unsigned* bbmax = w.take<unsigned>((size_t)B);
+  unsigned short* cand = w.take<unsigned short>((size_t)B * Nq * 128);
+  int* cand_cnt = w.take<int>((size_t)B * Nq);
   const bool use_tc = g_knn_mode != 1 && knn_tc_eligible(Nq, Nr, C, k);
   if (use_tc) {   // row_flags and bbmax are adjacent (256-byte granules): one memset node
     const size_t span = (size_t)((char*)(bbmax + B) - (char*)row_flags);
@@ -346,7 +362,8 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
     SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   }
   if (use_tc) {
-    if (int e = launch_knn_tc<I>(an, anorm, bn, bnorm, bbmax, B, Nq, Nr, Cp, k, thr, idx_out, dist_out, row_flags, st)) return e;
+    if (int e = launch_knn_tc<I>(an, anorm, bn, bnorm, bbmax, B, Nq, Nr, Cp, k, thr, cand, cand_cnt, idx_out, dist_out, row_flags, st))
+      return e;
     // rows whose candidate buffer overflowed are redone by the exact kernel (normally none: every tile exits at once)
     return launch_knn_feat<DotTileCfg<4>, I>(an, anorm, bn, bnorm, B, Nq, Nr, C, Cp, k, idx_out, dist_out, row_flags, st);
   }

@@ -7,8 +7,11 @@
 
 namespace samble {
 
+// With ext != 0 one more K=8 step is taken from compact NON-swizzled [128 x 32 B] slices (Ax, Bx: 128 x 8 fp32),
+// the layout the kNN kernel uses to carry the candidate norms through the GEMM.
 __global__ void __launch_bounds__(128) tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                                               int K, float* __restrict__ D) {
+                                                               int K, float* __restrict__ D, const float* __restrict__ Ax,
+                                                               const float* __restrict__ Bx) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -17,6 +20,14 @@ __global__ void __launch_bounds__(128) tc_gemm_selftest_kernel(const float* __re
   const int nkb = K / 32;
   uint8_t* sA = base;
   uint8_t* sB = base + (size_t)nkb * 16384;
+  uint8_t* sAx = sB + (size_t)nkb * 16384;
+  uint8_t* sBx = sAx + 4096;
+  if (Ax)
+    for (int p = tid; p < 256; p += 128) {
+      const int row = p >> 1, ch = p & 1;
+      *reinterpret_cast<float4*>(sAx + tc::nosw_offset(row, ch, 128)) = *reinterpret_cast<const float4*>(Ax + row * 8 + ch * 4);
+      *reinterpret_cast<float4*>(sBx + tc::nosw_offset(row, ch, 128)) = *reinterpret_cast<const float4*>(Bx + row * 8 + ch * 4);
+    }
   for (int kb = 0; kb < nkb; ++kb)
     for (int p = tid; p < 1024; p += 128) {
       const int row = p >> 3, ch = p & 7;
@@ -42,6 +53,7 @@ __global__ void __launch_bounds__(128) tc_gemm_selftest_kernel(const float* __re
       const uint64_t bd = tc::smem_desc_sw128(tc::smem_u32(sB + (size_t)kb * 16384));
       for (int k8 = 0; k8 < 4; ++k8) tc::mma_tf32(tmem, ad + 2 * k8, bd + 2 * k8, idesc, (kb | k8) != 0);
     }
+    if (Ax) tc::mma_tf32(tmem, tc::smem_desc_nosw(tc::smem_u32(sAx), 128), tc::smem_desc_nosw(tc::smem_u32(sBx), 128), idesc, 1);
     tc::mma_commit(&bar);
   }
   tc::mbar_wait(&bar, 0);
@@ -62,15 +74,17 @@ __global__ void __launch_bounds__(128) tc_gemm_selftest_kernel(const float* __re
 
 using namespace samble;
 
-extern "C" int samble_selftest_tc_gemm(const float* A, const float* B, int K, float* D, samble_stream_t stream) {
+extern "C" int samble_selftest_tc_gemm(const float* A, const float* B, int K, float* D, const float* Ax, const float* Bx,
+                                       samble_stream_t stream) {
   SAMBLE_REQUIRE(A && B && D, "samble_selftest_tc_gemm: null pointer");
   SAMBLE_REQUIRE(K > 0 && K % 32 == 0 && K <= 192, "samble_selftest_tc_gemm: K=%d must be a multiple of 32, <= 192", K);
-  size_t smem = (size_t)(K / 32) * 2 * 16384 + 1024;
+  SAMBLE_REQUIRE((Ax == nullptr) == (Bx == nullptr), "samble_selftest_tc_gemm: Ax and Bx go together");
+  size_t smem = (size_t)(K / 32) * 2 * 16384 + 8192 + 1024;
   if (cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("tc_gemm_selftest smem attribute");
   cudaStream_t st = (cudaStream_t)stream;
   SAMBLE_PRE(st);
-  tc_gemm_selftest_kernel<<<1, 128, smem, st>>>(A, B, K, D);
+  tc_gemm_selftest_kernel<<<1, 128, smem, st>>>(A, B, K, D, Ax, Bx);
   SAMBLE_LAUNCHED("tc_gemm_selftest_kernel");
   return SAMBLE_OK;
 }
