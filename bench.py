@@ -60,6 +60,8 @@ def cpu_reference_rate(batch, points, steps, warmup):
     from samble_b200.config import seg_config
     from samble_b200.testing import fill_state_dict_, synthetic_clouds
 
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core it can use
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     cfg = seg_config(M=(points // 2, points // 4))
     sd = fill_state_dict_(models.ShapeNetModel(cfg).state_dict(), seed=1, sharpen=4.0)
     x, cat = synthetic_clouds(batch, points, seed=2)

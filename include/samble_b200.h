@@ -103,6 +103,21 @@ int samble_gather_by_idx(const float* pcd, const void* idx, int idx_bits, int B,
 /* utils/ops.py:125-133  neighbor_mask: dense 0/1 (B,N,N) from idx (B,N,K) (zeros + scatter_). */
 int samble_neighbor_mask(const void* idx, int idx_bits, int B, int N, int K, float* out, samble_stream_t stream);
 
+/* --------------------------------------------------- point-wise linear layers ----
+ * The 1x1 convolutions / Linear layers over the points of a cloud (models/attention.py:171-191,
+ * downsample.py:124-137, upsample.py:150-160, seg_model.py:141-160) as one tcgen05 GEMM with fp32-class accuracy
+ * (3xTF32 operand split) and a fused epilogue:
+ *   acc = X W^T ;  y = [ (acc (+res if residual_first)) * scale[c] + shift[b?][c] ] -> LeakyReLU(0.2) if lrelu -> (+res)
+ * X: M x K.  row-major (x_channel_major=0): X[m*ldx + k]; channel-major: X[(b*K + k)*P + n] with m = b*P + n,
+ * P = points_per_cloud.  W: Nout x K row-major (the stored conv/linear weight).  scale/shift: [Nout] or NULL;
+ * shift_cloud_stride != 0 selects a per-cloud shift row.  residual and out are each row-major (ld) or
+ * channel-major (B, Nout, P). */
+int samble_linear(const float* X, long long ldx, int x_channel_major, const float* W, long long ldw,
+                  const float* scale, const float* shift, long long shift_cloud_stride, int lrelu,
+                  const float* residual, long long ldr, int residual_channel_major, int residual_first,
+                  float* out, long long ldo, int out_channel_major, int M, int K, int Nout, int points_per_cloud,
+                  samble_stream_t stream);
+
 /* ------------------------------------------------------------ EdgeConv ----------
  * models/embedding.py:29-39 fused (eval mode): group -> conv1+BN+LeakyReLU(0.2) -> conv2+BN+LeakyReLU
  * -> max over K.  conv1 is linear in [x_i ; x_j - x_i], so the caller projects the N points once:
@@ -119,9 +134,11 @@ int samble_edge_mlp_max(const float* pr, long long ld_pr, const void* idx, int i
  *   W(x_j - x_i) = W x_j - W x_i, and softmax over j is invariant to the -q.Wk x_i shift.
  * q,k,v: point-major (B,N,C) with leading dimension ld (elements per point), i.e. the
  * projections of the N points themselves; idx (B,N,K) from the kNN on x.
- * out (B,N,C) point-major: sum_j softmax_j(q_i.k_j/sqrt(C/H)) v_j - v_i per head. */
+ * out (B,N,C) point-major: att_i = sum_j softmax_j(q_i.k_j/sqrt(C/H)) v_j - v_i per head;
+ * optional fused tail of attention.py:187 (eval): out = (residual_i + att_i) * scale + shift  (BN1 folded). */
 int samble_n2p_attend(const float* q, const float* k, const float* v, long long ld,
                       const void* idx, int idx_bits, int B, int N, int C, int K, int heads,
+                      const float* residual, long long ld_res, const float* scale, const float* shift,
                       float* out, long long ld_out, samble_stream_t stream);
 
 /* --------------------------------------------------- DownSampleToken scoring ----

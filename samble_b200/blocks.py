@@ -32,6 +32,35 @@ def fold_bn(bn: nn.modules.batchnorm._BatchNorm):
     return a, bn.bias - bn.running_mean * a
 
 
+_BN_CACHE: "weakref.WeakKeyDictionary" = None
+
+
+def folded(bn: nn.modules.batchnorm._BatchNorm):
+    """fold_bn with a per-module cache keyed on the in-place version counters of its tensors."""
+    global _BN_CACHE
+    import weakref
+
+    if _BN_CACHE is None:
+        _BN_CACHE = weakref.WeakKeyDictionary()
+    ts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple((t.data_ptr(), t._version) for t in ts)
+    hit = _BN_CACHE.get(bn)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            a, b = fold_bn(bn)
+        hit = (key, (a.contiguous(), b.contiguous()))
+        _BN_CACHE[bn] = hit
+    return hit[1]
+
+
+def cbl(seq: nn.Sequential, x: Tensor, x_layout: str = "bcn", out_layout: str = "bcn", shift_extra: Tensor = None) -> Tensor:
+    """eval-mode nn.Sequential(Conv1d 1x1 (no bias), BatchNorm1d, LeakyReLU(0.2)) as ONE tensor-core GEMM with the
+    BatchNorm folded into the epilogue (csrc/linear_tc.cu)."""
+    a, b = folded(seq[1])
+    return ops.linear(x, seq[0].weight, x_layout=x_layout, out_layout=out_layout, scale=a,
+                      shift=b if shift_extra is None else shift_extra, lrelu=True)
+
+
 class _FoldCache:
     """Folded weights of an edge MLP, recomputed only when a parameter/buffer was modified in place
     (tensor._version) or moved."""
@@ -71,7 +100,7 @@ def edge_mlp_weights(conv1, bn1, conv2, bn2, group_type: str):
 def fused_edge_mlp(x: Tensor, idx: Tensor, weights) -> Tensor:
     """x (B,Cin,N), idx (B,N,K) -> (B,C2,N): one library GEMM over the N points + the fused kernel."""
     w_pr, bias_pr, w2, b2 = weights
-    pr = torch.matmul(x.transpose(1, 2), w_pr.t()) + bias_pr                                    # (B,N,2*C1)
+    pr = ops.linear(x, w_pr, x_layout="bcn", out_layout="rows", shift=bias_pr)                  # (B,N,2*C1)
     return ops.edge_mlp_max(pr, idx, w2, b2)
 
 
@@ -142,6 +171,7 @@ class Neighbor2PointAttention(nn.Module):
         )
         self.bn1 = nn.BatchNorm1d(v_out)
         self.bn2 = nn.BatchNorm1d(v_out)
+        self._wqkv = _FoldCache()
 
     @fp32_forward
     def forward(self, x: Tensor) -> Tensor:
@@ -150,11 +180,22 @@ class Neighbor2PointAttention(nn.Module):
                                       "attention_mode='scalar_dot', asm='dot' (the shipped configs)")
         B, C, N = x.shape
         idx = ops.knn_indices(x, self.K)                                        # (B,N,K) int32
-        w = torch.cat([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C)
-        qkv = torch.matmul(x.transpose(1, 2), w.t())                            # (B,N,3C) point-major
-        y = ops.n2p_attend(qkv, idx, self.num_heads)                            # (B,N,C)
-        x = self.bn1(x + y.transpose(1, 2))
-        return self.bn2(x + self.ff(x))
+        w = self._wqkv.get([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], lambda: torch.cat(
+            [self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C).contiguous())
+        if self.training:                                                       # BatchNorm batch statistics: library ops
+            qkv = torch.matmul(x.transpose(1, 2), w.t())                        # (B,N,3C) point-major
+            y = ops.n2p_attend(qkv, idx, self.num_heads)                        # (B,N,C)
+            x = self.bn1(x + y.transpose(1, 2))
+            return self.bn2(x + self.ff(x))
+        # eval: everything point-major, projections / feed-forward on the tensor cores, BatchNorms folded into epilogues
+        x_pm = x.transpose(1, 2).contiguous()                                   # (B,N,C)
+        qkv = ops.linear(x_pm, w)                                               # (B,N,3C)
+        a1, b1 = folded(self.bn1)
+        a2, b2 = folded(self.bn2)
+        x1 = ops.n2p_attend(qkv, idx, self.num_heads, residual=x_pm, scale=a1, shift=b1)     # bn1(x + attention)
+        h = ops.linear(x1, self.ff[0].weight, lrelu=True)                       # (B,N,4C)
+        return ops.linear(h, self.ff[2].weight, scale=a2, shift=b2, residual=x1, residual_first=True, residual_layout="rows",
+                          out_layout="bcn")
 
 
 class DownSampleToken(nn.Module):
@@ -207,6 +248,7 @@ class DownSampleToken(nn.Module):
         self.boltzmann_T = config_ds.bin.boltzmann_T[layer]
         self.boltzmann_norm_mode = config_ds.boltzmann.norm_mode[layer]
         self.token_orthognonal_loss_factor = config_ds.bin.token_orthognonal_loss_factor
+        self._wqkv = _FoldCache()
 
     # -- helpers -------------------------------------------------------------------------------
     def _cuts(self, device) -> Tensor:
@@ -227,8 +269,9 @@ class DownSampleToken(nn.Module):
         B, C, N = x.shape
         D, nb = self.q_depth, self.num_bins
         # projections of the points and of the nb bin tokens (shared by the whole batch, :116-118)
-        w = torch.cat([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C)
-        qkv = torch.matmul(x.transpose(1, 2), w.t())                           # (B,N,3C)
+        w = self._wqkv.get([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], lambda: torch.cat(
+            [self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C).contiguous())
+        qkv = ops.linear(x, w, x_layout="bcn")                                 # (B,N,3C) on the tensor cores (3xTF32)
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         tok = self.bin_tokens[0].t()                                           # (nb,C)
         k_tok = torch.matmul(tok, self.k_conv.weight.view(C, C).t()).contiguous()   # (nb,D)
@@ -295,10 +338,11 @@ class UpSampleInterpolation(nn.Module):
         (points_select, idx_select, points_select_xyz), (points_drop, idx_drop) = pcd_down
         interpolated = self.interpolate(pcd_up, points_select, pcd_up_xyz, points_select_xyz,
                                         distance_type=self.distance_type, K=self.K)
-        return self.res_conv(torch.cat([pcd_up, interpolated], dim=1))
+        x = torch.cat([pcd_up, interpolated], dim=1)
+        return self.res_conv(x) if self.training else cbl(self.res_conv, x)
 
     def interpolate(self, pcd_up, points_select, pcd_up_xyz, points_select_xyz, distance_type="feature", K=3):
-        feat = self.conv(points_select)
+        feat = self.conv(points_select) if self.training else cbl(self.conv, points_select)
         if distance_type == "xyz" and K == 3:
             return ops.interpolate3(pcd_up_xyz, points_select_xyz, feat)
         if distance_type == "feature":

@@ -16,8 +16,9 @@ template <class I, int KMAX>
 __global__ void __launch_bounds__(256) n2p_attend_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                          const float* __restrict__ v, long long ld,
                                                          const I* __restrict__ idx, int N, int C, int K, int lph,
-                                                         float inv_dummy, float sqrt_d, float* __restrict__ out,
-                                                         long long ld_out) {
+                                                         float sqrt_d, const float* __restrict__ residual, long long ld_res,
+                                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                                         float* __restrict__ out, long long ld_out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int n = blockIdx.x * 8 + warp;
@@ -73,6 +74,15 @@ __global__ void __launch_bounds__(256) n2p_attend_kernel(const float* __restrict
     o.y = acc.y / s - vi.y;
     o.z = acc.z / s - vi.z;
     o.w = acc.w / s - vi.w;
+    if (residual) {   // fused  bn1(x + attention)  of attention.py:187 (eval-mode BN folded to scale/shift)
+      const float4 r = *reinterpret_cast<const float4*>(residual + row * ld_res + lane * 4);
+      o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+    }
+    if (scale) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + lane * 4));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + lane * 4));
+      o.x = fmaf(o.x, sc.x, sh.x), o.y = fmaf(o.y, sc.y, sh.y), o.z = fmaf(o.z, sc.z, sh.z), o.w = fmaf(o.w, sc.w, sh.w);
+    }
     *reinterpret_cast<float4*>(out + row * ld_out + lane * 4) = o;
   }
 }
@@ -82,7 +92,8 @@ __global__ void __launch_bounds__(256) n2p_attend_kernel(const float* __restrict
 using namespace samble;
 
 extern "C" int samble_n2p_attend(const float* q, const float* k, const float* v, long long ld, const void* idx,
-                                 int idx_bits, int B, int N, int C, int K, int heads, float* out, long long ld_out,
+                                 int idx_bits, int B, int N, int C, int K, int heads, const float* residual,
+                                 long long ld_res, const float* scale, const float* shift, float* out, long long ld_out,
                                  samble_stream_t stream) {
   SAMBLE_REQUIRE(q && k && v && idx && out, "samble_n2p_attend: null pointer");
   SAMBLE_REQUIRE(B > 0 && N > 0 && K > 0, "samble_n2p_attend: bad shape");
@@ -94,14 +105,17 @@ extern "C" int samble_n2p_attend(const float* q, const float* k, const float* v,
   SAMBLE_REQUIRE(ld % 4 == 0 && ld_out % 4 == 0, "samble_n2p_attend: leading dimensions must be multiples of 4");
   SAMBLE_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) % 16 == 0, "samble_n2p_attend: 16-byte alignment required");
   SAMBLE_REQUIRE(idx_bits == 32 || idx_bits == 64, "samble_n2p_attend: idx_bits must be 32 or 64");
+  SAMBLE_REQUIRE((scale == nullptr) == (shift == nullptr), "samble_n2p_attend: scale and shift go together");
+  SAMBLE_REQUIRE(!residual || (ld_res % 4 == 0 && (uintptr_t)residual % 16 == 0), "samble_n2p_attend: residual alignment");
+  SAMBLE_REQUIRE(!scale || ((uintptr_t)scale | (uintptr_t)shift) % 16 == 0, "samble_n2p_attend: scale/shift alignment");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(ceil_div(N, 8), B);
   const float sqrt_d = sqrtf((float)(C / heads));
   SAMBLE_PRE(st);
   if (idx_bits == 64)
-    n2p_attend_kernel<long long, 32><<<grid, 256, 0, st>>>(q, k, v, ld, (const long long*)idx, N, C, K, lph, 0.f, sqrt_d, out, ld_out);
+    n2p_attend_kernel<long long, 32><<<grid, 256, 0, st>>>(q, k, v, ld, (const long long*)idx, N, C, K, lph, sqrt_d, residual, ld_res, scale, shift, out, ld_out);
   else
-    n2p_attend_kernel<int, 32><<<grid, 256, 0, st>>>(q, k, v, ld, (const int*)idx, N, C, K, lph, 0.f, sqrt_d, out, ld_out);
+    n2p_attend_kernel<int, 32><<<grid, 256, 0, st>>>(q, k, v, ld, (const int*)idx, N, C, K, lph, sqrt_d, residual, ld_res, scale, shift, out, ld_out);
   SAMBLE_LAUNCHED("n2p_attend_kernel");
   return SAMBLE_OK;
 }

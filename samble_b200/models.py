@@ -47,7 +47,7 @@ class STN(nn.Module):
 
     def _tail(self, x: Tensor) -> Tensor:
         B = x.size(0)
-        x = self.conv3(x).max(dim=-1, keepdim=False)[0]
+        x = (self.conv3(x) if self.training else blocks.cbl(self.conv3, x)).max(dim=-1, keepdim=False)[0]
         x = self.dp2(self.linear2(self.dp1(self.linear1(x))))
         return self.transform(x).view(B, 3, 3)
 
@@ -148,15 +148,27 @@ class ShapeNetModel(nn.Module):
             trans = self.STN.forward_cloud(x, 32)
             x = torch.bmm(x.transpose(2, 1), trans).transpose(2, 1).contiguous()
         f = self.block(x)                                                     # (B,C,N)
-        g = self.conv(f)
-        g = torch.cat([g.max(dim=-1, keepdim=True)[0], g.mean(dim=-1, keepdim=True), self.conv1(category_id)], dim=1)
-        # conv2 over cat([g.repeat(N), f]) == W_g g (per cloud) + W_f f (per point)
-        w2 = self.conv2[0].weight
-        ng = g.shape[1]
-        y = F.conv1d(f, w2[:, ng:]) + F.conv1d(g, w2[:, :ng])
-        y = self.conv2[2](self.conv2[1](y))
-        y = self.dp2(self.conv3(self.dp1(y)))
-        y = self.conv4(y)
+        if self.training:
+            g = self.conv(f)
+            g = torch.cat([g.max(dim=-1, keepdim=True)[0], g.mean(dim=-1, keepdim=True), self.conv1(category_id)], dim=1)
+            w2 = self.conv2[0].weight
+            ng = g.shape[1]
+            y = F.conv1d(f, w2[:, ng:]) + F.conv1d(g, w2[:, :ng])
+            y = self.conv2[2](self.conv2[1](y))
+            y = self.dp2(self.conv3(self.dp1(y)))
+            y = self.conv4(y)
+        else:
+            # head on the tensor cores (linear_tc.cu); BatchNorms folded; conv2 over cat([g.repeat(N), f]) ==
+            # W_g g (one vector per cloud, folded into a per-cloud shift) + W_f f (per point)
+            g = blocks.cbl(self.conv, f)
+            g = torch.cat([g.max(dim=-1, keepdim=True)[0], g.mean(dim=-1, keepdim=True), self.conv1(category_id)], dim=1)
+            w2 = self.conv2[0].weight
+            ng = g.shape[1]
+            a2, b2 = blocks.folded(self.conv2[1])
+            gv = F.conv1d(g, w2[:, :ng]).squeeze(-1)                          # (B,1024)
+            y = ops.linear(f, w2[:, ng:, 0], x_layout="bcn", out_layout="bcn", scale=a2, shift=gv * a2 + b2, lrelu=True)
+            y = blocks.cbl(self.conv3, y)
+            y = ops.linear(y, self.conv4.weight, x_layout="bcn", out_layout="bcn")
         return (y, trans) if self.stn_regularization_loss_factor > 0 else y
 
 

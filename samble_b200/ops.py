@@ -172,6 +172,73 @@ def gather_by_idx(pcd: Tensor, idx: Tensor) -> Tensor:
 # ------------------------------------------------------------------ fused block cores
 
 
+def linear(x: Tensor, weight: Tensor, *, x_layout: str = "rows", out_layout: str = "rows", scale: Optional[Tensor] = None,
+           shift: Optional[Tensor] = None, lrelu: bool = False, residual: Optional[Tensor] = None,
+           residual_first: bool = False, residual_layout: Optional[str] = None) -> Tensor:
+    """Point-wise linear layer on the tensor cores, fp32-class accuracy (csrc/linear_tc.cu).
+
+    x: 'rows' -> (..., K) with unit inner stride (leading dims flattened, one common row stride), or
+       'bcn'  -> (B, K, P) contiguous channel-major cloud.
+    weight: (Nout, K[,1[,1]]).  scale: (Nout,), shift: (Nout,) or per cloud (B, Nout).
+    out_layout 'rows' -> (..., Nout) ; 'bcn' -> (B, Nout, P).  residual_layout defaults to out_layout.
+    y = ((x W^T [+ residual if residual_first]) * scale + shift) -> LeakyReLU(0.2) if lrelu [-> + residual]."""
+    dev = L.need_cuda(x, weight, scale, shift, residual)
+    L.no_grad_check(x, weight)
+    w = _f32(weight, "weight").flatten(1)
+    if w.stride(1) != 1:
+        w = w.contiguous()
+    Nout, K = w.shape
+    if x_layout == "bcn":
+        x = _f32(x, "x").contiguous()
+        B, Kx, P = x.shape
+        M, ldx, lead = B * P, 0, None
+    else:
+        x = _f32(x, "x")
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        lead, Kx = x.shape[:-1], x.shape[-1]
+        x2 = x.reshape(-1, Kx) if x.dim() != 2 else x
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        x, M, ldx = x2, x2.shape[0], x2.stride(0)
+        B, P = (lead[0], M // lead[0]) if len(lead) >= 2 else (1, M)
+    if Kx != K:
+        raise RuntimeError(f"linear: x has {Kx} channels, weight expects {K}")
+    if out_layout == "bcn":
+        out = torch.empty(B, Nout, P, dtype=torch.float32, device=dev)
+        ldo = 0
+    else:
+        out = torch.empty(*(lead if lead is not None else (B, P)), Nout, dtype=torch.float32, device=dev)
+        ldo = Nout
+    shift_ldb = 0
+    if shift is not None:
+        shift = _f32(shift, "shift").contiguous()
+        if shift.dim() == 2:
+            shift_ldb = Nout
+    if scale is not None:
+        scale = _f32(scale, "scale").contiguous()
+    ldr = 0
+    res_layout = residual_layout or out_layout
+    if residual is not None:
+        residual = _f32(residual, "residual")
+        want = (B, Nout, P) if res_layout == "bcn" else (M, Nout)
+        if (tuple(residual.shape) != want) if res_layout == "bcn" else (residual.numel() != M * Nout or residual.shape[-1] != Nout):
+            raise RuntimeError(f"linear: residual shape {tuple(residual.shape)} does not match layout '{res_layout}' of a "
+                               f"{M} x {Nout} result")
+        if res_layout == "bcn":
+            residual = residual.contiguous()
+        else:
+            if residual.stride(-1) != 1:
+                residual = residual.contiguous()
+            r2 = residual.reshape(-1, Nout)
+            residual, ldr = r2, r2.stride(0)
+    L.check(L.lib().samble_linear(L.ptr(x), ldx, 1 if x_layout == "bcn" else 0, L.ptr(w), w.stride(0), L.ptr(scale), L.ptr(shift),
+                                  shift_ldb, 1 if lrelu else 0, L.ptr(residual), ldr, 1 if res_layout == "bcn" else 0,
+                                  1 if residual_first else 0, L.ptr(out), ldo,
+                                  1 if out_layout == "bcn" else 0, M, K, Nout, P, L.stream()), "samble_linear")
+    return out
+
+
 def edge_mlp_max(pr: Tensor, idx: Tensor, w2: Tensor, b2: Tensor) -> Tensor:
     """Fused EdgeConv core (csrc/edgeconv.cu): pr (B,N,2*C1) = [P'|R'] point projections, idx (B,N,K),
     w2 (C2,C1), b2 (C2) -> (B,C2,N).  models/embedding.py:29-39 after folding eval-mode BatchNorm."""
@@ -185,17 +252,24 @@ def edge_mlp_max(pr: Tensor, idx: Tensor, w2: Tensor, b2: Tensor) -> Tensor:
     return out
 
 
-def n2p_attend(qkv: Tensor, idx: Tensor, heads: int) -> Tensor:
+def n2p_attend(qkv: Tensor, idx: Tensor, heads: int, residual: Optional[Tensor] = None,
+               scale: Optional[Tensor] = None, shift: Optional[Tensor] = None) -> Tensor:
     """qkv (B,N,3C) point-major [q|k|v] projections of the points; idx (B,N,K) -> (B,N,C).
-    Core of models/attention.py:165-185,207-250 with the k/v convolutions hoisted (attention.cu)."""
-    dev = L.need_cuda(qkv, idx)
+    Core of models/attention.py:165-185,207-250 with the k/v convolutions hoisted (attention.cu).
+    With residual (B,N,C) / scale,shift (C,): returns (residual + attention) * scale + shift (folded bn1, :187)."""
+    dev = L.need_cuda(qkv, idx, residual, scale, shift)
     B, N, C3 = qkv.shape
     Cc = C3 // 3
     K = idx.shape[-1]
     out = torch.empty(B, N, Cc, dtype=torch.float32, device=dev)
     q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+    if residual is not None:
+        residual = residual.contiguous()
+    if scale is not None:
+        scale, shift = scale.contiguous(), shift.contiguous()
     L.check(L.lib().samble_n2p_attend(L.ptr(q), L.ptr(k), L.ptr(v), C3, L.ptr(idx), _idx_bits(idx), B, N, Cc, K, heads,
-                                      L.ptr(out), Cc, L.stream()), "samble_n2p_attend")
+                                      L.ptr(residual), Cc, L.ptr(scale), L.ptr(shift), L.ptr(out), Cc, L.stream()),
+            "samble_n2p_attend")
     return out
 
 

@@ -39,3 +39,54 @@ def test_tc_gemm_selftest_nonswizzled_extra_k_step():
     err = (D.double() - ref).abs().max().item()
     print(f"ext: max|D-tf32trunc| = {err:.3e}")
     assert err < 1e-3
+
+
+LIN_CASES = [  # (B, P, K, Nout, x_layout, out_layout, scale, shift, lrelu, residual, res_first)
+    (2, 300, 128, 384, "rows", "rows", False, None, False, False, False),
+    (2, 2048, 128, 512, "rows", "rows", True, "shared", True, False, False),
+    (3, 257, 512, 128, "rows", "bcn", True, "shared", False, True, True),
+    (2, 1000, 128, 1024, "bcn", "bcn", True, "cloud", True, False, False),
+    (1, 130, 64, 128, "bcn", "rows", False, "shared", False, True, False),
+    (2, 64, 1024, 256, "bcn", "bcn", True, "shared", True, False, False),
+    (1, 77, 256, 50, "bcn", "bcn", False, None, False, False, False),
+    (2, 96, 6, 64, "rows", "rows", False, "shared", False, False, False),
+    (1, 128, 100, 200, "rows", "rows", True, None, True, True, False),
+    (2, 515, 512, 128, "rows", "bcn", True, "shared", False, "rows", True),      # the N2P feed-forward tail
+]
+
+
+@pytest.mark.parametrize("case", LIN_CASES, ids=[f"B{c[0]}_P{c[1]}_K{c[2]}_N{c[3]}_{c[4]}_{c[5]}" for c in LIN_CASES])
+def test_linear_3xtf32_matches_fp64(case):
+    from samble_b200 import ops
+
+    B, P, K, Nout, xl, ol, use_scale, shift_kind, lrelu, use_res, res_first = case
+    g = torch.Generator().manual_seed(B * 1000 + P + K)
+    x_rows = torch.randn(B, P, K, generator=g) * 2
+    w = torch.randn(Nout, K, generator=g) / K ** 0.5
+    scale = torch.rand(Nout, generator=g) + 0.5 if use_scale else None
+    shift = None if shift_kind is None else (torch.randn(Nout, generator=g) if shift_kind == "shared" else torch.randn(B, Nout, generator=g))
+    res_rows = torch.randn(B, P, Nout, generator=g) if use_res else None
+    ref = x_rows.double() @ w.double().t()
+    if use_res and res_first:
+        ref = ref + res_rows.double()
+    if scale is not None:
+        ref = ref * scale.double()
+    if shift is not None:
+        ref = ref + (shift.double() if shift.dim() == 1 else shift.double().unsqueeze(1))
+    if lrelu:
+        ref = torch.where(ref > 0, ref, 0.2 * ref)
+    if use_res and not res_first:
+        ref = ref + res_rows.double()
+    x = x_rows.cuda() if xl == "rows" else x_rows.transpose(1, 2).contiguous().cuda()
+    rl = use_res if isinstance(use_res, str) else ol
+    res = None if res_rows is None else (res_rows.cuda() if rl == "rows" else res_rows.transpose(1, 2).contiguous().cuda())
+    y = ops.linear(x, w.cuda(), x_layout=xl, out_layout=ol, scale=None if scale is None else scale.cuda(),
+                   shift=None if shift is None else shift.cuda(), lrelu=lrelu, residual=res, residual_first=res_first,
+                   residual_layout=rl)
+    torch.cuda.synchronize()
+    y_rows = y if ol == "rows" else y.transpose(1, 2)
+    assert tuple(y_rows.shape) == (B, P, Nout)
+    err = (y_rows.double().cpu() - ref).abs().max().item()
+    fp32 = (x_rows @ w.t()).double()                    # what a plain fp32 GEMM on the CPU gives, for scale
+    print(f"max err vs fp64 {err:.2e}; an fp32 CPU GEMM is off by {(fp32 - x_rows.double() @ w.double().t()).abs().max().item():.2e}")
+    assert err < 2e-5 * max(1.0, ref.abs().max().item())
