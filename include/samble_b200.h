@@ -59,6 +59,10 @@ int samble_selftest_tc_gemm(const float* A, const float* B, int K, float* D, con
                             const float* Bx /* 128x8 or NULL: adds Ax*Bx^T from a non-swizzled slice */,
                             samble_stream_t stream);
 
+/* issue-rate probe: `ctas` CTAs each issue iters*4 back-to-back kind::tf32 128 x n_tile x 8 MMAs on resident smem tiles;
+ * cycles_out[cta] = SM cycles from first issue to completion (measured tensor-pipe ceiling of the SS form). */
+int samble_selftest_mma_rate(int n_tile, int iters, int ctas, long long* cycles_out, samble_stream_t stream);
+
 /* ---------------------------------------------------------------- kNN ----------
  * utils/ops.py:17-44  knn(a, b, k) -> (distance, idx).
  * a: queries, b: candidates; element (bi, n, c) lives at base + bi*a_sb + n*a_sn + c*a_sc
@@ -109,10 +113,12 @@ int samble_neighbor_mask(const void* idx, int idx_bits, int B, int N, int K, flo
  * (3xTF32 operand split) and a fused epilogue:
  *   acc = X W^T ;  y = [ (acc (+res if residual_first)) * scale[c] + shift[b?][c] ] -> LeakyReLU(0.2) if lrelu -> (+res)
  * X: M x K.  row-major (x_channel_major=0): X[m*ldx + k]; channel-major: X[(b*K + k)*P + n] with m = b*P + n,
- * P = points_per_cloud.  W: Nout x K row-major (the stored conv/linear weight).  scale/shift: [Nout] or NULL;
+ * P = points_per_cloud.  W: Nout x K row-major (the stored conv/linear weight), rows zero-padded to a multiple of 4
+ * columns; W_lo = W - tf32_trunc(W) (samble_split_tf32; weights are constants, split once).  scale/shift: [Nout] or NULL;
  * shift_cloud_stride != 0 selects a per-cloud shift row.  residual and out are each row-major (ld) or
  * channel-major (B, Nout, P). */
-int samble_linear(const float* X, long long ldx, int x_channel_major, const float* W, long long ldw,
+int samble_split_tf32(const float* x, float* lo, long long n, samble_stream_t stream);
+int samble_linear(const float* X, long long ldx, int x_channel_major, const float* W, const float* W_lo, long long ldw,
                   const float* scale, const float* shift, long long shift_cloud_stride, int lrelu,
                   const float* residual, long long ldr, int residual_channel_major, int residual_first,
                   float* out, long long ldo, int out_channel_major, int M, int K, int Nout, int points_per_cloud,

@@ -29,6 +29,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_profile_enable": (None, (_i,)),
     "samble_profile_report": (_i, (C.c_char_p, _sz)),
     "samble_selftest_tc_gemm": (_i, (_p, _p, _i, _p, _p, _p, _p)),
+    "samble_selftest_mma_rate": (_i, (_i, _i, _i, _p, _p)),
     "samble_set_knn_mode": (None, (_i,)),
     "samble_knn_workspace_bytes": (_sz, (_i, _i, _i, _i)),
     "samble_knn": (_i, (_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _p, _i, _p, _p, _sz, _p)),
@@ -36,7 +37,8 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_group": (_i, (_p, _p, _i, _i, _i, _i, _i, _i, _p, _p)),
     "samble_gather_by_idx": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
     "samble_neighbor_mask": (_i, (_p, _i, _i, _i, _i, _p, _p)),
-    "samble_linear": (_i, (_p, _ll, _i, _p, _ll, _p, _p, _ll, _i, _p, _ll, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p)),
+    "samble_split_tf32": (_i, (_p, _p, _ll, _p)),
+    "samble_linear": (_i, (_p, _ll, _i, _p, _p, _ll, _p, _p, _ll, _i, _p, _ll, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p)),
     "samble_edge_mlp_max": (_i, (_p, _ll, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p)),
     "samble_n2p_attend": (_i, (_p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p, _p, _ll, _p)),
     "samble_ds_row_stats": (_i, (_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p)),

@@ -19,7 +19,8 @@
 namespace samble {
 
 constexpr int kLinThreads = 288;
-constexpr int kLinStages = 2;
+constexpr int kLinStages = 3;     // smem ring depth; loads run kLinAhead stages ahead of the split/arrive step
+constexpr int kLinAhead = 2;
 // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the
 // accumulation chain (measured: 9e-5 abs at K=1024 vs 2e-5 at K=128 on O(10) outputs).  Chains are therefore cut
 // every kLinChain K-blocks: each chunk gets its own TMEM accumulator and the epilogue adds the chunks in fp32.
@@ -34,6 +35,7 @@ struct LinCfg {
 struct LinArgs {
   const float* X; long long ldx;      // row-major: X[m*ldx + k];  channel-major (x_cm): X[(b*K + k)*npc + n], m = b*npc + n
   const float* W; long long ldw;      // Nout x K
+  const float* Wlo;                   // W - tf32_trunc(W), same shape/stride (weights are constants: split once on the host side)
   const float* scale;                 // [Nout] or null (=1)
   const float* shift;                 // [Nout] (+ b*shift_ldb) or null (=0)
   const float* residual; long long ldr;   // same indexing as out, or null
@@ -55,6 +57,9 @@ __device__ __forceinline__ void split_store(uint8_t* hi_tile, uint8_t* lo_tile, 
   *reinterpret_cast<float4*>(lo_tile + off) = lo;
 }
 
+// Persistent: CTA c walks output tiles c, c+grid, ... (tile = (m-tile, n-tile), n fastest so that neighbouring CTAs
+// share the X tile in L2).  The loader streams K-block stages continuously across tile boundaries, the MMA issuer
+// alternates between two TMEM accumulator sets, and the epilogue of tile i overlaps the MMAs of tile i+1.
 template <int NT>
 __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(LinArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -63,24 +68,30 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(LinArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)kLinStages * Cfg::kStageBytes);
   uint64_t* full = bars;                  // [kLinStages] 128 loader arrivals
   uint64_t* empty = bars + kLinStages;    // [kLinStages] tcgen05.commit
-  uint64_t* done = empty + kLinStages;    // accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* tfull = empty + kLinStages;   // [2] accumulator set complete (tcgen05.commit)
+  uint64_t* tempty = tfull + 2;           // [2] accumulator set drained (128 epilogue arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * NT;
   const int nkb = (a.K + 31) / 32;
+  const int mtiles = (a.M + 127) / 128, ntiles = (a.Nout + NT - 1) / NT;
+  const int total = mtiles * ntiles;
+  const int nacc = (nkb + kLinChain - 1) / kLinChain;      // accumulation chunks per tile (host: nacc * NT <= 512)
+  const int nsets = (2 * nacc * NT <= 512) ? 2 : 1;        // double-buffer the accumulators when TMEM allows
+  uint32_t tcols = 32;
+  while (tcols < (uint32_t)(nsets * nacc * NT)) tcols <<= 1;
 
   if (tid == 0) {
     for (int s = 0; s < kLinStages; ++s) {
-      tc::mbar_init(&full[s], 128);
+      tc::mbar_init(&full[s], 4);        // one arrival per loader warp
       tc::mbar_init(&empty[s], 1);
     }
-    tc::mbar_init(done, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&tfull[i], 1);
+      tc::mbar_init(&tempty[i], 4);      // one arrival per epilogue warp
+    }
     tc::mbar_init_fence();
   }
-  const int nacc = (nkb + kLinChain - 1) / kLinChain;                 // host guarantees nacc * NT <= 512
-  uint32_t tcols = 32;
-  while (tcols < (uint32_t)(nacc * NT)) tcols <<= 1;
   if (warp == 0) tc::tmem_alloc(tmem_slot, tcols);
   tc::tc_fence_before();
   __syncthreads();
@@ -89,166 +100,206 @@ __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(LinArgs a) {
 
   if (warp >= 5) {
     // ================= loaders =================
+    // Raw operand tiles ARE the "hi" tiles (the MMA ignores the low 13 mantissa bits), so they are plain async copies.
+    // Row-major X: cp.async kLinAhead stages ahead, then this thread re-reads ITS OWN chunks from smem, writes
+    // lo = x - trunc(x), fences to the async proxy and arrives.  Channel-major X: coalesced scalar loads, one stage
+    // prefetched in registers.  W and W_lo: cp.async (W_lo was precomputed).
     const int lt = tid - 160;
-    const bool vec = (a.ldx % 4 == 0) && (a.ldw % 4 == 0) && (a.K % 4 == 0) &&
-                     ((reinterpret_cast<uintptr_t>(a.X) | reinterpret_cast<uintptr_t>(a.W)) % 16 == 0);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % kLinStages, ph = (kb / kLinStages) & 1;
-      tc::mbar_wait(&empty[s], ph ^ 1);
-      uint8_t* st = base + (size_t)s * Cfg::kStageBytes;
-      uint8_t *xh = st, *xl = st + 16384, *wh = st + 32768, *wl = st + 32768 + NT * 128;
+    const int ntl = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+    const int G = ntl * nkb;
+    float pre[32];
+    auto tile_of = [&](int g, int& m0, int& n0, int& kb) {
+      const int tile = blockIdx.x + (g / nkb) * gridDim.x;
+      m0 = (tile / ntiles) * 128;
+      n0 = (tile % ntiles) * NT;
+      kb = g % nkb;
+    };
+    auto prefetch_cm = [&](int g) {
+      int m0, n0, kb;
+      tile_of(g, m0, n0, kb);
+      const int m = m0 + lt;
+      const bool ok = m < a.M;
+      const float* src = a.X + ((ok ? m / a.npc : 0) * (long long)a.K) * a.npc + (ok ? m % a.npc : 0);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) pre[c] = (ok && kb * 32 + c < a.K) ? __ldg(src + (long long)(kb * 32 + c) * a.npc) : 0.f;
+    };
+    auto issue = [&](int g) {
+      int m0, n0, kb;
+      tile_of(g, m0, n0, kb);
+      uint8_t* st = base + (size_t)(g % kLinStages) * Cfg::kStageBytes;
+      uint8_t *xh = st, *wh = st + 32768, *wl = st + 32768 + NT * 128;
       const int k0 = kb * 32;
-      auto load4 = [&](const float* src, long long ld, int row, int rows_valid, int ch) -> float4 {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int k = k0 + ch * 4;
-        if (row < rows_valid && k < a.K) {
-          const float* p = src + (long long)row * ld + k;
-          if (vec) v = __ldg(reinterpret_cast<const float4*>(p));
-          else {
-            v.x = __ldg(p);
-            if (k + 1 < a.K) v.y = __ldg(p + 1);
-            if (k + 2 < a.K) v.z = __ldg(p + 2);
-            if (k + 3 < a.K) v.w = __ldg(p + 3);
-          }
-        }
-        return v;
-      };
-      // X K-block: 128 rows x 8 chunks
       if (!a.x_cm) {
-        float4 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int p = lt + 128 * i;
-          v[i] = load4(a.X + (long long)m0 * a.ldx, a.ldx, p >> 3, a.M - m0, p & 7);
+          const int p = lt + 128 * i, row = p >> 3, ch = p & 7;
+          const bool ok = (m0 + row) < a.M && (k0 + ch * 4) < a.K;
+          cp_async16(xh + tc::sw128_offset(row, ch), a.X + (long long)(ok ? m0 + row : 0) * a.ldx + (ok ? k0 + ch * 4 : 0), ok);
         }
+      }
+      const float* Wt = a.W + (long long)n0 * a.ldw;
+      const float* Wl = a.Wlo + (long long)n0 * a.ldw;
+#pragma unroll
+      for (int i = 0; i < NT / 16; ++i) {
+        const int p = lt + 128 * i, row = p >> 3, ch = p & 7;
+        const bool ok = (n0 + row) < a.Nout && (k0 + ch * 4) < a.K;
+        const long long off = (long long)(ok ? row : 0) * a.ldw + (ok ? k0 + ch * 4 : 0);
+        cp_async16(wh + tc::sw128_offset(row, ch), Wt + off, ok);
+        cp_async16(wl + tc::sw128_offset(row, ch), Wl + off, ok);
+      }
+      cp_async_commit();
+    };
+    auto finish = [&](int g) {     // this thread's cp.async groups up to stage g have landed
+      const int s = g % kLinStages;
+      uint8_t* st = base + (size_t)s * Cfg::kStageBytes;
+      uint8_t *xh = st, *xl = st + 16384;
+      if (!a.x_cm) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int p = lt + 128 * i;
-          split_store(xh, xl, p >> 3, p & 7, v[i]);
+          const uint32_t off = tc::sw128_offset(p >> 3, p & 7);
+          const float4 v = *reinterpret_cast<const float4*>(xh + off);
+          float4 lo;
+          lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          *reinterpret_cast<float4*>(xl + off) = lo;
         }
       } else {
-        // channel-major input: thread = row; for each channel the 128 rows of the tile are consecutive points
-        const int m = m0 + lt;
-        const bool ok = m < a.M;
-        const long long bq = ok ? m / a.npc : 0, nq = ok ? m % a.npc : 0;
-        const float* src = a.X + (bq * a.K + k0) * a.npc + nq;
-        float v[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = (ok && k0 + c < a.K) ? __ldg(src + (long long)c * a.npc) : 0.f;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) split_store(xh, xl, lt, ch, make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]));
-      }
-      // W K-block: NT rows x 8 chunks
-#pragma unroll
-      for (int j0 = 0; j0 < NT * 8; j0 += 128 * 8) {
-        float4 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int p = j0 + lt + 128 * i;
-          v[i] = p < NT * 8 ? load4(a.W + (long long)n0 * a.ldw, a.ldw, p >> 3, a.Nout - n0, p & 7) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int p = j0 + lt + 128 * i;
-          if (p < NT * 8) split_store(wh, wl, p >> 3, p & 7, v[i]);
-        }
+        for (int ch = 0; ch < 8; ++ch) split_store(xh, xl, lt, ch, make_float4(pre[4 * ch], pre[4 * ch + 1], pre[4 * ch + 2], pre[4 * ch + 3]));
       }
       tc::fence_proxy_async();
-      tc::mbar_arrive(&full[s]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full[s]);
+    };
+    if (a.x_cm && G > 0) prefetch_cm(0);
+    // Software pipeline: stage g-kLinAhead is completed (split + arrive) BEFORE we block on a free slot for stage g,
+    // so the MMAs of the older stage run while the newer loads are being issued.
+    for (int g = 0; g < G + kLinAhead; ++g) {
+      const int fb = g - kLinAhead;
+      if (fb >= 0) {
+        cp_async_wait<kLinAhead - 1>();     // groups issued so far: 0..g-1  ->  group fb has landed
+        finish(fb);
+        if (a.x_cm && fb + 1 < G) prefetch_cm(fb + 1);   // in flight while we wait for the next free stage
+      }
+      if (g < G) {
+        tc::mbar_wait(&empty[g % kLinStages], ((g / kLinStages) & 1) ^ 1);
+        issue(g);
+      } else {
+        cp_async_commit();           // keep the group count in step
+      }
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = tc::instr_desc(2, 128, NT);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kLinStages;
-        tc::mbar_wait(&full[s], (kb / kLinStages) & 1);
+      int g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int set = (nsets == 2) ? (it & 1) : 0;
+        const int use = (nsets == 2) ? (it >> 1) : it;           // how often this set was used before
+        tc::mbar_wait(&tempty[set], (use & 1) ^ 1);
         tc::tc_fence_after();
-        const uint32_t st = tc::smem_u32(base + (size_t)s * Cfg::kStageBytes);
-        const uint64_t xh = tc::smem_desc_sw128(st), xl = tc::smem_desc_sw128(st + 16384);
-        const uint64_t wh = tc::smem_desc_sw128(st + 32768), wl = tc::smem_desc_sw128(st + 32768 + NT * 128);
-        const uint32_t acc = tmem + (kb / kLinChain) * NT;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = g % kLinStages;
+          tc::mbar_wait(&full[s], (g / kLinStages) & 1);
+          tc::tc_fence_after();
+          const uint32_t st = tc::smem_u32(base + (size_t)s * Cfg::kStageBytes);
+          const uint64_t xh = tc::smem_desc_sw128(st), xl = tc::smem_desc_sw128(st + 16384);
+          const uint64_t wh = tc::smem_desc_sw128(st + 32768), wl = tc::smem_desc_sw128(st + 32768 + NT * 128);
+          const uint32_t acc = tmem + (set * nacc + kb / kLinChain) * NT;
 #pragma unroll
-        for (int k8 = 0; k8 < 4; ++k8) {
-          tc::mma_tf32(acc, xh + 2 * k8, wh + 2 * k8, idesc, ((kb % kLinChain) | k8) != 0);
-          tc::mma_tf32(acc, xl + 2 * k8, wh + 2 * k8, idesc, 1);
-          tc::mma_tf32(acc, xh + 2 * k8, wl + 2 * k8, idesc, 1);
+          for (int k8 = 0; k8 < 4; ++k8) {
+            tc::mma_tf32(acc, xh + 2 * k8, wh + 2 * k8, idesc, ((kb % kLinChain) | k8) != 0);
+            tc::mma_tf32(acc, xl + 2 * k8, wh + 2 * k8, idesc, 1);
+            tc::mma_tf32(acc, xh + 2 * k8, wl + 2 * k8, idesc, 1);
+          }
+          tc::mma_commit(&empty[s]);
         }
-        tc::mma_commit(&empty[s]);
+        tc::mma_commit(&tfull[set]);
       }
-      tc::mma_commit(done);
     }
     __syncwarp();
   } else {
     // ================= epilogue: thread = output row =================
-    tc::mbar_wait(done, 0);
-    tc::tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const bool live = m < a.M;
-    long long ob = 0, on = 0;
-    if (a.npc > 0) {
-      ob = (live ? m : 0) / a.npc;
-      on = (live ? m : 0) % a.npc;
-    }
-    const float* shift = a.shift ? a.shift + ob * a.shift_ldb : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < NT; c0 += 32) {
-      float v[32];
-      tc::tmem_ld32(tmem + lane_base + c0, v);      // warp-collective: every lane takes part, stores are predicated
-      for (int ac = 1; ac < nacc; ++ac) {           // add the accumulation chunks in fp32
-        float w[32];
-        tc::tmem_ld32(tmem + lane_base + ac * NT + c0, w);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += w[i];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int set = (nsets == 2) ? (it & 1) : 0;
+      const int use = (nsets == 2) ? (it >> 1) : it;
+      const int m0 = (tile / ntiles) * 128, n0 = (tile % ntiles) * NT;
+      tc::mbar_wait(&tfull[set], use & 1);
+      tc::tc_fence_after();
+      const int m = m0 + warp * 32 + lane;
+      const uint32_t lane_base = ((uint32_t)(warp * 32) << 16) + set * nacc * NT;
+      const bool live = m < a.M;
+      long long ob = 0, on = 0;
+      if (a.npc > 0) {
+        ob = (live ? m : 0) / a.npc;
+        on = (live ? m : 0) % a.npc;
       }
-      if (!live || n0 + c0 >= a.Nout) continue;
-      const bool full32 = n0 + c0 + 32 <= a.Nout;
-      float r[32];
-      if (a.residual) {
-        if (a.res_cm) {
+      const float* shift = a.shift ? a.shift + ob * a.shift_ldb : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem + lane_base + c0, v);      // warp-collective: every lane takes part, stores are predicated
+        for (int ac = 1; ac < nacc; ++ac) {           // add the accumulation chunks in fp32
+          float w[32];
+          tc::tmem_ld32(tmem + lane_base + ac * NT + c0, w);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = (n0 + c0 + i < a.Nout) ? __ldg(a.residual + (ob * a.Nout + n0 + c0 + i) * a.npc + on) : 0.f;
-        } else {
-          const float* rrow = a.residual + (long long)m * a.ldr + n0 + c0;
-          if (full32 && a.ldr % 4 == 0 && reinterpret_cast<uintptr_t>(a.residual) % 16 == 0) {
+          for (int i = 0; i < 32; ++i) v[i] += w[i];
+        }
+        if (!live || n0 + c0 >= a.Nout) continue;
+        const bool full32 = n0 + c0 + 32 <= a.Nout;
+        float r[32];
+        if (a.residual) {
+          if (a.res_cm) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(rrow + i));
-              r[i] = t.x, r[i + 1] = t.y, r[i + 2] = t.z, r[i + 3] = t.w;
+            for (int i = 0; i < 32; ++i) r[i] = (n0 + c0 + i < a.Nout) ? __ldg(a.residual + (ob * a.Nout + n0 + c0 + i) * a.npc + on) : 0.f;
+          } else {
+            const float* rrow = a.residual + (long long)m * a.ldr + n0 + c0;
+            if (full32 && a.ldr % 4 == 0 && reinterpret_cast<uintptr_t>(a.residual) % 16 == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(rrow + i));
+                r[i] = t.x, r[i + 1] = t.y, r[i + 2] = t.z, r[i + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = (n0 + c0 + i < a.Nout) ? __ldg(rrow + i) : 0.f;
             }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = min(n0 + c0 + i, a.Nout - 1);
+          float y = v[i];
+          if (a.residual && a.res_first) y += r[i];
+          if (a.scale) y *= __ldg(a.scale + c);
+          if (shift) y += __ldg(shift + c);
+          if (a.lrelu) y = y > 0.f ? y : 0.2f * y;
+          if (a.residual && !a.res_first) y += r[i];
+          v[i] = y;
+        }
+        if (a.out_cm) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (n0 + c0 + i < a.Nout) a.out[(ob * a.Nout + n0 + c0 + i) * a.npc + on] = v[i];
+        } else {
+          float* orow = a.out + (long long)m * a.ldo + n0 + c0;
+          if (full32 && a.ldo % 4 == 0 && reinterpret_cast<uintptr_t>(a.out) % 16 == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = (n0 + c0 + i < a.Nout) ? __ldg(rrow + i) : 0.f;
+            for (int i = 0; i < 32; ++i)
+              if (n0 + c0 + i < a.Nout) orow[i] = v[i];
           }
         }
       }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int c = min(n0 + c0 + i, a.Nout - 1);
-        float y = v[i];
-        if (a.residual && a.res_first) y += r[i];
-        if (a.scale) y *= __ldg(a.scale + c);
-        if (shift) y += __ldg(shift + c);
-        if (a.lrelu) y = y > 0.f ? y : 0.2f * y;
-        if (a.residual && !a.res_first) y += r[i];
-        v[i] = y;
-      }
-      if (a.out_cm) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (n0 + c0 + i < a.Nout) a.out[(ob * a.Nout + n0 + c0 + i) * a.npc + on] = v[i];
-      } else {
-        float* orow = a.out + (long long)m * a.ldo + n0 + c0;
-        if (full32 && a.ldo % 4 == 0 && reinterpret_cast<uintptr_t>(a.out) % 16 == 0) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n0 + c0 + i < a.Nout) orow[i] = v[i];
-        }
-      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[set]);
     }
   }
   tc::tc_fence_before();
@@ -261,7 +312,8 @@ static int launch_linear(const LinArgs& a, cudaStream_t st) {
   auto kern = linear_tc_kernel<NT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinCfg<NT>::smem) != cudaSuccess)
     return check_launch("linear_tc smem attribute");
-  dim3 grid(ceil_div(a.M, 128), ceil_div(a.Nout, NT));
+  const long long total = (long long)ceil_div(a.M, 128) * ceil_div(a.Nout, NT);
+  const int grid = (int)(total < 148 ? total : 148);       // one persistent CTA per SM
   SAMBLE_PRE(st);
   kern<<<grid, kLinThreads, LinCfg<NT>::smem, st>>>(a);
   SAMBLE_LAUNCHED("linear_tc_kernel");
@@ -272,23 +324,43 @@ static int launch_linear(const LinArgs& a, cudaStream_t st) {
 
 using namespace samble;
 
-extern "C" int samble_linear(const float* X, long long ldx, int x_channel_major, const float* W, long long ldw,
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  }
+}
+
+extern "C" int samble_split_tf32(const float* x, float* lo, long long n, samble_stream_t stream) {
+  SAMBLE_REQUIRE(x && lo && n > 0, "samble_split_tf32: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long g = (n + 255) / 256;
+  SAMBLE_PRE(st);
+  split_tf32_kernel<<<(int)(g > 1184 ? 1184 : g), 256, 0, st>>>(x, lo, n);
+  SAMBLE_LAUNCHED("split_tf32_kernel");
+  return SAMBLE_OK;
+}
+
+extern "C" int samble_linear(const float* X, long long ldx, int x_channel_major, const float* W, const float* W_lo, long long ldw,
                              const float* scale, const float* shift, long long shift_cloud_stride, int lrelu,
                              const float* residual, long long ldr, int residual_channel_major, int residual_first,
                              float* out, long long ldo, int out_channel_major, int M, int K, int Nout,
                              int points_per_cloud, samble_stream_t stream) {
-  SAMBLE_REQUIRE(X && W && out, "samble_linear: null pointer");
+  SAMBLE_REQUIRE(X && W && W_lo && out, "samble_linear: null pointer");
+  SAMBLE_REQUIRE(ldw % 4 == 0 && ldw >= ((K + 3) / 4) * 4 && ((uintptr_t)W | (uintptr_t)W_lo) % 16 == 0,
+                 "samble_linear: weight rows must be 16-byte aligned and zero-padded to a multiple of 4 columns");
+  SAMBLE_REQUIRE(x_channel_major || (ldx % 4 == 0 && ldx >= ((K + 3) / 4) * 4 && (uintptr_t)X % 16 == 0),
+                 "samble_linear: row-major X needs 16-byte aligned rows, zero-padded to a multiple of 4 columns");
   SAMBLE_REQUIRE(M > 0 && K > 0 && Nout > 0, "samble_linear: bad shape M=%d K=%d Nout=%d", M, K, Nout);
   const bool need_npc = x_channel_major || out_channel_major || shift_cloud_stride != 0 || (residual && residual_channel_major);
   SAMBLE_REQUIRE(!need_npc || (points_per_cloud > 0 && M % points_per_cloud == 0),
                  "samble_linear: M=%d is not a whole number of clouds of %d points", M, points_per_cloud);
   SAMBLE_REQUIRE(ceil_div(Nout, 64) <= 65535, "samble_linear: Nout too large");
-  LinArgs a{X, ldx, W, ldw, scale, shift, residual, ldr, out, ldo, M, K, Nout, need_npc ? points_per_cloud : 0,
+  LinArgs a{X, ldx, W, ldw, W_lo, scale, shift, residual, ldr, out, ldo, M, K, Nout, need_npc ? points_per_cloud : 0,
             lrelu, x_channel_major, out_channel_major, residual_first, residual_channel_major, shift_cloud_stride};
   cudaStream_t st = (cudaStream_t)stream;
   const int nacc = ceil_div(ceil_div(K, 32), kLinChain);
   SAMBLE_REQUIRE(nacc * 64 <= 512, "samble_linear: K=%d too large (max %d)", K, 8 * kLinChain * 32);
-  if (Nout > 128 && nacc * 256 <= 512) return launch_linear<256>(a, st);
   if (Nout > 64 && nacc * 128 <= 512) return launch_linear<128>(a, st);
   return launch_linear<64>(a, st);
 }

@@ -32,6 +32,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);                        // back off: hundreds of threads poll a handful of barriers
     if (clock64() - t0 > 4000000000LL) {   // ~2 s
       printf("samble: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();

@@ -88,3 +88,59 @@ extern "C" int samble_selftest_tc_gemm(const float* A, const float* B, int K, fl
   SAMBLE_LAUNCHED("tc_gemm_selftest_kernel");
   return SAMBLE_OK;
 }
+
+// ---- MMA issue-rate probe: every CTA issues `iters` x 4 back-to-back kind::tf32 128xNx8 MMAs on fixed smem tiles ----
+namespace samble {
+template <int NT>
+__global__ void __launch_bounds__(128) tc_mma_rate_kernel(int iters, long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int p = tid; p < (16384 + NT * 128) / 16; p += 128) reinterpret_cast<float4*>(base)[p] = make_float4(1.f, 0.5f, 0.25f, 2.f);
+  tc::fence_proxy_async();
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, NT < 32 ? 32 : NT);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = tc::instr_desc(2, 128, NT);
+    const uint64_t ad = tc::smem_desc_sw128(tc::smem_u32(base)), bd = tc::smem_desc_sw128(tc::smem_u32(base + 16384));
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+      for (int k8 = 0; k8 < 4; ++k8) tc::mma_tf32(tmem, ad + 2 * k8, bd + 2 * k8, idesc, 1);
+    tc::mma_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    cycles_out[blockIdx.x] = clock64() - t0;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, NT < 32 ? 32 : NT);
+}
+}  // namespace samble
+
+extern "C" int samble_selftest_mma_rate(int n_tile, int iters, int ctas, long long* cycles_out, samble_stream_t stream) {
+  SAMBLE_REQUIRE(cycles_out && iters > 0 && ctas > 0 && (n_tile == 64 || n_tile == 128 || n_tile == 256), "samble_selftest_mma_rate: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem = 16384 + (size_t)n_tile * 128 + 1024;
+  SAMBLE_PRE(st);
+  if (n_tile == 64) {
+    cudaFuncSetAttribute(tc_mma_rate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_mma_rate_kernel<64><<<ctas, 128, smem, st>>>(iters, cycles_out);
+  } else if (n_tile == 128) {
+    cudaFuncSetAttribute(tc_mma_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_mma_rate_kernel<128><<<ctas, 128, smem, st>>>(iters, cycles_out);
+  } else {
+    cudaFuncSetAttribute(tc_mma_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_mma_rate_kernel<256><<<ctas, 128, smem, st>>>(iters, cycles_out);
+  }
+  SAMBLE_LAUNCHED("tc_mma_rate_kernel");
+  return SAMBLE_OK;
+}

@@ -172,6 +172,34 @@ def gather_by_idx(pcd: Tensor, idx: Tensor) -> Tensor:
 # ------------------------------------------------------------------ fused block cores
 
 
+_W_SPLIT: dict = {}
+
+
+def _split_weight(weight: Tensor):
+    """(W padded to a multiple of 4 columns, W_lo = W - tf32_trunc(W)); cached per weight tensor and in-place version."""
+    key = (weight.data_ptr(), tuple(weight.shape), tuple(weight.stride()))
+    hit = _W_SPLIT.get(key)
+    if hit is not None and hit[0] == weight._version:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        w = _f32(weight, "weight").detach().flatten(1)
+        Nout, K = w.shape
+        K4 = (K + 3) // 4 * 4
+        if K4 != K or w.stride(1) != 1 or w.stride(0) % 4 != 0 or w.data_ptr() % 16 != 0:
+            wp = torch.zeros(Nout, K4, dtype=torch.float32, device=w.device)
+            wp[:, :K] = w
+            w = wp
+        lo = torch.empty(w.shape[0], w.stride(0), dtype=torch.float32, device=w.device)[:, : w.shape[1]]
+        if w.is_contiguous():
+            L.check(L.lib().samble_split_tf32(L.ptr(w), L.ptr(lo), w.numel(), L.stream()), "samble_split_tf32")
+        else:                       # strided view (e.g. a column slice of a bigger weight): split row by row via torch
+            lo.copy_(w - (w.view(torch.int32) & -8192).view(torch.float32))
+    if len(_W_SPLIT) > 4096:
+        _W_SPLIT.clear()
+    _W_SPLIT[key] = (weight._version, w, lo)
+    return w, lo
+
+
 def linear(x: Tensor, weight: Tensor, *, x_layout: str = "rows", out_layout: str = "rows", scale: Optional[Tensor] = None,
            shift: Optional[Tensor] = None, lrelu: bool = False, residual: Optional[Tensor] = None,
            residual_first: bool = False, residual_layout: Optional[str] = None) -> Tensor:
@@ -184,10 +212,8 @@ def linear(x: Tensor, weight: Tensor, *, x_layout: str = "rows", out_layout: str
     y = ((x W^T [+ residual if residual_first]) * scale + shift) -> LeakyReLU(0.2) if lrelu [-> + residual]."""
     dev = L.need_cuda(x, weight, scale, shift, residual)
     L.no_grad_check(x, weight)
-    w = _f32(weight, "weight").flatten(1)
-    if w.stride(1) != 1:
-        w = w.contiguous()
-    Nout, K = w.shape
+    w, w_lo = _split_weight(weight)
+    Nout, K = weight.shape[0], weight[0].numel()
     if x_layout == "bcn":
         x = _f32(x, "x").contiguous()
         B, Kx, P = x.shape
@@ -200,6 +226,8 @@ def linear(x: Tensor, weight: Tensor, *, x_layout: str = "rows", out_layout: str
         x2 = x.reshape(-1, Kx) if x.dim() != 2 else x
         if x2.stride(1) != 1:
             x2 = x2.contiguous()
+        if Kx % 4 != 0 or x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:     # cp.async rows must be 16-byte chunks
+            x2 = torch.nn.functional.pad(x2, (0, (-Kx) % 4)).contiguous()
         x, M, ldx = x2, x2.shape[0], x2.stride(0)
         B, P = (lead[0], M // lead[0]) if len(lead) >= 2 else (1, M)
     if Kx != K:
@@ -232,7 +260,7 @@ def linear(x: Tensor, weight: Tensor, *, x_layout: str = "rows", out_layout: str
                 residual = residual.contiguous()
             r2 = residual.reshape(-1, Nout)
             residual, ldr = r2, r2.stride(0)
-    L.check(L.lib().samble_linear(L.ptr(x), ldx, 1 if x_layout == "bcn" else 0, L.ptr(w), w.stride(0), L.ptr(scale), L.ptr(shift),
+    L.check(L.lib().samble_linear(L.ptr(x), ldx, 1 if x_layout == "bcn" else 0, L.ptr(w), L.ptr(w_lo), w.stride(0), L.ptr(scale), L.ptr(shift),
                                   shift_ldb, 1 if lrelu else 0, L.ptr(residual), ldr, 1 if res_layout == "bcn" else 0,
                                   1 if residual_first else 0, L.ptr(out), ldo,
                                   1 if out_layout == "bcn" else 0, M, K, Nout, P, L.stream()), "samble_linear")

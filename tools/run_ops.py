@@ -48,3 +48,11 @@ if "rowstats" in which:
 if os.environ.get("PROFILE", "0") == "1":
     for kname, (n, ms) in sorted(L.profile_report().items(), key=lambda kv: -kv[1][1]):
         print(f"  {kname:28s} {n:5d} launches  {ms / n * 1e3:9.1f} us avg")
+
+if "linear" in which:
+    for (M, K, Nn) in [(B * N, 128, 384), (B * N, 128, 512), (B * N, 512, 128), (B * N, 128, 1024), (B * N, 1024, 256), (B * N // 2, 128, 384), (B * N, 64, 128)]:
+        xx = torch.randn(M, K, device=dev)
+        ww = torch.randn(Nn, K, device=dev)
+        bench(f"lin {K}->{Nn}", lambda: ops.linear(xx, ww), 2.0 * M * K * Nn)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        bench(f" cublas fp32", lambda: xx @ ww.t(), 2.0 * M * K * Nn)
