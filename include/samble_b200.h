@@ -130,7 +130,10 @@ int samble_linear(const float* X, long long ldx, int x_channel_major, const floa
  *   pr (B,N,ld_pr) point-major = [P' | R'],  P'_i = a1*((W1a-W1b) x_i) + b1,  R'_j = a1*(W1b x_j)
  * (a1,b1 = folded BN1), w2 (C2,C1) = diag(a2) W2, b2 (C2) = folded BN2 shift.  idx (B,N,K) from the kNN.
  * out (B,C2,N) channel-major = lrelu(max_k (w2 . lrelu(P'_i + R'_idx[i,k]) + b2)).
- * Limits: K <= 32, C1 % 4 == 0, C1 <= 128, C2 in {32,64,128}. */
+ * Limits: K <= 32, C1 % 4 == 0, C1 <= 128, C2 in {32,64,128}.
+ * C1 % 32 == 0 and C2 in {64,128} run on the tensor cores (tcgen05, 3xTF32 split, fp32-class accuracy);
+ * samble_set_edge_mode(1) forces the FFMA kernel (used by the tests as the cross-check). */
+void samble_set_edge_mode(int mode);
 int samble_edge_mlp_max(const float* pr, long long ld_pr, const void* idx, int idx_bits, const float* w2,
                         const float* b2, int B, int N, int K, int C1, int C2, float* out, samble_stream_t stream);
 

@@ -39,6 +39,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_neighbor_mask": (_i, (_p, _i, _i, _i, _i, _p, _p)),
     "samble_split_tf32": (_i, (_p, _p, _ll, _p)),
     "samble_linear": (_i, (_p, _ll, _i, _p, _p, _ll, _p, _p, _ll, _i, _p, _ll, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p)),
+    "samble_set_edge_mode": (None, (_i,)),
     "samble_edge_mlp_max": (_i, (_p, _ll, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p)),
     "samble_n2p_attend": (_i, (_p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p, _p, _ll, _p)),
     "samble_ds_row_stats": (_i, (_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p)),

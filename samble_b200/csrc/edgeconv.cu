@@ -115,9 +115,18 @@ static int launch_edge_mlp(const float* pr, long long ld_pr, const I* idx, const
   return SAMBLE_OK;
 }
 
+// tensor-core form (edgeconv_tc.cu)
+bool edge_tc_eligible(int K, int C1, int C2);
+template <class I>
+int edge_mlp_tc(const float* pr, long long ld_pr, const I* idx, const float* w2, const float* b2, int B, int N, int K, int C1,
+                int C2, float* out, cudaStream_t st);
+static int g_edge_mode = 0;   // 0 auto (tcgen05 when eligible), 1 FFMA kernel only
+
 }  // namespace samble
 
 using namespace samble;
+
+extern "C" void samble_set_edge_mode(int mode) { g_edge_mode = mode; }
 
 extern "C" int samble_edge_mlp_max(const float* pr, long long ld_pr, const void* idx, int idx_bits, const float* w2,
                                    const float* b2, int B, int N, int K, int C1, int C2, float* out,
@@ -131,6 +140,10 @@ extern "C" int samble_edge_mlp_max(const float* pr, long long ld_pr, const void*
                  "samble_edge_mlp_max: PR/W2 need 16-byte aligned rows");
   SAMBLE_REQUIRE(idx_bits == 32 || idx_bits == 64, "samble_edge_mlp_max: idx_bits must be 32 or 64");
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_edge_mode == 0 && edge_tc_eligible(K, C1, C2)) {
+    if (idx_bits == 64) return edge_mlp_tc<long long>(pr, ld_pr, (const long long*)idx, w2, b2, B, N, K, C1, C2, out, st);
+    return edge_mlp_tc<int>(pr, ld_pr, (const int*)idx, w2, b2, B, N, K, C1, C2, out, st);
+  }
 #define EC_DISPATCH(CPT)                                                                                              \
   (idx_bits == 64 ? launch_edge_mlp<long long, CPT>(pr, ld_pr, (const long long*)idx, w2, b2, B, N, K, C1, out, st)   \
                   : launch_edge_mlp<int, CPT>(pr, ld_pr, (const int*)idx, w2, b2, B, N, K, C1, out, st))

@@ -178,6 +178,7 @@ def test_blocks_vs_oracle(N):
 
 @pytest.mark.parametrize("B,N,K,Cin,C1,C2,gt", [(2, 300, 32, 3, 64, 64, "center_diff"), (1, 515, 16, 64, 64, 128, "center_diff"),
                                                 (2, 128, 7, 8, 32, 32, "diff"), (1, 200, 20, 16, 64, 64, "center_neighbor"),
+                                                (2, 2048, 32, 3, 64, 128, "center_diff"), (1, 1023, 32, 64, 128, 64, "center_diff"),
                                                 (1, 64, 32, 6, 16, 32, "neighbor")])
 def test_fused_edge_mlp_vs_unfused(B, N, K, Cin, C1, C2, gt):
     """csrc/edgeconv.cu against the literal group -> conv -> BN -> LeakyReLU -> conv -> BN -> LeakyReLU -> max
@@ -204,9 +205,15 @@ def test_fused_edge_mlp_vs_unfused(B, N, K, Cin, C1, C2, gt):
         lrelu = torch.nn.functional.leaky_relu
         ref = lrelu(bn2(conv2(lrelu(bn1(conv1(grouped)), 0.2))), 0.2).max(dim=-1)[0]
         w = [t.to(DEV) for t in blocks.edge_mlp_weights(conv1, bn1, conv2, bn2, gt)]
-        for dt in (torch.int32, torch.int64):
-            out = blocks.fused_edge_mlp(cu(x), cu(idx.to(dt)), w)
-            assert close_frac(out, ref, atol=1e-4, rtol=1e-4) == 1.0
+        from samble_b200 import _lib as L
+        for mode in (0, 1):                                # 0: tcgen05 where eligible, 1: FFMA kernel
+            L.lib().samble_set_edge_mode(mode)
+            try:
+                for dt in (torch.int32, torch.int64):
+                    out = blocks.fused_edge_mlp(cu(x), cu(idx.to(dt)), w)
+                    assert close_frac(out, ref, atol=1e-4, rtol=1e-4) == 1.0, (mode, dt)
+            finally:
+                L.lib().samble_set_edge_mode(0)
 
 
 def test_cuda_graph_replay_matches_eager():
