@@ -155,7 +155,10 @@ int samble_n2p_attend(const float* q, const float* k, const float* v, long long 
  * N+nb columns.  The N x (N+nb) map is never written: this pass leaves per-row
  * max and sum-of-exp plus the PRE-softmax token columns (:149-152).
  * q,k: point-major (B,N,D) with leading dims; k_tok: (nb,D) (tokens are shared by the
- * batch, :116).  rowmax,rowsum: (B,N).  token_logits: (B,N,nb). */
+ * batch, :116).  rowmax,rowsum: (B,N).  token_logits: (B,N,nb).
+ * D % 32 == 0, D <= 128, nb <= 8 runs on the tensor cores (tcgen05, 3xTF32 split); samble_set_ds_mode(1) forces the
+ * exact FFMA tile kernel (cross-check in the tests; bit-consistent logits with samble_ds_edge_score). */
+void samble_set_ds_mode(int mode);
 int samble_ds_row_stats(const float* q, long long ldq, const float* k, long long ldk, const float* k_tok,
                         int B, int N, int D, int nb, float* rowmax, float* rowsum, float* token_logits,
                         samble_stream_t stream);

@@ -42,6 +42,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_set_edge_mode": (None, (_i,)),
     "samble_edge_mlp_max": (_i, (_p, _ll, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p)),
     "samble_n2p_attend": (_i, (_p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p, _p, _ll, _p)),
+    "samble_set_ds_mode": (None, (_i,)),
     "samble_ds_row_stats": (_i, (_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p)),
     "samble_ds_edge_score_workspace_bytes": (_sz, (_i, _i)),
     "samble_ds_edge_score": (_i, (_p, _ll, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p)),

@@ -170,9 +170,17 @@ static EdgePlan edge_plan(int B, int N, int D) {
   return e;
 }
 
+// tensor-core form (ds_rowstats_tc.cu)
+bool ds_row_stats_tc_eligible(int D, int nb, long long ldq, long long ldk);
+int launch_ds_row_stats_tc(const float* q, long long ldq, const float* k, long long ldk, const float* k_tok, int B, int N, int D,
+                           int nb, float* rowmax, float* rowsum, float* token_logits, cudaStream_t st);
+static int g_ds_mode = 0;   // 0 auto (tcgen05 when eligible), 1 exact FFMA tile kernel only
+
 }  // namespace samble
 
 using namespace samble;
+
+extern "C" void samble_set_ds_mode(int mode) { g_ds_mode = mode; }
 
 extern "C" int samble_ds_row_stats(const float* q, long long ldq, const float* k, long long ldk, const float* k_tok,
                                    int B, int N, int D, int nb, float* rowmax, float* rowsum, float* token_logits,
@@ -184,6 +192,8 @@ extern "C" int samble_ds_row_stats(const float* q, long long ldq, const float* k
   SAMBLE_REQUIRE(nb >= 0 && nb <= 32, "samble_ds_row_stats: nb=%d outside [0,32]", nb);
   SAMBLE_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ((uintptr_t)q | (uintptr_t)k) % 16 == 0,
                  "samble_ds_row_stats: q/k need 16-byte aligned rows");
+  if (g_ds_mode == 0 && ds_row_stats_tc_eligible(D, nb, ldq, ldk))
+    return launch_ds_row_stats_tc(q, ldq, k, ldk, k_tok, B, N, D, nb, rowmax, rowsum, token_logits, (cudaStream_t)stream);
   using Cfg = DotTileCfg<4>;
   size_t smem = (Cfg::smem_floats(D) + 2 * Cfg::TQ) * sizeof(float);
   auto kern = ds_row_stats_kernel<Cfg>;

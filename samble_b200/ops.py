@@ -172,15 +172,24 @@ def gather_by_idx(pcd: Tensor, idx: Tensor) -> Tensor:
 # ------------------------------------------------------------------ fused block cores
 
 
-_W_SPLIT: dict = {}
+_W_SPLIT: dict = {}      # id(base tensor) -> (weakref(base), version, {view key: (W padded, W_lo)})
 
 
 def _split_weight(weight: Tensor):
-    """(W padded to a multiple of 4 columns, W_lo = W - tf32_trunc(W)); cached per weight tensor and in-place version."""
-    key = (weight.data_ptr(), tuple(weight.shape), tuple(weight.stride()))
-    hit = _W_SPLIT.get(key)
-    if hit is not None and hit[0] == weight._version:
-        return hit[1], hit[2]
+    """(W padded to a multiple of 4 columns, W_lo = W - tf32_trunc(W)).  Cached per LIVE base tensor (weak reference:
+    an address recycled by the allocator for a new tensor never hits), its in-place version, and the view taken of it."""
+    import weakref
+
+    base = weight._base if weight._base is not None else weight
+    vkey = (weight.data_ptr(), tuple(weight.shape), tuple(weight.stride()))
+    ent = _W_SPLIT.get(id(base))
+    if ent is not None and ent[0]() is base and ent[1] == base._version:
+        hit = ent[2].get(vkey)
+        if hit is not None:
+            return hit
+    else:
+        ent = (weakref.ref(base, lambda _r, k=id(base): _W_SPLIT.pop(k, None)), base._version, {})
+        _W_SPLIT[id(base)] = ent
     with torch.no_grad():
         w = _f32(weight, "weight").detach().flatten(1)
         Nout, K = w.shape
@@ -192,11 +201,9 @@ def _split_weight(weight: Tensor):
         lo = torch.empty(w.shape[0], w.stride(0), dtype=torch.float32, device=w.device)[:, : w.shape[1]]
         if w.is_contiguous():
             L.check(L.lib().samble_split_tf32(L.ptr(w), L.ptr(lo), w.numel(), L.stream()), "samble_split_tf32")
-        else:                       # strided view (e.g. a column slice of a bigger weight): split row by row via torch
+        else:                       # strided view (e.g. a column slice of a bigger weight): split via torch bit ops
             lo.copy_(w - (w.view(torch.int32) & -8192).view(torch.float32))
-    if len(_W_SPLIT) > 4096:
-        _W_SPLIT.clear()
-    _W_SPLIT[key] = (weight._version, w, lo)
+    ent[2][vkey] = (w, lo)
     return w, lo
 
 

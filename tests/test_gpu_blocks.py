@@ -53,10 +53,24 @@ def test_ds_row_stats_and_edge_score(B, N, nb, sharp):
     mask = torch.zeros(B, N, N, dtype=torch.float64).scatter_(2, idx, 1.0)
     indeg = mask.sum(1)
     score_ref = ((amap[..., :N] * mask).sum(1) / (indeg + 1e-8) / (indeg + 1e-8))
-    rowmax, rowsum, tok = ops.ds_row_stats(cu(q), cu(k), cu(k_tok))
+    from samble_b200 import _lib as L
     m_ref = logits.max(-1)[0]
-    torch.testing.assert_close(rowmax.cpu().double(), m_ref, atol=1e-4, rtol=1e-5)
-    torch.testing.assert_close(rowsum.cpu().double(), torch.exp(logits - m_ref.unsqueeze(-1)).sum(-1), atol=1e-5, rtol=1e-4)
+    L.lib().samble_set_ds_mode(1)                      # exact FFMA tile kernel
+    try:
+        rm_f, rs_f, tok_f = ops.ds_row_stats(cu(q), cu(k), cu(k_tok))
+    finally:
+        L.lib().samble_set_ds_mode(0)
+    torch.testing.assert_close(rm_f.cpu().double(), m_ref, atol=1e-4, rtol=1e-5)
+    torch.testing.assert_close(rs_f.cpu().double(), torch.exp(logits - m_ref.unsqueeze(-1)).sum(-1), atol=1e-5, rtol=1e-4)
+    rowmax, rowsum, tok = ops.ds_row_stats(cu(q), cu(k), cu(k_tok))      # tcgen05 3xTF32 kernel
+    assert torch.equal(tok, tok_f)                     # token columns: exact fp32 in both
+    print(f"row stats tc vs fp64: max|dm| {(rowmax.cpu().double() - m_ref).abs().max():.2e}, max rel ds "
+          f"{((rowsum.cpu().double() * torch.exp(rowmax.cpu().double() - m_ref)) / torch.exp(logits - m_ref.unsqueeze(-1)).sum(-1) - 1).abs().max():.2e}")
+    torch.testing.assert_close(rowmax.cpu().double(), m_ref, atol=3e-4, rtol=1e-5)
+    # the pair (max, sum) matters only through logsumexp = max + log(sum)
+    lse_ref = torch.logsumexp(logits, -1)
+    lse = rowmax.cpu().double() + torch.log(rowsum.cpu().double())
+    torch.testing.assert_close(lse, lse_ref, atol=2e-4, rtol=1e-5)
     torch.testing.assert_close(tok.cpu().double(), logits[..., N:], atol=1e-4, rtol=1e-5)
     for bits in (torch.int64, torch.int32):
         score = ops.ds_edge_score(cu(q), cu(k), rowmax, rowsum, cu(idx.to(bits)))
@@ -160,7 +174,10 @@ def test_blocks_vs_oracle(N):
             (x_ds, idx), _ = ds(cu(x128))
             ref = O.downsample_token(sd, "block.downsample_list.0.", x128, N // 2, 32, 4, st)
             torch.testing.assert_close(ds.bin_boundaries[0].cpu(), ref["boundaries"][0], rtol=1e-4, atol=1e-5)
-            assert close_frac(ds.attention_point_score, ref["score"], atol=1e-10, rtol=5e-5) >= 0.995
+            # 3xTF32 projections / row statistics: the logit error (~1e-6 of sum|q_c k_c|) is amplified by exp() when the
+            # sharpened logits reach |l| ~ 100; measured median 1e-4, max 5e-4 (tools/probe_ds_precision.py), with
+            # no change of the sampled sets relative to the all-fp32 kernels.
+            assert close_frac(ds.attention_point_score, ref["score"], atol=1e-30, rtol=1e-3) >= 0.995
             assert tuple(ds.bin_points_mask.shape) == tuple(ref["mask"].shape) and ds.bin_points_mask.dtype == torch.bool
             assert float((ds.bin_points_mask.cpu() != ref["mask"]).float().mean()) < 2e-3
             assert int((ds.k_point_to_choose.cpu() - ref["k"]).abs().max()) <= 2
