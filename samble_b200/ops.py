@@ -221,6 +221,10 @@ def linear(x: Tensor, weight: Tensor, *, x_layout: str = "rows", out_layout: str
     L.no_grad_check(x, weight)
     w, w_lo = _split_weight(weight)
     Nout, K = weight.shape[0], weight[0].numel()
+    if x_layout == "bcn" and x.shape[1] >= 32:
+        # measured: the row-major loader (cp.async, two stages ahead) is 2x faster than the channel-major one even
+        # after paying for this transposing copy (tools/time_linear_calls.py)
+        x, x_layout = _f32(x, "x").transpose(1, 2).contiguous(), "rows"
     if x_layout == "bcn":
         x = _f32(x, "x").contiguous()
         B, Kx, P = x.shape
