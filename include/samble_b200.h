@@ -77,13 +77,19 @@ int samble_selftest_mma_rate(int n_tile, int iters, int ctas, long long* cycles_
  *
  * C <= 3 runs the FFMA xyz kernel.  4 <= C <= 128 runs the tcgen05 path (tf32 contraction -> candidate set ->
  * exact fp32 re-rank; output identical to the exact kernel); larger C runs the exact FFMA tile kernel.
- * samble_set_knn_mode: 0 = auto (default), 1 = exact FFMA kernels only (used by the tests as the cross-check). */
+ * samble_set_knn_mode: 0 = auto (default), 1 = exact FFMA kernels only (used by the tests as the cross-check).
+ *
+ * flags: 0, or SAMBLE_KNN_ANY_ORDER (dist_out must be NULL): the k indices of each row are the same SET but in no
+ * particular order.  Every consumer on the path reduces over the neighbours (max, softmax-weighted sum, scatter),
+ * so the blocks ask for this; the tcgen05 path then computes exact distances only for the few candidates whose tf32
+ * score is within the error margin of the k-th (knn_select_kernel) instead of for the whole candidate list. */
+#define SAMBLE_KNN_ANY_ORDER 1
 void samble_set_knn_mode(int mode);
 size_t samble_knn_workspace_bytes(int B, int Nq, int Nr, int C);
 int samble_knn(const float* a, long long a_sb, long long a_sn, long long a_sc,
                const float* b, long long b_sb, long long b_sn, long long b_sc,
                int B, int Nq, int Nr, int C, int k,
-               void* idx_out, int idx_bits, float* dist_out,
+               void* idx_out, int idx_bits, float* dist_out, int flags,
                void* ws, size_t ws_bytes, samble_stream_t stream);
 
 /* ------------------------------------------------------------- gathers ----------

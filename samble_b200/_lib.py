@@ -32,7 +32,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_selftest_mma_rate": (_i, (_i, _i, _i, _p, _p)),
     "samble_set_knn_mode": (None, (_i,)),
     "samble_knn_workspace_bytes": (_sz, (_i, _i, _i, _i)),
-    "samble_knn": (_i, (_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _p, _i, _p, _p, _sz, _p)),
+    "samble_knn": (_i, (_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _sz, _p)),
     "samble_index_points": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
     "samble_group": (_i, (_p, _p, _i, _i, _i, _i, _i, _i, _p, _p)),
     "samble_gather_by_idx": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),

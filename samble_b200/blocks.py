@@ -134,7 +134,7 @@ class EdgeConv(nn.Module):
             x, _ = ops.group(x, self.K, self.group_type, self.normal_channel)
             return self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0]
         key = x[:, :3, :] if (self.normal_channel and x.shape[1] == 6) else x
-        idx = ops.knn_indices(key, self.K)
+        idx = ops.knn_indices(key, self.K, ordered=False)
         params = [self.conv1[0].weight, self.conv2[0].weight, *self.conv1[1].parameters(), *self.conv1[1].buffers(),
                   *self.conv2[1].parameters(), *self.conv2[1].buffers()]
         weights = self._fold.get(params, lambda: edge_mlp_weights(self.conv1[0], self.conv1[1], self.conv2[0],
@@ -179,7 +179,7 @@ class Neighbor2PointAttention(nn.Module):
             raise NotImplementedError("native Neighbor2PointAttention covers group_type='diff', "
                                       "attention_mode='scalar_dot', asm='dot' (the shipped configs)")
         B, C, N = x.shape
-        idx = ops.knn_indices(x, self.K)                                        # (B,N,K) int32
+        idx = ops.knn_indices(x, self.K, ordered=False)                                        # (B,N,K) int32
         w = self._wqkv.get([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], lambda: torch.cat(
             [self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C).contiguous())
         if self.training:                                                       # BatchNorm batch statistics: library ops
@@ -277,7 +277,7 @@ class DownSampleToken(nn.Module):
         k_tok = torch.matmul(tok, self.k_conv.weight.view(C, C).t()).contiguous()   # (nb,D)
         v_tok = torch.matmul(tok, self.v_conv.weight.view(C, C).t())
 
-        idx = ops.knn_indices(x, self.K)                                       # neighbor_mask's kNN (:301)
+        idx = ops.knn_indices(x, self.K, ordered=False)                                       # neighbor_mask's kNN (:301)
         rowmax, rowsum, tok_logits = ops.ds_row_stats(q, k, k_tok)
         score = ops.ds_edge_score(q, k, rowmax, rowsum, idx)                   # (B,N)
         self.attention_point_score = score.view(B, 1, N)

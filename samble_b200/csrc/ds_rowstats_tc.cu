@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t idesc = tc::instr_desc(2, 128, 128);
       int g = 0;
       for (int t = 0; t < ntiles; ++t) {

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kEtThreads, 1)
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t idesc = tc::instr_desc(2, 128, C2);
       int g = 0, it = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {

@@ -69,15 +69,32 @@ __global__ void __launch_bounds__(256) knn_prep_xyz_kernel(const float* __restri
   out[(long long)b * N + n] = make_float4(v[0], v[1], v[2], nn);
 }
 
+// Norm slice of the tensor-core path (knn_tc.cu): candidate n contributes the K=8 operand row (h_hi, h_lo, 0, ..., 0),
+// h = -|b|^2/2 split into two tf32 terms, stored per (cloud, tile of 128) in the compact no-swizzle operand layout
+// [chunk][row][16 B]; only chunk 0 is non-zero (chunk 1 is all zero).
+__device__ __forceinline__ void knn_store_ext(float* ext, int b, int N, int n, float h) {
+  const int ntiles = (N + 127) >> 7;
+  if (n >= ntiles * 128) return;
+  const float hi = __uint_as_float(__float_as_uint(h) & 0xffffe000u);
+  float* blk = ext + ((size_t)b * ntiles + (n >> 7)) * 1024;
+  *reinterpret_cast<float4*>(blk + (n & 127) * 4) = make_float4(hi, h - hi, 0.f, 0.f);
+  *reinterpret_cast<float4*>(blk + 512 + (n & 127) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // feature path: point-major normalised copy (B,N,Cp) (channels >= C zero) + squared norms (B,N).
 // 32x32 smem transpose so both the channel-major read and the point-major write coalesce.
 __global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restrict__ x, long long sb, long long sn,
                                                             long long sc, int N, int C, int Cp,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ stdv, float* __restrict__ out,
-                                                            float* __restrict__ norms, unsigned* __restrict__ maxnorm) {
+                                                            float* __restrict__ norms, unsigned* __restrict__ maxnorm,
+                                                            float* __restrict__ ext) {
   __shared__ float tile[32][33];
   const int b = blockIdx.y, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (n0 >= N) {                                        // padding rows of the last 128-candidate tile (ext only)
+    if (ty == 0) knn_store_ext(ext, b, N, n0 + tx, -1e30f);
+    return;
+  }
   const float sigma = cloud_sigma(stdv + b * C, C);
   float nn = 0.f;
   for (int c0 = 0; c0 < Cp; c0 += 32) {
@@ -102,6 +119,7 @@ __global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restr
   }
   if (ty == 0) {
     if (n0 + tx < N) norms[(long long)b * N + n0 + tx] = nn;
+    if (ext) knn_store_ext(ext, b, N, n0 + tx, n0 + tx < N ? -0.5f * nn : -1e30f);   // past N: can never win
     if (maxnorm) {                                    // per-cloud max |p'|^2 (>= 0: uint order == float order)
       const unsigned m = __reduce_max_sync(kFull, n0 + tx < N ? __float_as_uint(nn) : 0u);
       if (tx == 0) atomicMax(maxnorm + b, m);
@@ -287,11 +305,12 @@ int launch_knn_prep_xyz(const float* x, long long sb, long long sn, long long sc
 
 // tensor-core path (knn_tc.cu)
 bool knn_tc_eligible(int Nq, int Nr, int C, int k);
-size_t knn_tc_workspace_bytes(int B, int Nq);
+size_t knn_tc_workspace_bytes(int B, int Nq, int Nr);
+size_t knn_tc_ext_floats(int B, int Nr);
 template <class I>
-int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const unsigned* bbmax, int B,
-                  int Nq, int Nr, int Cp, int k, float* thr, unsigned short* cand, int* cnt, I* idx, float* dist,
-                  int* row_flags, cudaStream_t st);
+int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const float* bext,
+                  const unsigned* bbmax, int B, int Nq, int Nr, int Cp, int k, float* thr, uint32_t* cand, int* cnt,
+                  bool ordered, I* idx, float* dist, int* row_flags, cudaStream_t st);
 
 static int g_knn_mode = 0;   // 0 auto, 1 exact FFMA kernel only, 2 tensor-core path wherever eligible
 
@@ -307,14 +326,14 @@ static KnnPlan knn_plan(int B, int Nq, int Nr, int C) {
   size_t per_pt = p.xyz ? sizeof(float4) : (size_t)(p.Cp + 1) * sizeof(float);
   p.bytes = 2 * align_up((size_t)B * C * sizeof(float), 256) + align_up((size_t)B * Nq * per_pt, 256) +
             align_up((size_t)B * Nr * per_pt, 256) + 2 * align_up((size_t)B * Nq * sizeof(float), 256) +
-            align_up((size_t)B * sizeof(unsigned), 256) + (p.xyz ? 0 : knn_tc_workspace_bytes(B, Nq)) + 10 * 256;
+            align_up((size_t)B * sizeof(unsigned), 256) + (p.xyz ? 0 : knn_tc_workspace_bytes(B, Nq, Nr)) + 12 * 256;
   return p;
 }
 
 template <class I>
 static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_sc, const float* b, long long b_sb,
                     long long b_sn, long long b_sc, int B, int Nq, int Nr, int C, int k, I* idx_out, float* dist_out,
-                    void* ws, size_t ws_bytes, cudaStream_t st) {
+                    bool ordered, void* ws, size_t ws_bytes, cudaStream_t st) {
   KnnPlan plan = knn_plan(B, Nq, Nr, C);
   SAMBLE_REQUIRE(ws_bytes >= plan.bytes, "samble_knn: workspace %zu < %zu bytes", ws_bytes, plan.bytes);
   const bool self = (a == b) && a_sb == b_sb && a_sn == b_sn && a_sc == b_sc && Nq == Nr;
@@ -343,8 +362,9 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   float* thr = w.take<float>((size_t)B * Nq);
   int* row_flags = w.take<int>((size_t)B * Nq);
   unsigned* bbmax = w.take<unsigned>((size_t)B);
-  unsigned short* cand = w.take<unsigned short>((size_t)B * Nq * 128);
+  uint32_t* cand = w.take<uint32_t>((size_t)B * Nq * 128);
   int* cand_cnt = w.take<int>((size_t)B * Nq);
+  float* bext = w.take<float>(knn_tc_ext_floats(B, Nr));
   const bool use_tc = g_knn_mode != 1 && knn_tc_eligible(Nq, Nr, C, k);
   if (use_tc) {   // row_flags and bbmax are adjacent (256-byte granules): one memset node
     const size_t span = (size_t)((char*)(bbmax + B) - (char*)row_flags);
@@ -352,17 +372,20 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
     count_launch();
   }
   SAMBLE_PRE(st);
-  knn_prep_feat_kernel<<<dim3(ceil_div(Nq, 32), B), 256, 0, st>>>(a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv, an, anorm,
-                                                                    (use_tc && self) ? bbmax : nullptr);
+  // the candidate-side launch also covers the padding rows of the last 128-candidate tile (norm slice only)
+  const bool a_is_cand = use_tc && self;
+  knn_prep_feat_kernel<<<dim3(ceil_div(a_is_cand ? (int)align_up(Nq, 128) : Nq, 32), B), 256, 0, st>>>(
+      a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv, an, anorm, a_is_cand ? bbmax : nullptr, a_is_cand ? bext : nullptr);
   SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   if (!self) {
     SAMBLE_PRE(st);
-    knn_prep_feat_kernel<<<dim3(ceil_div(Nr, 32), B), 256, 0, st>>>(b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn, bnorm,
-                                                                      use_tc ? bbmax : nullptr);
+    knn_prep_feat_kernel<<<dim3(ceil_div(use_tc ? (int)align_up(Nr, 128) : Nr, 32), B), 256, 0, st>>>(
+        b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn, bnorm, use_tc ? bbmax : nullptr, use_tc ? bext : nullptr);
     SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   }
   if (use_tc) {
-    if (int e = launch_knn_tc<I>(an, anorm, bn, bnorm, bbmax, B, Nq, Nr, Cp, k, thr, cand, cand_cnt, idx_out, dist_out, row_flags, st))
+    if (int e = launch_knn_tc<I>(an, anorm, bn, bnorm, bext, bbmax, B, Nq, Nr, Cp, k, thr, cand, cand_cnt, ordered, idx_out,
+                                 dist_out, row_flags, st))
       return e;
     // rows whose candidate buffer overflowed are redone by the exact kernel (normally none: every tile exits at once)
     return launch_knn_feat<DotTileCfg<4>, I>(an, anorm, bn, bnorm, B, Nq, Nr, C, Cp, k, idx_out, dist_out, row_flags, st);
@@ -386,7 +409,7 @@ extern "C" size_t samble_knn_workspace_bytes(int B, int Nq, int Nr, int C) {
 
 extern "C" int samble_knn(const float* a, long long a_sb, long long a_sn, long long a_sc, const float* b,
                           long long b_sb, long long b_sn, long long b_sc, int B, int Nq, int Nr, int C, int k,
-                          void* idx_out, int idx_bits, float* dist_out, void* ws, size_t ws_bytes,
+                          void* idx_out, int idx_bits, float* dist_out, int flags, void* ws, size_t ws_bytes,
                           samble_stream_t stream) {
   SAMBLE_REQUIRE(a && b && idx_out && ws, "samble_knn: null pointer");
   SAMBLE_REQUIRE(B > 0 && Nq > 0 && Nr > 0 && C > 0, "samble_knn: empty shape B=%d Nq=%d Nr=%d C=%d", B, Nq, Nr, C);
@@ -395,10 +418,13 @@ extern "C" int samble_knn(const float* a, long long a_sb, long long a_sn, long l
   SAMBLE_REQUIRE(k <= Nr, "samble_knn: k=%d > number of candidates %d", k, Nr);
   SAMBLE_REQUIRE(idx_bits == 32 || idx_bits == 64, "samble_knn: idx_bits must be 32 or 64");
   SAMBLE_REQUIRE(B <= 65535, "samble_knn: B=%d > 65535", B);
+  SAMBLE_REQUIRE((flags & ~SAMBLE_KNN_ANY_ORDER) == 0, "samble_knn: unknown flags 0x%x", flags);
+  SAMBLE_REQUIRE(!(flags & SAMBLE_KNN_ANY_ORDER) || !dist_out, "samble_knn: SAMBLE_KNN_ANY_ORDER returns indices only");
+  const bool ordered = !(flags & SAMBLE_KNN_ANY_ORDER);
   cudaStream_t st = (cudaStream_t)stream;
   if (idx_bits == 64)
     return knn_impl<long long>(a, a_sb, a_sn, a_sc, b, b_sb, b_sn, b_sc, B, Nq, Nr, C, k, (long long*)idx_out,
-                               dist_out, ws, ws_bytes, st);
-  return knn_impl<int>(a, a_sb, a_sn, a_sc, b, b_sb, b_sn, b_sc, B, Nq, Nr, C, k, (int*)idx_out, dist_out, ws,
-                       ws_bytes, st);
+                               dist_out, ordered, ws, ws_bytes, st);
+  return knn_impl<int>(a, a_sb, a_sn, a_sc, b, b_sb, b_sn, b_sc, B, Nq, Nr, C, k, (int*)idx_out, dist_out, ordered,
+                       ws, ws_bytes, st);
 }

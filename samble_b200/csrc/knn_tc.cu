@@ -18,7 +18,8 @@
 //
 // CTA = 128 query rows (UMMA M=128), candidate tiles of 128 (UMMA N=128), K-blocks of 32 channels
 // (128-byte rows, SWIZZLE_128B).  Warps 0-3: epilogue (thread = TMEM lane = query row); warp 4: MMA issuer;
-// warps 5-8: cp.async loaders.  smem ring of K-block stages (full/empty mbarriers), two TMEM accumulators
+// warp 5: TMA producer (one thread: tensor-map box loads of the K-blocks, a bulk copy of the tile's norm slice).
+// smem ring of K-block stages (full/empty mbarriers, full[] counted in bytes by the TMA unit), two TMEM accumulators
 // (tmem_full/tmem_empty mbarriers) so the epilogue of tile t overlaps the MMAs of tile t+1.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -29,12 +30,14 @@ constexpr int kTcRows = 128;      // query rows per CTA
 constexpr int kTcTile = 128;      // candidates per tile
 constexpr int kTcStages = 5;      // smem ring depth (16 KB each)
 constexpr int kExt = 4096;        // compact non-swizzled [128 x 32 B] slice (tc::smem_desc_nosw)
-constexpr int kTcCap = 128;       // candidate list entries per row
-constexpr int kTcThreads = 288;   // 4 epilogue + 1 mma + 4 loader warps
+constexpr int kTcCap = 120;       // usable candidate-list entries per row (a row that reaches it is redone exactly)
+constexpr int kTcListLd = 128;    // list row pitch in global memory (32-bit entries)
+constexpr int kTcListSm = 129;    // ... and in shared memory: odd, so the 32 rows of a warp hit 32 banks
+constexpr int kTcThreads = 192;   // 4 epilogue warps + MMA issuer + TMA producer
 
 static size_t tc_smem_bytes(int nkb, bool pass_b) {
   return (size_t)nkb * 16384 + (size_t)kTcStages * 16384 /* A + B ring */ + 3 * kExt /* A_ext, B_ext x2 */
-         + (pass_b ? (size_t)kTcRows * kTcCap * 2 : 0) + 1024 + 256;
+         + (pass_b ? (size_t)kTcRows * kTcListSm * 4 : 0) + 1024 + 256;
 }
 
 // |d~ - d_fp32| <= e:  2 * |<a,b>_tf32 - <a,b>| <= 2 * (2^-10 + 2^-10 + 2^-20) |a||b|  (operand truncation)
@@ -43,6 +46,13 @@ __device__ __forceinline__ float knn_margin(float aa, float bbmax) {
   const float s = sqrtf(aa * bbmax);
   return (0.00390625f + 0.00012207031f) * s + 3.0517578e-05f * (aa + bbmax);
 }
+
+// A list entry is one 32-bit word: candidate index in the low half, and in the high half the upper 16 bits (sign,
+// exponent, 7 mantissa bits) of delta = s - T >= 0, the score's offset above the row's collection threshold T.
+// Words therefore order by score, and  delta_lo <= delta <= delta_lo * (1 + 2^-7)  with delta_lo = word & 0xffff0000.
+__device__ __forceinline__ uint32_t knn_pack(float delta, int j) { return (__float_as_uint(delta) & 0xffff0000u) | (uint32_t)j; }
+__device__ __forceinline__ float knn_delta_lo(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float knn_delta_hi(float lo) { return lo * 1.0079f; }
 
 // in-register bitonic sort of 64 floats (ascending).  Canonical counted loops so that everything unrolls and
 // every index is a compile-time constant (otherwise the array drops to local memory).
@@ -67,9 +77,10 @@ __device__ __forceinline__ void sort64(float (&v)[64]) {
 
 template <bool PASS_B>
 __global__ void __launch_bounds__(kTcThreads, 1)
-    knn_tc_kernel(const float* __restrict__ an, const float* __restrict__ anorm, const float* __restrict__ bn,
-                  const float* __restrict__ bnorm, const unsigned* __restrict__ bbmax_bits, int Nq, int Nr, int Cp,
-                  int k, float* __restrict__ thr, unsigned short* __restrict__ cand_out, int* __restrict__ cnt_out) {
+    knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const float* __restrict__ anorm, const float* __restrict__ bext, const unsigned* __restrict__ bbmax_bits,
+                  int Nq, int Nr, int Cp, int k, float* __restrict__ thr, uint32_t* __restrict__ cand_out,
+                  int* __restrict__ cnt_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nkb = Cp / 32;
@@ -78,30 +89,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   uint8_t* sAx = sB + (size_t)kTcStages * 16384;            // query-side norm slice: (1,1,0,...) per row
   uint8_t* sBx = sAx + kExt;                                // candidate-side norm slice, double buffered per tile
   uint8_t* tail = sBx + 2 * kExt;
-  unsigned short* cand = reinterpret_cast<unsigned short*>(tail);                    // [128][kTcCap]   (pass B)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + (PASS_B ? kTcRows * kTcCap * 2 : 0));
+  uint32_t* cand = reinterpret_cast<uint32_t*>(tail);                                 // [128][kTcListSm]   (pass B)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + (PASS_B ? kTcRows * kTcListSm * 4 : 0));
   uint64_t* full = bars;                      // [kTcStages]
   uint64_t* empty = bars + kTcStages;         // [kTcStages]
   uint64_t* tfull = bars + 2 * kTcStages;     // [2]
   uint64_t* tempty = tfull + 2;               // [2]
   uint64_t* xempty = tempty + 2;              // [2]  norm slice of tile t may be overwritten (its MMA retired)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + 2);
+  uint64_t* afull = xempty + 2;               // query tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, q0 = blockIdx.x * kTcRows;
-  const float* A_g = an + (size_t)b * Nq * Cp;
-  const float* B_g = bn + (size_t)b * Nr * Cp;
-  const float* bnorm_g = bnorm + (size_t)b * Nr;
   const int ntiles = (Nr + kTcTile - 1) / kTcTile;
-  const int G = ntiles * nkb;
 
-  // ---- one-time setup: resident query tile (swizzled), barriers, TMEM ----
-  for (int p = tid; p < nkb * 1024; p += kTcThreads) {
-    const int kb = p >> 10, row = (p >> 3) & 127, ch = p & 7;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + row < Nq) v = __ldg(reinterpret_cast<const float4*>(A_g + (size_t)(q0 + row) * Cp + kb * 32 + ch * 4));
-    *reinterpret_cast<float4*>(sA + (size_t)kb * 16384 + tc::sw128_offset(row, ch)) = v;
-  }
+  // ---- one-time setup: query-side norm slice, barriers, TMEM ----
   for (int p = tid; p < 256; p += kTcThreads) {
     const int row = p >> 1, ch = p & 1;
     *reinterpret_cast<float4*>(sAx + tc::nosw_offset(row, ch, 128)) = ch == 0 ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   tc::fence_proxy_async();
   if (tid == 0) {
     for (int s = 0; s < kTcStages; ++s) {
-      tc::mbar_init(&full[s], 128);
+      tc::mbar_init(&full[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       tc::mbar_init(&tempty[a], 128);
       tc::mbar_init(&xempty[a], 1);
     }
+    tc::mbar_init(afull, 1);
     tc::mbar_init_fence();
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
@@ -125,47 +128,40 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= 5) {
-    // ================= loaders: candidate K-blocks (+ norm block with K-block 0) -> swizzled smem =================
-    const int lt = tid - 160;                         // 0..127
-    for (int g = 0; g < G; ++g) {
-      const int s = g % kTcStages, ph = (g / kTcStages) & 1;
-      tc::mbar_wait(&empty[s], ph ^ 1);
-      const int t = g / nkb, kb = g % nkb;
-      uint8_t* dst = sB + (size_t)s * 16384;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int p = lt + 128 * i, row = p >> 3, ch = p & 7;
-        const int n = t * kTcTile + row;
-        const bool ok = n < Nr;
-        cp_async16(dst + tc::sw128_offset(row, ch), B_g + (size_t)(ok ? n : 0) * Cp + kb * 32 + ch * 4, ok);
-      }
-      cp_async_commit();
-      if (kb == 0) {
-        // norm slice row = (-|b|^2/2 as tf32 hi, lo, 0, ...); buffer t&1 is free once the norm MMA of tile t-2 retired.
-        // These generic stores precede this thread's fence.proxy.async + arrive on full[] of (t, kb=0).
-        tc::mbar_wait(&xempty[t & 1], ((t >> 1) & 1) ^ 1);
-        const int n = t * kTcTile + lt;
-        const float h = n < Nr ? -0.5f * __ldg(bnorm_g + n) : -1e30f;      // out-of-range candidates can never win
-        const float hi = __uint_as_float(__float_as_uint(h) & 0xffffe000u);
-        uint8_t* xb = sBx + (size_t)(t & 1) * kExt;
-        *reinterpret_cast<float4*>(xb + tc::nosw_offset(lt, 0, 128)) = make_float4(hi, h - hi, 0.f, 0.f);
-        *reinterpret_cast<float4*>(xb + tc::nosw_offset(lt, 1, 128)) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (g > 0) {
-        cp_async_wait<1>();
-        tc::fence_proxy_async();
-        tc::mbar_arrive(&full[(g - 1) % kTcStages]);
+  if (warp == 5) {
+    // ================= TMA producer =================
+    if (tc::elect_one()) {
+      tc::tma_prefetch_desc(&map_a);
+      tc::tma_prefetch_desc(&map_b);
+      // resident query tile: nkb boxes of [128 rows x 32 channels]; rows past Nq read as zero
+      tc::mbar_arrive_expect_tx(afull, (uint32_t)nkb * 16384u);
+      for (int kb = 0; kb < nkb; ++kb) tc::tma_load_3d(sA + (size_t)kb * 16384, &map_a, afull, kb * 32, q0, b);
+      const float* ext_g = bext + (size_t)b * ntiles * (kExt / 4);
+      int s = 0, ph = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          tc::mbar_wait(&empty[s], ph ^ 1);
+          if (kb == 0) {
+            // the tile's norm slice rides on the barrier of its first K-block; buffer t&1 is free once the norm
+            // MMA of tile t-2 retired
+            tc::mbar_wait(&xempty[t & 1], ((t >> 1) & 1) ^ 1);
+            tc::mbar_arrive_expect_tx(&full[s], 16384u + kExt);
+            tc::bulk_load_1d(sBx + (size_t)(t & 1) * kExt, ext_g + (size_t)t * (kExt / 4), kExt, &full[s]);
+          } else {
+            tc::mbar_arrive_expect_tx(&full[s], 16384u);
+          }
+          tc::tma_load_3d(sB + (size_t)s * 16384, &map_b, &full[s], kb * 32, t * kTcTile, b);   // rows past Nr: zero
+          if (++s == kTcStages) { s = 0; ph ^= 1; }
+        }
       }
     }
-    cp_async_wait<0>();
-    tc::fence_proxy_async();
-    tc::mbar_arrive(&full[(G - 1) % kTcStages]);
+    __syncwarp();
   } else if (warp == 4) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint32_t idesc = tc::instr_desc(2, kTcRows, kTcTile);
       const uint64_t axd = tc::smem_desc_nosw(tc::smem_u32(sAx), 128);
+      tc::mbar_wait(afull, 0);
       for (int t = 0; t < ntiles; ++t) {
         const int acc = t & 1;
         tc::mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);
@@ -179,7 +175,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) tc::mma_tf32(tmem + acc * kTcTile, ad + 2 * k8, bd + 2 * k8, idesc, (kb | k8) != 0);
           if (kb == nkb - 1) {
-            // norm slice of tile t: stored before the loaders' arrive on full[] of (t, kb=0), which this thread waited on
+            // norm slice of tile t: landed with full[] of (t, kb=0), which this thread waited on
             tc::mma_tf32(tmem + acc * kTcTile, axd, tc::smem_desc_nosw(tc::smem_u32(sBx + (size_t)(t & 1) * kExt), 128), idesc, 1);
             tc::mma_commit(&xempty[t & 1]);
           }
@@ -196,7 +192,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     float gmax[64];
     float my_thr = 0.f;
-    int cnt = 0;
+    const uint32_t lbeg = tc::smem_u32(cand + row * kTcListSm);      // list cursor as a 32-bit shared address
+    uint32_t lptr = lbeg;
     if (!PASS_B) {
 #pragma unroll
       for (int i = 0; i < 64; ++i) gmax[i] = -INFINITY;
@@ -215,12 +212,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
           for (int i = 0; i < 64; ++i) gmax[i] = fmaxf(gmax[i], v[i]);     // group = column mod 64
         } else {
+          // branch-free compaction: every element is stored at the cursor, the cursor moves on a hit.  The cursor
+          // is clamped every 8 elements (the row has 8 words of slack), so the list saturates at kTcCap.
           const int jbase = t * kTcTile + c0;
 #pragma unroll
           for (int i = 0; i < 64; ++i) {
-            const bool hit = v[i] >= my_thr;
-            if (hit && cnt < kTcCap) cand[row * kTcCap + cnt] = (unsigned short)(jbase + i);
-            cnt += hit ? 1 : 0;
+            const float delta = v[i] - my_thr;
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(lptr), "r"(knn_pack(delta, jbase + i)) : "memory");
+            lptr += delta >= 0.f ? 4u : 0u;
+            if ((i & 7) == 7) lptr = min(lptr, lbeg + 4u * kTcCap);
           }
         }
       }
@@ -243,17 +243,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         thr[(size_t)b * Nq + q] = fminf(kth - e, 0.5f * (aa - e));
       }
     } else if (q < Nq) {
-      cnt_out[(size_t)b * Nq + q] = cnt;
+      cnt_out[(size_t)b * Nq + q] = (int)(min(lptr, lbeg + 4u * kTcCap) - lbeg) >> 2;   // == kTcCap: saturated
     }
   }
 
   if (PASS_B) {
-    // candidate lists -> global, 256 B per row, coalesced
+    // candidate lists -> global, 512 B per row, coalesced
     __syncthreads();
     for (int row = warp; row < kTcRows; row += kTcThreads / 32) {
       const int q = q0 + row;
       if (q >= Nq) break;
-      reinterpret_cast<uint2*>(cand_out + ((size_t)b * Nq + q) * kTcCap)[lane] = reinterpret_cast<const uint2*>(cand + row * kTcCap)[lane];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        cand_out[((size_t)b * Nq + q) * kTcListLd + u * 32 + lane] = cand[row * kTcListSm + u * 32 + lane];
     }
   }
   tc::tc_fence_before();
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 template <class I>
 __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict__ an, const float* __restrict__ anorm,
                                                          const float* __restrict__ bn, const float* __restrict__ bnorm,
-                                                         const unsigned short* __restrict__ cand,
+                                                         const uint32_t* __restrict__ cand,
                                                          const int* __restrict__ cnt_in, int Nq, int Nr, int Cp, int k,
                                                          I* __restrict__ idx_out, float* __restrict__ dist_out,
                                                          int* __restrict__ row_flags) {
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   if (q >= Nq) return;
   const size_t rowi = (size_t)b * Nq + q;
   const int cnt = cnt_in[rowi];
-  if (cnt > kTcCap) {                                   // overflow: hand the row to the exact kernel
+  if (cnt >= kTcCap) {                                  // saturated list: hand the row to the exact kernel
     if (lane == 0) row_flags[rowi] = 1;
     return;
   }
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   for (int r = 0; r < cnt; r += 32) {
     const int e = r + lane;
     const bool have = e < cnt;
-    const int j = have ? (int)cand[rowi * kTcCap + e] : 0;
+    const int j = have ? (int)(cand[rowi * kTcListLd + e] & 0xffffu) : 0;
     const float4* br = reinterpret_cast<const float4*>(B_g + (size_t)j * Cp);
     float acc = 0.f;
 #pragma unroll 4
@@ -316,21 +318,165 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   }
 }
 
+// ---- pass C', indices only, any order: exact work only where the tf32 scores cannot decide. ----
+// With |d~ - d| <= e for every candidate (knn_margin) and d~(k), d~(k+1) the k-th / (k+1)-th smallest approx distances
+// of the row (both are in the list, which holds everything up to d~(k) + 2e):
+//   d~_j < d~(k+1) - 2e  and  d~(k+1) > e   =>  fewer than k candidates can beat j  -> j is in the exact answer
+//   d~_j > d~(k)   + 2e  and  d~_j    > e   =>  at least k candidates beat j         -> j is not
+// (the "> e" clauses keep the argument valid under the exact kernel's clamp of negative d^2 to 0, where
+// near-duplicates of the query tie and the index decides).  Only the band in between -- a handful of candidates --
+// gets exact fp32 distances, and the best (k - #in) of it by (distance, index) completes the SET the exact kernel
+// returns.  In s = <a,b> - |b|^2/2 units (d~ = |a|^2 - 2s):  in: s_j > s(k+1) + e,  out: s_j < s(k) - e, evaluated
+// on the list's truncated offsets delta = s - T with their interval [delta_lo, delta_hi] (knn_pack).
+template <class I>
+__global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict__ an, const float* __restrict__ anorm,
+                                                         const float* __restrict__ bn, const float* __restrict__ bnorm,
+                                                         const unsigned* __restrict__ bbmax_bits,
+                                                         const uint32_t* __restrict__ cand,
+                                                         const float* __restrict__ thr_in, const int* __restrict__ cnt_in,
+                                                         int Nq, int Nr, int Cp, int k, I* __restrict__ idx_out,
+                                                         int* __restrict__ row_flags) {
+  __shared__ unsigned short amb[8][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, q = blockIdx.x * 8 + warp;
+  if (q >= Nq) return;
+  const size_t rowi = (size_t)b * Nq + q;
+  const int cnt = cnt_in[rowi];
+  if (cnt >= kTcCap) {                                  // saturated list: hand the row to the exact kernel
+    if (lane == 0) row_flags[rowi] = 1;
+    return;
+  }
+  const float aa = anorm[rowi];
+  const float e = knn_margin(aa, __uint_as_float(bbmax_bits[b])) * 1.001f;
+  uint32_t w[4], x[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int t = u * 32 + lane;
+    w[u] = t < cnt ? __ldg(cand + rowi * kTcListLd + t) : 0u;
+    x[u] = ~w[u];                                       // ascending x = descending score; padding (all ones) last
+  }
+  // bitonic sort of the 128 keys, element p = u*32 + lane
+#pragma unroll
+  for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+      if (stride >= 32) {
+        const int du = stride >> 5;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if ((u & du) == 0) {
+            const bool up = ((u * 32) & size) == 0;
+            const uint32_t lo = min(x[u], x[u | du]), hi = max(x[u], x[u | du]);
+            x[u] = up ? lo : hi;
+            x[u | du] = up ? hi : lo;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t other = __shfl_xor_sync(kFull, x[u], stride);
+          const bool up = ((u * 32 + lane) & size) == 0;
+          const bool lower = (lane & stride) == 0;
+          x[u] = (lower == up) ? min(x[u], other) : max(x[u], other);
+        }
+      }
+    }
+  }
+  uint32_t xk = 0, xk1 = 0;                             // sorted[k-1], sorted[k]
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint32_t a0 = __shfl_sync(kFull, x[u], (k - 1) & 31);
+    const uint32_t a1 = __shfl_sync(kFull, x[u], k & 31);
+    if (((k - 1) >> 5) == u) xk = a0;
+    if ((k >> 5) == u) xk1 = a1;
+  }
+  const float dk = knn_delta_lo(~xk);                                   // k-th largest offset (lower end)
+  const float dk1 = cnt > k ? knn_delta_lo(~xk1) : -INFINITY;           // (k+1)-th; none if the list holds exactly k
+  // offsets at or above n0 may belong to d~ <= e, where the exact kernel's clamp makes the index decide
+  const float n0 = (0.5f * (aa - e) - __ldg(thr_in + rowi)) * 0.999f;
+  const bool in_ok = knn_delta_hi(dk1) < n0 || cnt == k;
+  const float in_thr = knn_delta_hi(dk1) + e;           // in:  delta_lo_j > this
+  const float out_thr = dk - e;                         // out: delta_hi_j < this
+  int n_in = 0, n_amb = 0;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const bool have = u * 32 + lane < cnt;
+    const float dlo = knn_delta_lo(w[u]), dhi = knn_delta_hi(dlo);
+    const int j = (int)(w[u] & 0xffffu);
+    const bool is_in = have && in_ok && dlo > in_thr;
+    const bool is_out = have && dhi < out_thr && dhi < n0;
+    const bool is_amb = have && !is_in && !is_out;
+    const unsigned m_in = __ballot_sync(kFull, is_in), m_amb = __ballot_sync(kFull, is_amb);
+    if (is_in) idx_out[rowi * k + n_in + __popc(m_in & lt)] = (I)j;
+    if (is_amb) amb[warp][n_amb + __popc(m_amb & lt)] = (unsigned short)j;
+    n_in += __popc(m_in);
+    n_amb += __popc(m_amb);
+  }
+  const int need = k - n_in;
+  if (need <= 0) return;                                // (n_in <= k always: an "in" entry has at most k-1 rivals)
+  if (n_amb < need) {                                   // cannot happen while the margin holds; stay safe
+    if (lane == 0) row_flags[rowi] = 1;
+    return;
+  }
+  __syncwarp();
+  const float4* ar = reinterpret_cast<const float4*>(an + rowi * Cp);
+  const float* B_g = bn + (size_t)b * Nr * Cp;
+  const float* bnorm_g = bnorm + (size_t)b * Nr;
+  LaneTopK top;
+  top.init(lane, need);
+  for (int r = 0; r < n_amb; r += 32) {
+    const int t = r + lane;
+    const bool have = t < n_amb;
+    const int j = have ? (int)amb[warp][t] : 0;
+    const float4* br = reinterpret_cast<const float4*>(B_g + (size_t)j * Cp);
+    float acc = 0.f;
+    if (have) {
+#pragma unroll 4
+      for (int c4 = 0; c4 < Cp / 4; ++c4) {            // ascending channels, one accumulator: knn.cu's order
+        const float4 a4 = __ldg(ar + c4);
+        const float4 b4 = __ldg(br + c4);
+        acc = fmaf(a4.x, b4.x, acc);
+        acc = fmaf(a4.y, b4.y, acc);
+        acc = fmaf(a4.z, b4.z, acc);
+        acc = fmaf(a4.w, b4.w, acc);
+      }
+    }
+    const float d2 = __fmaf_rn(-2.f, acc, __fadd_rn(aa, __ldg(bnorm_g + j)));
+    const unsigned db = dist_bits(d2);
+    if (r == 0) {                                       // n_amb >= need: the first `need` entries seed the set
+      top.fill(db, j, have && lane < need);
+      top.offer(db, j, have && lane >= need);
+    } else {
+      top.offer(db, j, have);
+    }
+  }
+  if (top.active) idx_out[rowi * k + n_in + lane] = (I)top.i;
+}
+
 // ---- host side ----
+size_t knn_tc_ext_floats(int B, int Nr);
 bool knn_tc_eligible(int Nq, int Nr, int C, int k) {
   const int Cp = (int)align_up(C, 32);
   return C >= 4 && Cp <= 128 && k <= 32 && Nr <= 65535 && Nr >= k;
 }
 
-size_t knn_tc_workspace_bytes(int B, int Nq) {
-  return align_up((size_t)B * Nq * kTcCap * sizeof(unsigned short), 256) + align_up((size_t)B * Nq * sizeof(int), 256);
+size_t knn_tc_workspace_bytes(int B, int Nq, int Nr) {
+  return align_up((size_t)B * Nq * kTcListLd * sizeof(uint32_t), 256) + align_up((size_t)B * Nq * sizeof(int), 256) +
+         align_up(knn_tc_ext_floats(B, Nr) * sizeof(float), 256);
 }
+// candidate-side norm slices, one 4 KB block per (cloud, tile of 128 candidates), already in the compact
+// no-swizzle operand layout (tc::nosw_offset) so that the kernel fetches a tile's slice with one bulk copy
+size_t knn_tc_ext_floats(int B, int Nr) { return (size_t)B * ceil_div(Nr, kTcTile) * (kExt / 4); }
 
 template <class I>
-int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const unsigned* bbmax, int B,
-                  int Nq, int Nr, int Cp, int k, float* thr, unsigned short* cand, int* cnt, I* idx, float* dist,
-                  int* row_flags, cudaStream_t st) {
+int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const float* bext,
+                  const unsigned* bbmax, int B, int Nq, int Nr, int Cp, int k, float* thr, uint32_t* cand, int* cnt,
+                  bool ordered, I* idx, float* dist, int* row_flags, cudaStream_t st) {
   const int nkb = Cp / 32;
+  alignas(64) CUtensorMap map_a, map_b;
+  if (int e = make_tile_map(&map_a, an, Cp, Nq, B, kTcRows)) return e;
+  if (int e = make_tile_map(&map_b, bn, Cp, Nr, B, kTcTile)) return e;
   dim3 grid(ceil_div(Nq, kTcRows), B);
   {
     size_t smem = tc_smem_bytes(nkb, false);
@@ -338,7 +484,7 @@ int launch_knn_tc(const float* an, const float* anorm, const float* bn, const fl
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("knn_tc pass A smem attribute");
     SAMBLE_PRE(st);
-    kern<<<grid, kTcThreads, smem, st>>>(an, anorm, bn, bnorm, bbmax, Nq, Nr, Cp, k, thr, cand, cnt);
+    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_b, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt);
     SAMBLE_LAUNCHED("knn_tc_threshold_kernel");
   }
   {
@@ -347,18 +493,24 @@ int launch_knn_tc(const float* an, const float* anorm, const float* bn, const fl
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("knn_tc pass B smem attribute");
     SAMBLE_PRE(st);
-    kern<<<grid, kTcThreads, smem, st>>>(an, anorm, bn, bnorm, bbmax, Nq, Nr, Cp, k, thr, cand, cnt);
+    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_b, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt);
     SAMBLE_LAUNCHED("knn_tc_collect_kernel");
   }
   SAMBLE_PRE(st);
-  knn_rerank_kernel<I><<<dim3(ceil_div(Nq, 8), B), 256, 0, st>>>(an, anorm, bn, bnorm, cand, cnt, Nq, Nr, Cp, k, idx, dist, row_flags);
-  SAMBLE_LAUNCHED("knn_rerank_kernel");
+  if (ordered) {
+    knn_rerank_kernel<I><<<dim3(ceil_div(Nq, 8), B), 256, 0, st>>>(an, anorm, bn, bnorm, cand, cnt, Nq, Nr, Cp, k, idx, dist, row_flags);
+    SAMBLE_LAUNCHED("knn_rerank_kernel");
+  } else {
+    knn_select_kernel<I><<<dim3(ceil_div(Nq, 8), B), 256, 0, st>>>(an, anorm, bn, bnorm, bbmax, cand, thr, cnt, Nq, Nr, Cp, k, idx, row_flags);
+    SAMBLE_LAUNCHED("knn_select_kernel");
+  }
   return SAMBLE_OK;
 }
 
-template int launch_knn_tc<int>(const float*, const float*, const float*, const float*, const unsigned*, int, int, int, int,
-                                int, float*, unsigned short*, int*, int*, float*, int*, cudaStream_t);
-template int launch_knn_tc<long long>(const float*, const float*, const float*, const float*, const unsigned*, int, int, int,
-                                      int, int, float*, unsigned short*, int*, long long*, float*, int*, cudaStream_t);
+template int launch_knn_tc<int>(const float*, const float*, const float*, const float*, const float*, const unsigned*, int, int,
+                                int, int, int, float*, uint32_t*, int*, bool, int*, float*, int*, cudaStream_t);
+template int launch_knn_tc<long long>(const float*, const float*, const float*, const float*, const float*, const unsigned*,
+                                      int, int, int, int, int, float*, uint32_t*, int*, bool, long long*, float*, int*,
+                                      cudaStream_t);
 
 }  // namespace samble

@@ -3,12 +3,23 @@
 // Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (vendored CUTLASS headers were read for the
 // field positions only; nothing is included from them).
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only; the encoder is resolved at run time, libcuda is not linked)
+
 #include "common.cuh"
 
 namespace samble {
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One lane of the (converged) warp.  Unlike `lane == 0`, elect.sync tells the compiler that exactly one thread
+// runs the guarded region, so descriptors and barrier addresses go straight to uniform registers instead of
+// through a per-lane broadcast loop (3x fewer instructions in the MMA issue loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -38,6 +49,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+// ---- TMA (bulk async copies; completion is counted in bytes on an mbarrier) ----
+// this thread's arrival + "expect `bytes` more" on the barrier
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// box of a 3-D tensor map -> shared memory (layout/swizzle as encoded in the map); coordinates innermost first
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// contiguous global -> shared copy, 16-byte aligned, size a multiple of 16
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
@@ -128,4 +163,10 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 }
 
 }  // namespace tc
+
+// host: rank-3 fp32 tensor map over a (batch, rows, inner) row-major array, box = (1, box_rows, 32 floats = 128 B),
+// 128-byte swizzle -- i.e. exactly the K-major SW128 operand tile smem_desc_sw128 describes; out-of-range rows and
+// channels read as zero.  Returns SAMBLE_OK or sets the error text.
+int make_tile_map(CUtensorMap* map, const float* base, int inner, int rows, int batch, int box_rows);
+
 }  // namespace samble

@@ -40,7 +40,7 @@ def _idx_bits(idx: Tensor) -> int:
 # ------------------------------------------------------------------ kNN
 
 
-def _knn_strided(a: Tensor, b: Tensor, k: int, layout: str, want_dist: bool, idx_dtype=torch.int64):
+def _knn_strided(a: Tensor, b: Tensor, k: int, layout: str, want_dist: bool, idx_dtype=torch.int64, ordered=True):
     """a, b: 3-D fp32 CUDA tensors in 'bnc' (B,N,C) or 'bcn' (B,C,N) layout, any strides."""
     dev = L.need_cuda(a, b)
     L.no_grad_check(a, b)
@@ -61,7 +61,7 @@ def _knn_strided(a: Tensor, b: Tensor, k: int, layout: str, want_dist: bool, idx
     nbytes = lib.samble_knn_workspace_bytes(B, Nq, Nr, Cc)
     ws = L.workspace(nbytes, dev)
     rc = lib.samble_knn(L.ptr(a), *sa, L.ptr(b), *sb_, B, Nq, Nr, Cc, k, L.ptr(idx), _idx_bits(idx), L.ptr(dist),
-                        L.ptr(ws), ws.numel(), L.stream())
+                        0 if ordered else 1, L.ptr(ws), ws.numel(), L.stream())
     L.check(rc, "samble_knn")
     return dist, idx
 
@@ -71,10 +71,11 @@ def knn(a: Tensor, b: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     return _knn_strided(a, b, k, "bnc", True)
 
 
-def knn_indices(pcd: Tensor, K: int, idx_dtype=torch.int32) -> Tensor:
+def knn_indices(pcd: Tensor, K: int, idx_dtype=torch.int32, ordered: bool = True) -> Tensor:
     """Self-kNN of a channel-major cloud (B,C,N) -> idx (B,N,K); the internal fast path
-    (int32 indices, no distance output, no permute copy)."""
-    return _knn_strided(pcd, pcd, K, "bcn", False, idx_dtype)[1]
+    (int32 indices, no distance output, no permute copy).  ordered=False (SAMBLE_KNN_ANY_ORDER): the same
+    neighbour SET per row in arbitrary order, for consumers that reduce over the neighbours."""
+    return _knn_strided(pcd, pcd, K, "bcn", False, idx_dtype, ordered)[1]
 
 
 # ------------------------------------------------------------------ gathers

@@ -29,13 +29,13 @@ def test_header_symbols_exported_and_bound(lib):
 def test_invalid_arguments_return_codes_not_crashes(lib):
     z = C.c_void_p(0)
     one = C.c_void_p(16)          # never dereferenced: validation fails first
-    assert lib.samble_knn(z, 0, 0, 0, z, 0, 0, 0, 1, 8, 8, 3, 4, z, 64, z, z, 0, z) == -1
+    assert lib.samble_knn(z, 0, 0, 0, z, 0, 0, 0, 1, 8, 8, 3, 4, z, 64, z, 0, z, 0, z) == -1
     assert b"null" in lib.samble_last_error()
-    assert lib.samble_knn(one, 0, 0, 0, one, 0, 0, 0, 1, 8, 8, 3, 33, one, 64, z, one, 1 << 20, z) == -1
+    assert lib.samble_knn(one, 0, 0, 0, one, 0, 0, 0, 1, 8, 8, 3, 33, one, 64, z, 0, one, 1 << 20, z) == -1
     assert b"k=33" in lib.samble_last_error()
-    assert lib.samble_knn(one, 0, 0, 0, one, 0, 0, 0, 1, 8, 4, 3, 5, one, 64, z, one, 1 << 20, z) == -1
-    assert lib.samble_knn(one, 0, 0, 0, one, 0, 0, 0, 1, 8, 8, 3, 4, one, 16, z, one, 1 << 20, z) == -1
-    assert lib.samble_knn(one, 0, 0, 0, one, 0, 0, 0, 1, 8, 8, 3, 4, one, 64, z, one, 8, z) == -1   # workspace too small
+    assert lib.samble_knn(one, 0, 0, 0, one, 0, 0, 0, 1, 8, 4, 3, 5, one, 64, z, 0, one, 1 << 20, z) == -1
+    assert lib.samble_knn(one, 0, 0, 0, one, 0, 0, 0, 1, 8, 8, 3, 4, one, 16, z, 0, one, 1 << 20, z) == -1
+    assert lib.samble_knn(one, 0, 0, 0, one, 0, 0, 0, 1, 8, 8, 3, 4, one, 64, z, 0, one, 8, z) == -1   # workspace too small
     assert lib.samble_group(one, one, 64, 1, 3, 8, 4, 7, one, z) == -1
     assert lib.samble_ds_sample(one, one, one, 1, 8, 9, 4, one, one, one, one, one, z, z) == -1
     assert lib.samble_ds_row_stats(one, 128, one, 128, one, 1, 8, 100, 4, one, one, one, z) == -1

@@ -234,6 +234,13 @@ def _knn_both(a, b, k):
     return (d0, i0), (d1, i1)
 
 
+def _same_sets_any_order(a, b, k, i_ref):
+    """SAMBLE_KNN_ANY_ORDER (knn_select_kernel): the same neighbour set per row, order free."""
+    i_any = ops._knn_strided(a, b, k, "bnc", False, torch.int32, ordered=False)[1]
+    torch.cuda.synchronize()
+    return torch.equal(i_any.long().sort(-1).values, i_ref.sort(-1).values)
+
+
 TC_SHAPES = [(2, 2048, 0, 128, 32), (2, 2048, 0, 64, 32), (3, 1000, 0, 128, 32), (2, 512, 0, 128, 16), (1, 700, 260, 20, 5),
              (2, 130, 0, 8, 32), (1, 64, 0, 128, 32), (1, 40, 33, 64, 32), (1, 4096, 0, 128, 32), (4, 300, 1200, 96, 3)]
 
@@ -248,6 +255,7 @@ def test_tensor_core_knn_is_bit_identical_to_exact_kernel(shape):
     (d0, i0), (d1, i1) = _knn_both(a, b, k)
     assert torch.equal(i0, i1)
     assert torch.equal(d0, d1)
+    assert _same_sets_any_order(a, b, k, i1)
 
 
 def test_tensor_core_knn_hard_cases():
@@ -259,12 +267,21 @@ def test_tensor_core_knn_hard_cases():
     a = cu(a.contiguous())
     (d0, i0), (d1, i1) = _knn_both(a, a, 32)
     assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    assert _same_sets_any_order(a, a, 32, i1)
     # (2) wildly different norms (margin driven by the largest candidate norm)
     s = cu(synthetic_features(2, 600, 64, 7) * (1 + 50 * (torch.rand(2, 600, 1, generator=g) > 0.97).float()))
     (d0, i0), (d1, i1) = _knn_both(s, s, 32)
     assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    assert _same_sets_any_order(s, s, 32, i1)
     # (3) low intrinsic dimension (a curve embedded in 128-d): many candidates near the threshold
     tt = torch.linspace(0, 1, 2048).view(1, 2048, 1)
     curve = cu(torch.cat([torch.sin(tt * (i + 1)) for i in range(128)], dim=-1).contiguous())
     (d0, i0), (d1, i1) = _knn_both(curve, curve, 32)
     assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    assert _same_sets_any_order(curve, curve, 32, i1)
+    # (4) k duplicates and more of every point: the clamp-to-zero tie rule decides, nothing is "certainly in"
+    base = synthetic_features(1, 40, 64, 11)
+    dup = cu(base.repeat(1, 40, 1).contiguous())          # 1600 points, each present 40 times
+    (d0, i0), (d1, i1) = _knn_both(dup, dup, 32)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    assert _same_sets_any_order(dup, dup, 32, i1)
