@@ -475,8 +475,8 @@ int launch_knn_tc(const float* an, const float* anorm, const float* bn, const fl
                   bool ordered, I* idx, float* dist, int* row_flags, cudaStream_t st) {
   const int nkb = Cp / 32;
   alignas(64) CUtensorMap map_a, map_b;
-  if (int e = make_tile_map(&map_a, an, Cp, Nq, B, kTcRows)) return e;
-  if (int e = make_tile_map(&map_b, bn, Cp, Nr, B, kTcTile)) return e;
+  if (int e = make_tile_map(&map_a, an, Cp, Cp, Nq, B, kTcRows)) return e;
+  if (int e = make_tile_map(&map_b, bn, Cp, Cp, Nr, B, kTcTile)) return e;
   dim3 grid(ceil_div(Nq, kTcRows), B);
   {
     size_t smem = tc_smem_bytes(nkb, false);

@@ -164,9 +164,10 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 
 }  // namespace tc
 
-// host: rank-3 fp32 tensor map over a (batch, rows, inner) row-major array, box = (1, box_rows, 32 floats = 128 B),
-// 128-byte swizzle -- i.e. exactly the K-major SW128 operand tile smem_desc_sw128 describes; out-of-range rows and
-// channels read as zero.  Returns SAMBLE_OK or sets the error text.
-int make_tile_map(CUtensorMap* map, const float* base, int inner, int rows, int batch, int box_rows);
+// host: rank-3 fp32 tensor map over a (batch, rows, inner) array with row pitch `ld` floats (16-byte multiple) and
+// batch pitch rows*ld, box = (1, box_rows, 32 floats = 128 B), 128-byte swizzle -- i.e. exactly the K-major SW128
+// operand tile smem_desc_sw128 describes; out-of-range rows and channels read as zero.
+// Returns SAMBLE_OK or sets the error text.
+int make_tile_map(CUtensorMap* map, const float* base, int inner, long long ld, int rows, int batch, int box_rows);
 
 }  // namespace samble

@@ -20,14 +20,14 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-int make_tile_map(CUtensorMap* map, const float* base, int inner, int rows, int batch, int box_rows) {
+int make_tile_map(CUtensorMap* map, const float* base, int inner, long long ld, int rows, int batch, int box_rows) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return SAMBLE_E_CUDA;
   }
   const cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
-  const cuuint64_t strides[2] = {(cuuint64_t)inner * sizeof(float), (cuuint64_t)inner * rows * sizeof(float)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)ld * rows * sizeof(float)};
   const cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
