@@ -130,6 +130,17 @@ int samble_linear(const float* X, long long ldx, int x_channel_major, const floa
                   float* out, long long ldo, int out_channel_major, int M, int K, int Nout, int points_per_cloud,
                   samble_stream_t stream);
 
+/* The same layer followed by max and/or mean over the points of each cloud -- conv -> max/avg pool of
+ * models/seg_model.py:199-203, cls_model.py:104/133 (res-link max), embedding.py:88-89 (STN) -- without ever storing
+ * the (M x Nout) activation: the epilogue reduces each 32-row group in registers, a second tiny kernel combines the
+ * groups of a cloud in a fixed order (deterministic).  X row-major; points_per_cloud a multiple of 32.
+ * out_max / out_mean: (M / points_per_cloud, Nout), either may be NULL. */
+size_t samble_linear_pool_workspace_bytes(int M, int Nout);
+int samble_linear_pool(const float* X, long long ldx, const float* W, const float* W_lo, long long ldw,
+                       const float* scale, const float* shift, long long shift_cloud_stride, int lrelu,
+                       int M, int K, int Nout, int points_per_cloud, float* out_max, float* out_mean,
+                       void* ws, size_t ws_bytes, samble_stream_t stream);
+
 /* ------------------------------------------------------------ EdgeConv ----------
  * models/embedding.py:29-39 fused (eval mode): group -> conv1+BN+LeakyReLU(0.2) -> conv2+BN+LeakyReLU
  * -> max over K.  conv1 is linear in [x_i ; x_j - x_i], so the caller projects the N points once:

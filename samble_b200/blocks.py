@@ -61,6 +61,17 @@ def cbl(seq: nn.Sequential, x: Tensor, x_layout: str = "bcn", out_layout: str = 
                       shift=b if shift_extra is None else shift_extra, lrelu=True)
 
 
+def cbl_pool(seq: nn.Sequential, x: Tensor, x_layout: str = "bcn", want_max: bool = True, want_mean: bool = True):
+    """(cbl(seq, x).max over points, .mean over points) with the activation never stored (ops.linear_pool).
+    Falls back to the unfused form when a cloud is not a whole number of 32-point groups."""
+    a, b = folded(seq[1])
+    x_rows = x.transpose(1, 2).contiguous() if x_layout == "bcn" else x
+    if x_rows.shape[1] % 32:
+        y = ops.linear(x_rows, seq[0].weight, scale=a, shift=b, lrelu=True)
+        return (y.max(dim=1)[0] if want_max else None), (y.mean(dim=1) if want_mean else None)
+    return ops.linear_pool(x_rows, seq[0].weight, scale=a, shift=b, lrelu=True, want_max=want_max, want_mean=want_mean)
+
+
 class _FoldCache:
     """Folded weights of an edge MLP, recomputed only when a parameter/buffer was modified in place
     (tensor._version) or moved."""

@@ -231,8 +231,7 @@ static int launch_linear(const LinArgs& a, cudaStream_t st) {
   return SAMBLE_OK;
 }
 
-template <int NT>
-int launch_linear_tma(const LinArgs& a, cudaStream_t st);   // linear_tma.cu
+int launch_linear_tma_auto(const LinArgs& a, int nacc, cudaStream_t st);   // linear_tma.cu
 
 }  // namespace samble
 
@@ -271,11 +270,61 @@ extern "C" int samble_linear(const float* X, long long ldx, int x_channel_major,
                  "samble_linear: M=%d is not a whole number of clouds of %d points", M, points_per_cloud);
   SAMBLE_REQUIRE(ceil_div(Nout, 64) <= 65535, "samble_linear: Nout too large");
   LinArgs a{X, ldx, W, ldw, W_lo, scale, shift, residual, ldr, out, ldo, M, K, Nout, need_npc ? points_per_cloud : 0,
-            lrelu, x_channel_major, out_channel_major, residual_first, residual_channel_major, shift_cloud_stride};
+            lrelu, x_channel_major, out_channel_major, residual_first, residual_channel_major, shift_cloud_stride,
+            nullptr, nullptr};
   cudaStream_t st = (cudaStream_t)stream;
   const int nacc = ceil_div(ceil_div(K, 32), kLinChain);
   SAMBLE_REQUIRE(nacc * 64 <= 512, "samble_linear: K=%d too large (max %d)", K, 8 * kLinChain * 32);
   const bool wide = Nout > 64 && nacc * 128 <= 512;
-  if (!x_channel_major) return wide ? launch_linear_tma<128>(a, st) : launch_linear_tma<64>(a, st);
+  if (!x_channel_major) return launch_linear_tma_auto(a, nacc, st);
   return wide ? launch_linear<128>(a, st) : launch_linear<64>(a, st);
+}
+
+// ---- pooled linear: max / mean over the points of each cloud of  lrelu(X W^T * scale + shift), y never stored ----
+__global__ void linear_pool_finalize_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int groups_per_cloud,
+                                            int Nout, int npc, float* __restrict__ out_max, float* __restrict__ out_mean) {
+  const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Nout) return;
+  float m = -INFINITY, s = 0.f;
+  for (int g = 0; g < groups_per_cloud; ++g) {        // fixed order: deterministic
+    const long long o = ((long long)b * groups_per_cloud + g) * Nout + c;
+    m = fmaxf(m, pmax[o]);
+    if (psum) s += psum[o];
+  }
+  if (out_max) out_max[(long long)b * Nout + c] = m;
+  if (out_mean) out_mean[(long long)b * Nout + c] = s / (float)npc;
+}
+
+extern "C" size_t samble_linear_pool_workspace_bytes(int M, int Nout) {
+  if (M <= 0 || Nout <= 0) return 0;
+  return 2 * align_up((size_t)ceil_div(M, 32) * Nout * sizeof(float), 256) + 256;
+}
+
+extern "C" int samble_linear_pool(const float* X, long long ldx, const float* W, const float* W_lo, long long ldw,
+                                  const float* scale, const float* shift, long long shift_cloud_stride, int lrelu, int M,
+                                  int K, int Nout, int points_per_cloud, float* out_max, float* out_mean, void* ws,
+                                  size_t ws_bytes, samble_stream_t stream) {
+  SAMBLE_REQUIRE(X && W && W_lo && ws && (out_max || out_mean), "samble_linear_pool: null pointer");
+  SAMBLE_REQUIRE(ldw % 4 == 0 && ldw >= ((K + 3) / 4) * 4 && ((uintptr_t)W | (uintptr_t)W_lo) % 16 == 0,
+                 "samble_linear_pool: weight rows must be 16-byte aligned and zero-padded to a multiple of 4 columns");
+  SAMBLE_REQUIRE(ldx % 4 == 0 && ldx >= ((K + 3) / 4) * 4 && (uintptr_t)X % 16 == 0,
+                 "samble_linear_pool: X needs 16-byte aligned rows, zero-padded to a multiple of 4 columns");
+  SAMBLE_REQUIRE(M > 0 && K > 0 && Nout > 0, "samble_linear_pool: bad shape M=%d K=%d Nout=%d", M, K, Nout);
+  SAMBLE_REQUIRE(points_per_cloud > 0 && points_per_cloud % 32 == 0 && M % points_per_cloud == 0,
+                 "samble_linear_pool: clouds of %d points (must be a multiple of 32 dividing M=%d)", points_per_cloud, M);
+  SAMBLE_REQUIRE(ws_bytes >= samble_linear_pool_workspace_bytes(M, Nout), "samble_linear_pool: workspace too small");
+  const int nacc = ceil_div(ceil_div(K, 32), kLinChain);
+  SAMBLE_REQUIRE(nacc * 64 <= 512, "samble_linear_pool: K=%d too large (max %d)", K, 8 * kLinChain * 32);
+  Workspace w(ws, ws_bytes);
+  float* pmax = w.take<float>((size_t)ceil_div(M, 32) * Nout);
+  float* psum = w.take<float>((size_t)ceil_div(M, 32) * Nout);
+  LinArgs a{X, ldx, W, ldw, W_lo, scale, shift, nullptr, 0, nullptr, 0, M, K, Nout, points_per_cloud,
+            lrelu, 0, 0, 0, 0, shift_cloud_stride, pmax, out_mean ? psum : nullptr};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = launch_linear_tma_auto(a, nacc, st)) return e;
+  SAMBLE_PRE(st);
+  linear_pool_finalize_kernel<<<dim3(ceil_div(Nout, 128), M / points_per_cloud), 128, 0, st>>>(
+      pmax, out_mean ? psum : nullptr, points_per_cloud / 32, Nout, points_per_cloud, out_max, out_mean);
+  SAMBLE_LAUNCHED("linear_pool_finalize_kernel");
+  return SAMBLE_OK;
 }

@@ -22,28 +22,37 @@ struct LtPlan {
   int stages;       // X (or X+W) ring depth
   int w_res;        // weight slice resident
   int stage_bytes;
+  int staged;       // epilogue staging slab present
   size_t smem;
 };
+
+constexpr size_t kLtFixed = 1024 /* alignment slack */ + 512 /* barriers */;
+constexpr size_t kLtLimit = 227 * 1024;
+
+// Resident weights need a ring of at least 3 X stages next to them to hide the TMA latency.  The epilogue staging
+// slab (coalesced row-major stores, measured ~10% on the streaming shapes) is taken only when it costs no stage.
+template <int NT>
+static bool lt_resident_ok(int K) {
+  const int nkb = (K + 31) / 32;
+  return (size_t)2 * nkb * NT * 128 + (size_t)3 * 32768 + kLtFixed <= kLtLimit;
+}
 
 template <int NT>
 static LtPlan lt_plan(int K) {
   const int nkb = (K + 31) / 32;
   LtPlan p;
-  const size_t limit = 227 * 1024 - 2048;
-  const size_t wres = (size_t)2 * nkb * NT * 128;
-  if (wres + 2 * 32768 <= limit) {
-    p.w_res = 1;
-    p.stage_bytes = 32768;
-    p.stages = (int)((limit - wres) / 32768);
-    if (p.stages > 4) p.stages = 4;
-    p.smem = wres + (size_t)p.stages * 32768 + 2048;
-  } else {
-    p.w_res = 0;
-    p.stage_bytes = 32768 + 2 * NT * 128;
-    p.stages = (int)(limit / p.stage_bytes);
-    if (p.stages > 4) p.stages = 4;
-    p.smem = (size_t)p.stages * p.stage_bytes + 2048;
+  const size_t wres = lt_resident_ok<NT>(K) ? (size_t)2 * nkb * NT * 128 : 0;
+  p.w_res = wres != 0;
+  p.stage_bytes = p.w_res ? 32768 : 32768 + 2 * NT * 128;
+  const size_t room = kLtLimit - kLtFixed - wres;
+  p.stages = (int)(room / p.stage_bytes);
+  if (p.stages > 4) p.stages = 4;
+  p.staged = room - (size_t)p.stages * p.stage_bytes >= (size_t)kLinSlabBytes;
+  if (!p.staged && p.stages == 4) {          // 4 -> 3 stages still hides the latency
+    p.stages = 3;
+    p.staged = 1;
   }
+  p.smem = wres + (size_t)p.stages * p.stage_bytes + (p.staged ? kLinSlabBytes : 0) + kLtFixed;
   return p;
 }
 
@@ -57,14 +66,16 @@ __device__ __forceinline__ void lt_range(int total, int& t0, int& t1) {
 template <int NT>
 __global__ void __launch_bounds__(kLtThreads, 1)
     linear_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                      const __grid_constant__ CUtensorMap map_wlo, LinArgs a, int stages, int w_res, int stage_bytes) {
+                      const __grid_constant__ CUtensorMap map_wlo, LinArgs a, int stages, int w_res, int stage_bytes,
+                      int staged) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nkb = (a.K + 31) / 32;
   const int wtile = NT * 128;                                   // one K-block of the weight slice
   uint8_t* wres = base;                                         // [hi: nkb tiles][lo: nkb tiles]   (w_res only)
   uint8_t* ring = base + (w_res ? (size_t)2 * nkb * wtile : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)stages * stage_bytes);
+  float* slab = reinterpret_cast<float*>(ring + (size_t)stages * stage_bytes);       // epilogue staging (4 warps)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(slab) + (staged ? kLinSlabBytes : 0));
   uint64_t* landed = bars;            // [4] TMA bytes of the stage arrived
   uint64_t* ready = bars + 4;         // [4] ... and X_lo written (4 splitter-warp arrivals)
   uint64_t* empty = bars + 8;         // [4] tcgen05.commit: stage consumed
@@ -211,7 +222,12 @@ __global__ void __launch_bounds__(kLtThreads, 1)
       const int m0 = (tile % mtiles) * 128, n0 = (tile / mtiles) * NT;
       tc::mbar_wait(&tfull[set], use & 1);
       tc::tc_fence_after();
-      linear_epilogue_tile<NT>(a, tmem, set, nacc, m0, n0, warp, lane);
+      if (a.pool_max)
+        linear_epilogue_tile_pool<NT>(a, tmem, set, nacc, m0, n0, warp, lane);
+      else if (a.out_cm || (a.residual && a.res_cm) || !staged)
+        linear_epilogue_tile<NT>(a, tmem, set, nacc, m0, n0, warp, lane);
+      else
+        linear_epilogue_tile_staged<NT>(a, tmem, set, nacc, m0, n0, warp, lane, slab);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[set]);
@@ -237,12 +253,14 @@ int launch_linear_tma(const LinArgs& a, cudaStream_t st) {
   const long long total = (long long)ceil_div(a.M, 128) * ceil_div(a.Nout, NT);
   const int grid = (int)(total < 148 ? total : 148);
   SAMBLE_PRE(st);
-  kern<<<grid, kLtThreads, p.smem, st>>>(mx, mw, mwl, a, p.stages, p.w_res, p.stage_bytes);
+  kern<<<grid, kLtThreads, p.smem, st>>>(mx, mw, mwl, a, p.stages, p.w_res, p.stage_bytes, p.staged);
   SAMBLE_LAUNCHED("linear_tma_kernel");
   return SAMBLE_OK;
 }
 
-template int launch_linear_tma<64>(const LinArgs&, cudaStream_t);
-template int launch_linear_tma<128>(const LinArgs&, cudaStream_t);
+int launch_linear_tma_auto(const LinArgs& a, int nacc, cudaStream_t st) {
+  const bool wide_ok = a.Nout > 64 && nacc * 128 <= 512;
+  return wide_ok ? launch_linear_tma<128>(a, st) : launch_linear_tma<64>(a, st);
+}
 
 }  // namespace samble

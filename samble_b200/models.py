@@ -47,7 +47,7 @@ class STN(nn.Module):
 
     def _tail(self, x: Tensor) -> Tensor:
         B = x.size(0)
-        x = (self.conv3(x) if self.training else blocks.cbl(self.conv3, x)).max(dim=-1, keepdim=False)[0]
+        x = self.conv3(x).max(dim=-1, keepdim=False)[0] if self.training else blocks.cbl_pool(self.conv3, x, want_mean=False)[0]
         x = self.dp2(self.linear2(self.dp1(self.linear1(x))))
         return self.transform(x).view(B, 3, 3)
 
@@ -160,15 +160,18 @@ class ShapeNetModel(nn.Module):
         else:
             # head on the tensor cores (linear_tc.cu); BatchNorms folded; conv2 over cat([g.repeat(N), f]) ==
             # W_g g (one vector per cloud, folded into a per-cloud shift) + W_f f (per point)
-            g = blocks.cbl(self.conv, f)
-            g = torch.cat([g.max(dim=-1, keepdim=True)[0], g.mean(dim=-1, keepdim=True), self.conv1(category_id)], dim=1)
+            # The head stays point-major between its layers (one transpose in, the last GEMM writes (B,50,N)); the
+            # 1024-channel global branch is pooled inside the GEMM epilogue and never stored.
+            f_rows = f.transpose(1, 2).contiguous()                           # (B,N,C)
+            gmax, gmean = blocks.cbl_pool(self.conv, f_rows, x_layout="rows")
+            g = torch.cat([gmax, gmean, self.conv1(category_id).squeeze(-1)], dim=1)     # (B, 2048+64)
             w2 = self.conv2[0].weight
             ng = g.shape[1]
             a2, b2 = blocks.folded(self.conv2[1])
-            gv = F.conv1d(g, w2[:, :ng]).squeeze(-1)                          # (B,1024)
-            y = ops.linear(f, w2[:, ng:, 0], x_layout="bcn", out_layout="bcn", scale=a2, shift=gv * a2 + b2, lrelu=True)
-            y = blocks.cbl(self.conv3, y)
-            y = ops.linear(y, self.conv4.weight, x_layout="bcn", out_layout="bcn")
+            gv = g @ w2[:, :ng, 0].t()                                        # (B,1024)
+            y = ops.linear(f_rows, w2[:, ng:, 0], scale=a2, shift=gv * a2 + b2, lrelu=True)      # (B,N,1024)
+            y = blocks.cbl(self.conv3, y, x_layout="rows", out_layout="rows")
+            y = ops.linear(y, self.conv4.weight, out_layout="bcn")
         return (y, trans) if self.stn_regularization_loss_factor > 0 else y
 
 
@@ -189,6 +192,12 @@ class ClsFeatureLearningBlock(_BlockBase):
             self.conv = nn.Conv1d(outs[-1], 1024, kernel_size=1, bias=False)
         self.M_list = cfg.downsample.M
 
+    def _pooled(self, conv: nn.Conv1d, x: Tensor) -> Tensor:
+        """conv(x).max(dim=-1)[0] (cls_model.py:104,133); eval mode pools inside the GEMM epilogue."""
+        if self.training or x.shape[-1] % 32:
+            return conv(x).max(dim=-1)[0]
+        return ops.linear_pool(x.transpose(1, 2).contiguous(), conv.weight, want_mean=False)[0]
+
     @fp32_forward
     def forward(self, x: Tensor):
         x_xyz = x.clone()
@@ -196,13 +205,13 @@ class ClsFeatureLearningBlock(_BlockBase):
         if not self.res_link_enable:
             for i, ds in enumerate(self.downsample_list):
                 x = self.feature_learning_layer_list[i + 1](ds(x)[0][0])
-            return self.conv(x).max(dim=-1)[0]
-        res = [self.conv_list[0](x).max(dim=-1)[0]]
+            return self._pooled(self.conv, x)
+        res = [self._pooled(self.conv_list[0], x)]
         for i, ds in enumerate(self.downsample_list):
             (x, idx_select) = ds(x, x_xyz)[0]
             x = self.feature_learning_layer_list[i + 1](x)
             x_xyz = ops.gather_by_idx(x_xyz, idx_select)
-            res.append(self.conv_list[i + 1](x).max(dim=-1)[0])
+            res.append(self._pooled(self.conv_list[i + 1], x))
         self.res_link_list = res
         return torch.cat(res, dim=1), res
 

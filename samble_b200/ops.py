@@ -279,6 +279,37 @@ def linear(x: Tensor, weight: Tensor, *, x_layout: str = "rows", out_layout: str
     return out
 
 
+def linear_pool(x: Tensor, weight: Tensor, *, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None,
+                lrelu: bool = False, want_max: bool = True, want_mean: bool = True):
+    """max / mean over the points of each cloud of  lrelu(x W^T * scale + shift)  without storing the activation
+    (samble_linear_pool).  x: (B, P, K) row-major with P % 32 == 0.  Returns (max (B,Nout) | None, mean (B,Nout) | None)."""
+    dev = L.need_cuda(x, weight, scale, shift)
+    L.no_grad_check(x, weight)
+    w, w_lo = _split_weight(weight)
+    Nout, K = weight.shape[0], weight[0].numel()
+    x = _f32(x, "x")
+    B, P, Kx = x.shape
+    if Kx != K:
+        raise RuntimeError(f"linear_pool: x has {Kx} channels, weight expects {K}")
+    x2 = x.reshape(B * P, Kx)
+    if x2.stride(1) != 1 or Kx % 4 != 0 or x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = torch.nn.functional.pad(x2, (0, (-Kx) % 4)).contiguous()
+    shift_ldb = 0
+    if shift is not None:
+        shift = _f32(shift, "shift").contiguous()
+        shift_ldb = Nout if shift.dim() == 2 else 0
+    if scale is not None:
+        scale = _f32(scale, "scale").contiguous()
+    omax = torch.empty(B, Nout, dtype=torch.float32, device=dev) if want_max else None
+    omean = torch.empty(B, Nout, dtype=torch.float32, device=dev) if want_mean else None
+    lib = L.lib()
+    ws = L.workspace(lib.samble_linear_pool_workspace_bytes(B * P, Nout), dev)
+    L.check(lib.samble_linear_pool(L.ptr(x2), x2.stride(0), L.ptr(w), L.ptr(w_lo), w.stride(0), L.ptr(scale), L.ptr(shift),
+                                   shift_ldb, 1 if lrelu else 0, B * P, K, Nout, P, L.ptr(omax), L.ptr(omean),
+                                   L.ptr(ws), ws.numel(), L.stream()), "samble_linear_pool")
+    return omax, omean
+
+
 def edge_mlp_max(pr: Tensor, idx: Tensor, w2: Tensor, b2: Tensor) -> Tensor:
     """Fused EdgeConv core (csrc/edgeconv.cu): pr (B,N,2*C1) = [P'|R'] point projections, idx (B,N,K),
     w2 (C2,C1), b2 (C2) -> (B,C2,N).  models/embedding.py:29-39 after folding eval-mode BatchNorm."""

@@ -90,3 +90,40 @@ def test_linear_3xtf32_matches_fp64(case):
     fp32 = (x_rows @ w.t()).double()                    # what a plain fp32 GEMM on the CPU gives, for scale
     print(f"max err vs fp64 {err:.2e}; an fp32 CPU GEMM is off by {(fp32 - x_rows.double() @ w.double().t()).abs().max().item():.2e}")
     assert err < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+POOL_CASES = [(2, 256, 128, 1024, True, "shared", True), (3, 96, 64, 200, False, None, False), (1, 2048, 128, 1024, True, "cloud", True),
+              (4, 32, 36, 50, True, "shared", True), (2, 512, 512, 128, False, "shared", True)]
+
+
+@pytest.mark.parametrize("case", POOL_CASES, ids=[f"B{c[0]}_P{c[1]}_K{c[2]}_N{c[3]}" for c in POOL_CASES])
+def test_linear_pool_matches_fp64(case):
+    """samble_linear_pool: max / mean over each cloud's points of the fused layer, activation never stored."""
+    from samble_b200 import ops
+
+    B, P, K, Nout, use_scale, shift_kind, lrelu = case
+    g = torch.Generator().manual_seed(B * 77 + P + K)
+    x = torch.randn(B, P, K, generator=g) * 2
+    w = torch.randn(Nout, K, generator=g) / K ** 0.5
+    scale = torch.rand(Nout, generator=g) + 0.5 if use_scale else None
+    shift = None if shift_kind is None else (torch.randn(Nout, generator=g) if shift_kind == "shared" else torch.randn(B, Nout, generator=g))
+    ref = x.double() @ w.double().t()
+    if scale is not None:
+        ref = ref * scale.double()
+    if shift is not None:
+        ref = ref + (shift.double() if shift.dim() == 1 else shift.double().unsqueeze(1))
+    if lrelu:
+        ref = torch.where(ref > 0, ref, 0.2 * ref)
+    mx, mean = ops.linear_pool(x.cuda(), w.cuda(), scale=None if scale is None else scale.cuda(),
+                               shift=None if shift is None else shift.cuda(), lrelu=lrelu)
+    torch.cuda.synchronize()
+    tol = 2e-5 * max(1.0, ref.abs().max().item())
+    assert (mx.double().cpu() - ref.max(dim=1)[0]).abs().max().item() < tol
+    assert (mean.double().cpu() - ref.mean(dim=1)).abs().max().item() < tol
+    only_max, none = ops.linear_pool(x.cuda(), w.cuda(), scale=None if scale is None else scale.cuda(),
+                                     shift=None if shift is None else shift.cuda(), lrelu=lrelu, want_mean=False)
+    assert none is None and torch.equal(only_max, mx)
+    # deterministic: fixed reduction order, no atomics
+    mx2, mean2 = ops.linear_pool(x.cuda(), w.cuda(), scale=None if scale is None else scale.cuda(),
+                                 shift=None if shift is None else shift.cuda(), lrelu=lrelu)
+    assert torch.equal(mx, mx2) and torch.equal(mean, mean2)

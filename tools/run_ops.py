@@ -50,9 +50,24 @@ if os.environ.get("PROFILE", "0") == "1":
         print(f"  {kname:28s} {n:5d} launches  {ms / n * 1e3:9.1f} us avg")
 
 if "linear" in which:
-    for (M, K, Nn) in [(B * N, 128, 384), (B * N, 128, 512), (B * N, 512, 128), (B * N, 128, 1024), (B * N, 1024, 256), (B * N // 2, 128, 384), (B * N, 64, 128)]:
+    # GPU-side kernel time from the library's own event pairs (host launch overhead ~30 us would hide short kernels)
+    shapes = [(B * N, 128, 384), (B * N, 128, 512), (B * N, 512, 128), (B * N, 128, 1024), (B * N, 1024, 256),
+              (B * N // 2, 128, 384), (B * N, 64, 128), (B * N, 256, 128), (B * N // 4, 512, 128)]
+    for (M, K, Nn) in shapes:
         xx = torch.randn(M, K, device=dev)
         ww = torch.randn(Nn, K, device=dev)
-        bench(f"lin {K}->{Nn}", lambda: ops.linear(xx, ww), 2.0 * M * K * Nn)
-        torch.backends.cuda.matmul.allow_tf32 = False
-        bench(f" cublas fp32", lambda: xx @ ww.t(), 2.0 * M * K * Nn)
+        sc, sh = torch.rand(Nn, device=dev) + 0.5, torch.randn(Nn, device=dev)
+        for _ in range(3):
+            ops.linear(xx, ww, scale=sc, shift=sh, lrelu=True)
+        torch.cuda.synchronize()
+        L.profile(True)
+        for _ in range(10):
+            ops.linear(xx, ww, scale=sc, shift=sh, lrelu=True)
+        torch.cuda.synchronize()
+        rep = L.profile_report()
+        L.profile(False)
+        n, ms = [v for k, v in rep.items() if k.startswith("linear")][0]
+        us = ms / n * 1e3
+        mma_us = 3 * 2.0 * M * K * Nn / 1151e12 * 1e6
+        print(f"lin {K:4d}->{Nn:4d} M={M:6d}  {us:7.1f} us   {2.0 * M * K * Nn / us / 1e6:6.1f} TF/s(fp32-equiv)   tensor-pipe floor {mma_us:5.1f} us"
+              f"   out {M * Nn * 4 / 1e6:5.0f} MB", flush=True)
