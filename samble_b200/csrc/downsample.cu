@@ -86,8 +86,11 @@ __global__ void __launch_bounds__(256, 2)
 }
 
 // ---- pass 2 -------------------------------------------------------------------------------
-// grid (P, B); CTA = W warps; warp w of chunk p owns rows [ (p*W + w)*RW, +RW ) and walks them in
-// order; lanes = the K neighbours of the row (distinct columns => race-free private accumulation).
+// grid (P, B); CTA = W warps; warp w of chunk p owns rows [ (p*W + w)*RW, +RW ) and walks them in order.
+// Per row the warp fetches the K neighbour key rows with coalesced 16-byte loads (lane = 4-channel chunk, all K loads
+// in flight at once), multiplies by its chunk of q_i, and reduces the 32 x 32 partial products with a halving
+// butterfly (31 shuffles) that leaves neighbour e's logit in lane e.  Lane e then adds p_ie to ITS column of the
+// warp-private column sums (the K neighbours of a row are distinct => race-free, no float atomics, fixed order).
 template <class I>
 __global__ void __launch_bounds__(256) ds_edge_partial_kernel(const float* __restrict__ q, long long ldq,
                                                               const float* __restrict__ k, long long ldk,
@@ -100,30 +103,44 @@ __global__ void __launch_bounds__(256) ds_edge_partial_kernel(const float* __res
   const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, p = blockIdx.x, P = gridDim.x;
   float* col = sm + (size_t)warp * N;                 // this warp's private partial column sums
-  float* qrow = sm + (size_t)W * N + warp * D;        // staged query row
   for (int j = lane; j < N; j += 32) col[j] = 0.f;
   __syncwarp();
+  const int nch = D >> 2;                             // 16-byte chunks per row
   const int r0 = (p * W + warp) * RW;
   for (int i = r0; i < min(r0 + RW, N); ++i) {
     const long long row = (long long)b * N + i;
-    for (int c = lane; c < D; c += 32) qrow[c] = q[row * ldq + c];
-    __syncwarp();
+    const float rmax = rowmax[row], rsum = rowsum[row];
     for (int e0 = 0; e0 < K; e0 += 32) {
       const int e = e0 + lane;
-      if (e < K) {
-        const int j = ld_idx(idx, row * K + e);
-        const float4* kr = reinterpret_cast<const float4*>(k + ((long long)b * N + j) * ldk);
-        float acc = 0.f;
-        for (int c = 0; c < D; c += 4) {
-          const float4 kv = __ldg(kr + (c >> 2));
-          acc = fmaf(qrow[c], kv.x, acc);
-          acc = fmaf(qrow[c + 1], kv.y, acc);
-          acc = fmaf(qrow[c + 2], kv.z, acc);
-          acc = fmaf(qrow[c + 3], kv.w, acc);
+      const int j_mine = e < K ? (int)ld_idx(idx, row * K + e) : 0;
+      float acc[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) acc[t] = 0.f;
+      for (int c = lane; c < nch; c += 32) {
+        const float4 qv = __ldg(reinterpret_cast<const float4*>(q + row * ldq) + c);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int j = __shfl_sync(kFull, j_mine, t);
+          const float4 kv = __ldg(reinterpret_cast<const float4*>(k + ((long long)b * N + j) * ldk) + c);
+          acc[t] = fmaf(qv.x, kv.x, acc[t]);
+          acc[t] = fmaf(qv.y, kv.y, acc[t]);
+          acc[t] = fmaf(qv.z, kv.z, acc[t]);
+          acc[t] = fmaf(qv.w, kv.w, acc[t]);
         }
-        const float pr = __fdiv_rn(expf(__fdiv_rn(acc, scale) - rowmax[row]), rowsum[row]);
-        col[j] += pr;
-        atomicAdd(indeg + (long long)b * N + j, 1);
+      }
+#pragma unroll
+      for (int w = 16; w >= 1; w >>= 1) {
+        const bool upper = (lane & w) != 0;
+#pragma unroll
+        for (int t = 0; t < w; ++t) {
+          const float keep = upper ? acc[t + w] : acc[t], send = upper ? acc[t] : acc[t + w];
+          acc[t] = keep + __shfl_xor_sync(kFull, send, w);
+        }
+      }
+      if (e < K) {                                    // acc[0] = logit numerator of neighbour e0 + lane
+        const float pr = __fdiv_rn(expf(__fdiv_rn(acc[0], scale) - rmax), rsum);
+        col[j_mine] += pr;
+        atomicAdd(indeg + (long long)b * N + j_mine, 1);
       }
       __syncwarp();
     }
@@ -218,7 +235,8 @@ extern "C" int samble_ds_edge_score(const float* q, long long ldq, const float* 
   SAMBLE_REQUIRE(q && k && rowmax && rowsum && idx && score && ws, "samble_ds_edge_score: null pointer");
   SAMBLE_REQUIRE(B > 0 && N > 0 && K > 0 && B <= 65535, "samble_ds_edge_score: bad shape");
   SAMBLE_REQUIRE(D > 0 && D % 4 == 0 && D <= 256, "samble_ds_edge_score: D=%d must be a multiple of 4, <= 256", D);
-  SAMBLE_REQUIRE(ldk % 4 == 0 && (uintptr_t)k % 16 == 0, "samble_ds_edge_score: k needs 16-byte aligned rows");
+  SAMBLE_REQUIRE(ldk % 4 == 0 && (uintptr_t)k % 16 == 0 && ldq % 4 == 0 && (uintptr_t)q % 16 == 0,
+                 "samble_ds_edge_score: q and k need 16-byte aligned rows");
   SAMBLE_REQUIRE(idx_bits == 32 || idx_bits == 64, "samble_ds_edge_score: idx_bits must be 32 or 64");
   EdgePlan e = edge_plan(B, N, 256);
   SAMBLE_REQUIRE(e.W >= 1, "samble_ds_edge_score: N=%d too large for one shared-memory column buffer", N);

@@ -187,6 +187,178 @@ __global__ void __launch_bounds__(256) knn_xyz_kernel(const float4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// K1b: xyz kNN in two passes -- same distances, same answer, ~5x fewer instructions (profiles/r1_knn_xyz.md: K1 spends
+// 90% of its issue slots on k-set insertions, ~165 per query at k=32, N=2048).
+//   pass 1  each lane keeps the minimum distance of two interleaved candidate groups (64 groups per query); the k-th
+//           smallest group minimum T bounds the k-th nearest distance (k distinct candidates reach it)
+//   pass 2  distances are recomputed (bit-identical) and the few candidates with d <= T (~45 of 2048) are appended to a
+//           per-query list as (distance bits, index) keys
+//   final   rank counting over the list: the key with r smaller keys is the r-th neighbour (distance, then index --
+//           the order of K1's LaneTopK); a list that overflows sends the whole CTA back to K1's algorithm.
+// ------------------------------------------------------------------------------------------
+constexpr int kXyzCap = 128;          // list entries per query
+
+__device__ __forceinline__ unsigned xyz_dist_bits(float ax, float ay, float az, float aw, const float4 p) {
+  float acc = __fmul_rn(ax, p.x);
+  acc = __fmaf_rn(ay, p.y, acc);
+  acc = __fmaf_rn(az, p.z, acc);
+  acc = __fadd_rn(acc, aw);
+  acc = __fadd_rn(acc, p.w);
+  return dist_bits(acc);
+}
+
+size_t knn_xyz2_smem() { return (size_t)kXyzChunk * sizeof(float4) + (size_t)8 * kXyzQW * kXyzCap * sizeof(unsigned long long); }
+
+template <class I>
+__global__ void __launch_bounds__(256) knn_xyz2_kernel(const float4* __restrict__ qp, const float4* __restrict__ rp,
+                                                       int Nq, int Nr, int k, I* __restrict__ idx_out,
+                                                       float* __restrict__ dist_out) {
+  extern __shared__ __align__(16) unsigned char xyz_sm[];
+  float4* cand = reinterpret_cast<float4*>(xyz_sm);
+  unsigned long long* lists = reinterpret_cast<unsigned long long*>(cand + kXyzChunk);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
+  const int qbase = (blockIdx.x * 8 + warp) * kXyzQW;
+  const bool warp_live = qbase < Nq;
+  unsigned long long* mylist = lists + (size_t)warp * kXyzQW * kXyzCap;
+  float ax[kXyzQW], ay[kXyzQW], az[kXyzQW], aw[kXyzQW];
+#pragma unroll
+  for (int i = 0; i < kXyzQW; ++i) {
+    float4 q = qp[(long long)b * Nq + min(qbase + i, Nq - 1)];
+    ax[i] = -2.f * q.x, ay[i] = -2.f * q.y, az[i] = -2.f * q.z, aw[i] = q.w;
+  }
+  // ---- pass 1: 64 group minima per query ----
+  unsigned m0[kXyzQW], m1[kXyzQW];
+#pragma unroll
+  for (int i = 0; i < kXyzQW; ++i) m0[i] = m1[i] = 0xffffffffu;
+  for (int c0 = 0; c0 < Nr; c0 += kXyzChunk) {
+    const int n = min(kXyzChunk, Nr - c0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) cand[j] = rp[(long long)b * Nr + c0 + j];
+    __syncthreads();
+    if (!warp_live) continue;
+    for (int j0 = 0; j0 < n; j0 += 64) {
+      const int ja = j0 + lane, jb = j0 + 32 + lane;
+      const float4 pa = cand[ja < n ? ja : 0], pb = cand[jb < n ? jb : 0];
+#pragma unroll
+      for (int i = 0; i < kXyzQW; ++i) {
+        const unsigned da = xyz_dist_bits(ax[i], ay[i], az[i], aw[i], pa);
+        const unsigned db = xyz_dist_bits(ax[i], ay[i], az[i], aw[i], pb);
+        m0[i] = min(m0[i], ja < n ? da : 0xffffffffu);
+        m1[i] = min(m1[i], jb < n ? db : 0xffffffffu);
+      }
+    }
+  }
+  // ---- thresholds: k-th smallest of the 64 minima (bitonic sort, element p = u*32 + lane) ----
+  unsigned T[kXyzQW];
+#pragma unroll
+  for (int i = 0; i < kXyzQW; ++i) {
+    unsigned x[2] = {m0[i], m1[i]};
+#pragma unroll
+    for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+        if (stride == 32) {
+          const unsigned lo = min(x[0], x[1]), hi = max(x[0], x[1]);
+          x[0] = lo, x[1] = hi;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const unsigned other = __shfl_xor_sync(kFull, x[u], stride);
+            const bool up = ((u * 32 + lane) & size) == 0;
+            const bool lower = (lane & stride) == 0;
+            x[u] = (lower == up) ? min(x[u], other) : max(x[u], other);
+          }
+        }
+      }
+    }
+    T[i] = __shfl_sync(kFull, x[0], k - 1);             // k <= 32: the k smallest sit in x[0]
+  }
+  // ---- pass 2: collect d <= T ----
+  int cnt[kXyzQW];
+#pragma unroll
+  for (int i = 0; i < kXyzQW; ++i) cnt[i] = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int c0 = 0; c0 < Nr; c0 += kXyzChunk) {
+    const int n = min(kXyzChunk, Nr - c0);
+    if (Nr > kXyzChunk) {                               // single-chunk clouds keep pass 1's copy
+      __syncthreads();
+      for (int j = threadIdx.x; j < n; j += blockDim.x) cand[j] = rp[(long long)b * Nr + c0 + j];
+      __syncthreads();
+    }
+    if (!warp_live) continue;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      const bool valid = j < n;
+      const float4 p = cand[valid ? j : 0];
+#pragma unroll
+      for (int i = 0; i < kXyzQW; ++i) {
+        const unsigned db = xyz_dist_bits(ax[i], ay[i], az[i], aw[i], p);
+        const bool hit = valid && db <= T[i];
+        const unsigned m = __ballot_sync(kFull, hit);
+        if (m) {
+          const int pos = cnt[i] + __popc(m & lt);
+          if (hit && pos < kXyzCap) mylist[i * kXyzCap + pos] = ((unsigned long long)db << 32) | (unsigned)(c0 + j);
+          cnt[i] += __popc(m);
+        }
+      }
+    }
+  }
+  // ---- final: rank counting; overflow -> the whole CTA redoes its queries with the k-set algorithm ----
+  bool over = false;
+#pragma unroll
+  for (int i = 0; i < kXyzQW; ++i) over |= warp_live && qbase + i < Nq && cnt[i] > kXyzCap;
+  if (__syncthreads_or(over ? 1 : 0)) {
+    LaneTopK t[kXyzQW];
+#pragma unroll
+    for (int i = 0; i < kXyzQW; ++i) t[i].init(lane, k);
+    for (int c0 = 0; c0 < Nr; c0 += kXyzChunk) {
+      const int n = min(kXyzChunk, Nr - c0);
+      __syncthreads();
+      for (int j = threadIdx.x; j < n; j += blockDim.x) cand[j] = rp[(long long)b * Nr + c0 + j];
+      __syncthreads();
+      if (!warp_live) continue;
+      for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        const bool valid = j < n;
+        const float4 p = cand[valid ? j : 0];
+#pragma unroll
+        for (int i = 0; i < kXyzQW; ++i) t[i].offer(xyz_dist_bits(ax[i], ay[i], az[i], aw[i], p), c0 + j, valid);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kXyzQW; ++i) {
+      const int q = qbase + i;
+      if (q >= Nq) break;
+      const int r = t[i].rank();
+      if (t[i].active) {
+        long long o = ((long long)b * Nq + q) * k + r;
+        idx_out[o] = (I)t[i].i;
+        if (dist_out) dist_out[o] = -sqrtf(__uint_as_float(t[i].d));
+      }
+    }
+    return;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < kXyzQW; ++i) {
+    const int q = qbase + i;
+    if (q >= Nq) break;
+    const unsigned long long* L = mylist + i * kXyzCap;
+    const int c = cnt[i];
+    for (int t = lane; t < c; t += 32) {
+      const unsigned long long mine = L[t];
+      int rank = 0;
+      for (int u = 0; u < c; ++u) rank += L[u] < mine ? 1 : 0;
+      if (rank < k) {
+        const long long o = ((long long)b * Nq + q) * k + rank;
+        idx_out[o] = (I)(unsigned)(mine & 0xffffffffu);
+        if (dist_out) dist_out[o] = -sqrtf(__uint_as_float((unsigned)(mine >> 32)));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K2 (exact fp32 form): feature-space kNN.  FFMA dot tiles + per-row k-selection epilogue.
 //   d2 = fma(-2, <a,b>, |a|^2 + |b|^2), clamp >= 0.
 // ------------------------------------------------------------------------------------------
@@ -348,6 +520,15 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
     if (!self)
       if (int e = launch_knn_prep_xyz(b, b_sb, b_sn, b_sc, B, Nr, C, mean, stdv, qb, st)) return e;
     dim3 grid(ceil_div(Nq, 8 * kXyzQW), B);
+    if (g_knn_mode != 1 && Nr >= 256) {        // two-pass form; small clouds gain nothing from the threshold
+      auto kern = knn_xyz2_kernel<I>;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_xyz2_smem()) != cudaSuccess)
+        return check_launch("knn_xyz2 smem attribute");
+      SAMBLE_PRE(st);
+      kern<<<grid, 256, knn_xyz2_smem(), st>>>(qa, qb, Nq, Nr, k, idx_out, dist_out);
+      SAMBLE_LAUNCHED("knn_xyz2_kernel");
+      return SAMBLE_OK;
+    }
     SAMBLE_PRE(st);
     knn_xyz_kernel<I><<<grid, 256, 0, st>>>(qa, qb, Nq, Nr, k, idx_out, dist_out);
     SAMBLE_LAUNCHED("knn_xyz_kernel");

@@ -328,6 +328,82 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
 // gets exact fp32 distances, and the best (k - #in) of it by (distance, index) completes the SET the exact kernel
 // returns.  In s = <a,b> - |b|^2/2 units (d~ = |a|^2 - 2s):  in: s_j > s(k+1) + e,  out: s_j < s(k) - e, evaluated
 // on the list's truncated offsets delta = s - T with their interval [delta_lo, delta_hi] (knn_pack).
+// Classification step of knn_select_kernel for a list of up to 32*NPL entries (element p = u*32 + lane):
+// bitonic-sort the packed words (descending score), read the k-th and (k+1)-th, then split the list into
+// certain-in (written to idx_row), certain-out (dropped) and ambiguous (compacted into amb[], list order kept).
+template <int NPL, class I>
+__device__ __forceinline__ void select_classify(const uint32_t* __restrict__ list, int cnt, int k, float aa, float e,
+                                                float thr_row, int lane, I* __restrict__ idx_row,
+                                                unsigned short* __restrict__ amb, int& n_in, int& n_amb) {
+  constexpr int kN = 32 * NPL;
+  uint32_t w[NPL], x[NPL];
+#pragma unroll
+  for (int u = 0; u < NPL; ++u) {
+    const int t = u * 32 + lane;
+    w[u] = t < cnt ? __ldg(list + t) : 0u;
+    x[u] = ~w[u];                                       // ascending x = descending score; padding (all ones) last
+  }
+#pragma unroll
+  for (int size = 2; size <= kN; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+      if (stride >= 32) {
+        const int du = stride >> 5;
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) {
+          if ((u & du) == 0) {
+            const bool up = ((u * 32) & size) == 0;
+            const uint32_t lo = min(x[u], x[u | du]), hi = max(x[u], x[u | du]);
+            x[u] = up ? lo : hi;
+            x[u | du] = up ? hi : lo;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) {
+          const uint32_t other = __shfl_xor_sync(kFull, x[u], stride);
+          const bool up = ((u * 32 + lane) & size) == 0;
+          const bool lower = (lane & stride) == 0;
+          x[u] = (lower == up) ? min(x[u], other) : max(x[u], other);
+        }
+      }
+    }
+  }
+  uint32_t xk = 0xffffffffu, xk1 = 0xffffffffu;         // sorted[k-1], sorted[k]  (k <= 32 <= kN)
+#pragma unroll
+  for (int u = 0; u < NPL; ++u) {
+    const uint32_t a0 = __shfl_sync(kFull, x[u], (k - 1) & 31);
+    const uint32_t a1 = __shfl_sync(kFull, x[u], k & 31);
+    if (((k - 1) >> 5) == u) xk = a0;
+    if ((k >> 5) == u) xk1 = a1;
+  }
+  const float dk = knn_delta_lo(~xk);                                   // k-th largest offset (lower end)
+  const float dk1 = cnt > k ? knn_delta_lo(~xk1) : -INFINITY;           // (k+1)-th; none if the list holds exactly k
+  // offsets at or above n0 may belong to d~ <= e, where the exact kernel's clamp makes the index decide
+  const float n0 = (0.5f * (aa - e) - thr_row) * 0.999f;
+  const bool in_ok = knn_delta_hi(dk1) < n0 || cnt == k;
+  const float in_thr = knn_delta_hi(dk1) + e;           // in:  delta_lo_j > this
+  const float out_thr = dk - e;                         // out: delta_hi_j < this
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int u = 0; u < NPL; ++u) {
+    const bool have = u * 32 + lane < cnt;
+    const float dlo = knn_delta_lo(w[u]), dhi = knn_delta_hi(dlo);
+    const int j = (int)(w[u] & 0xffffu);
+    const bool is_in = have && in_ok && dlo > in_thr;
+    const bool is_out = have && dhi < out_thr && dhi < n0;
+    const bool is_amb = have && !is_in && !is_out;
+    const unsigned m_in = __ballot_sync(kFull, is_in), m_amb = __ballot_sync(kFull, is_amb);
+    if (is_in) idx_row[n_in + __popc(m_in & lt)] = (I)j;
+    if (is_amb) amb[n_amb + __popc(m_amb & lt)] = (unsigned short)j;
+    n_in += __popc(m_in);
+    n_amb += __popc(m_amb);
+  }
+}
+
+constexpr int kSelBatch = 8;          // candidate rows fetched per round
+constexpr int kSelRowLd = 132;        // floats per parked row (pad 4: the 8 evaluating lanes hit distinct banks)
+
 template <class I>
 __global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict__ an, const float* __restrict__ anorm,
                                                          const float* __restrict__ bn, const float* __restrict__ bnorm,
@@ -337,6 +413,9 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict
                                                          int Nq, int Nr, int Cp, int k, I* __restrict__ idx_out,
                                                          int* __restrict__ row_flags) {
   __shared__ unsigned short amb[8][128];
+  __shared__ __align__(16) float s_arow[8][128];                       // query row
+  __shared__ __align__(16) float s_rows[8][kSelBatch * kSelRowLd];     // candidate rows of the current round
+  __shared__ unsigned long long s_keys[8][128];                        // (distance bits, index) of the ambiguous ones
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, q = blockIdx.x * 8 + warp;
   if (q >= Nq) return;
@@ -348,71 +427,16 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict
   }
   const float aa = anorm[rowi];
   const float e = knn_margin(aa, __uint_as_float(bbmax_bits[b])) * 1.001f;
-  uint32_t w[4], x[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int t = u * 32 + lane;
-    w[u] = t < cnt ? __ldg(cand + rowi * kTcListLd + t) : 0u;
-    x[u] = ~w[u];                                       // ascending x = descending score; padding (all ones) last
-  }
-  // bitonic sort of the 128 keys, element p = u*32 + lane
-#pragma unroll
-  for (int size = 2; size <= 128; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride >= 1; stride >>= 1) {
-      if (stride >= 32) {
-        const int du = stride >> 5;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if ((u & du) == 0) {
-            const bool up = ((u * 32) & size) == 0;
-            const uint32_t lo = min(x[u], x[u | du]), hi = max(x[u], x[u | du]);
-            x[u] = up ? lo : hi;
-            x[u | du] = up ? hi : lo;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t other = __shfl_xor_sync(kFull, x[u], stride);
-          const bool up = ((u * 32 + lane) & size) == 0;
-          const bool lower = (lane & stride) == 0;
-          x[u] = (lower == up) ? min(x[u], other) : max(x[u], other);
-        }
-      }
-    }
-  }
-  uint32_t xk = 0, xk1 = 0;                             // sorted[k-1], sorted[k]
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const uint32_t a0 = __shfl_sync(kFull, x[u], (k - 1) & 31);
-    const uint32_t a1 = __shfl_sync(kFull, x[u], k & 31);
-    if (((k - 1) >> 5) == u) xk = a0;
-    if ((k >> 5) == u) xk1 = a1;
-  }
-  const float dk = knn_delta_lo(~xk);                                   // k-th largest offset (lower end)
-  const float dk1 = cnt > k ? knn_delta_lo(~xk1) : -INFINITY;           // (k+1)-th; none if the list holds exactly k
-  // offsets at or above n0 may belong to d~ <= e, where the exact kernel's clamp makes the index decide
-  const float n0 = (0.5f * (aa - e) - __ldg(thr_in + rowi)) * 0.999f;
-  const bool in_ok = knn_delta_hi(dk1) < n0 || cnt == k;
-  const float in_thr = knn_delta_hi(dk1) + e;           // in:  delta_lo_j > this
-  const float out_thr = dk - e;                         // out: delta_hi_j < this
   int n_in = 0, n_amb = 0;
-  const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const bool have = u * 32 + lane < cnt;
-    const float dlo = knn_delta_lo(w[u]), dhi = knn_delta_hi(dlo);
-    const int j = (int)(w[u] & 0xffffu);
-    const bool is_in = have && in_ok && dlo > in_thr;
-    const bool is_out = have && dhi < out_thr && dhi < n0;
-    const bool is_amb = have && !is_in && !is_out;
-    const unsigned m_in = __ballot_sync(kFull, is_in), m_amb = __ballot_sync(kFull, is_amb);
-    if (is_in) idx_out[rowi * k + n_in + __popc(m_in & lt)] = (I)j;
-    if (is_amb) amb[warp][n_amb + __popc(m_amb & lt)] = (unsigned short)j;
-    n_in += __popc(m_in);
-    n_amb += __popc(m_amb);
-  }
+  const uint32_t* list = cand + rowi * kTcListLd;
+  const float thr_row = __ldg(thr_in + rowi);
+  // the list is sorted only to read off its k-th and (k+1)-th scores: 1, 2 or 4 entries per lane as its length needs
+  if (cnt <= 32)
+    select_classify<1, I>(list, cnt, k, aa, e, thr_row, lane, idx_out + rowi * k, amb[warp], n_in, n_amb);
+  else if (cnt <= 64)
+    select_classify<2, I>(list, cnt, k, aa, e, thr_row, lane, idx_out + rowi * k, amb[warp], n_in, n_amb);
+  else
+    select_classify<4, I>(list, cnt, k, aa, e, thr_row, lane, idx_out + rowi * k, amb[warp], n_in, n_amb);
   const int need = k - n_in;
   if (need <= 0) return;                                // (n_in <= k always: an "in" entry has at most k-1 rivals)
   if (n_amb < need) {                                   // cannot happen while the margin holds; stay safe
@@ -420,38 +444,51 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict
     return;
   }
   __syncwarp();
+  // Exact fp32 distances of the ambiguous candidates.  Rows are fetched by the whole warp (lane = 16-byte chunk, up to
+  // 8 rows in flight per round: coalesced 512-byte reads instead of one serial gather per lane) and parked in shared
+  // memory; lane u then runs candidate u's dot product there -- ascending channels, one accumulator, i.e. exactly the
+  // arithmetic of the exact kernel in knn.cu.
+  const int nch = Cp >> 2;
   const float4* ar = reinterpret_cast<const float4*>(an + rowi * Cp);
   const float* B_g = bn + (size_t)b * Nr * Cp;
   const float* bnorm_g = bnorm + (size_t)b * Nr;
-  LaneTopK top;
-  top.init(lane, need);
-  for (int r = 0; r < n_amb; r += 32) {
-    const int t = r + lane;
-    const bool have = t < n_amb;
-    const int j = have ? (int)amb[warp][t] : 0;
-    const float4* br = reinterpret_cast<const float4*>(B_g + (size_t)j * Cp);
-    float acc = 0.f;
-    if (have) {
+  if (lane < nch) reinterpret_cast<float4*>(s_arow[warp])[lane] = __ldg(ar + lane);
+  for (int r = 0; r < n_amb; r += kSelBatch) {
+    const int nb = min(kSelBatch, n_amb - r);
+    float4 tmp[kSelBatch];
+#pragma unroll
+    for (int u = 0; u < kSelBatch; ++u)
+      if (u < nb && lane < nch) tmp[u] = __ldg(reinterpret_cast<const float4*>(B_g + (size_t)amb[warp][r + u] * Cp) + lane);
+#pragma unroll
+    for (int u = 0; u < kSelBatch; ++u)
+      if (u < nb && lane < nch) reinterpret_cast<float4*>(s_rows[warp] + u * kSelRowLd)[lane] = tmp[u];
+    __syncwarp();
+    if (lane < nb) {
+      const int j = (int)amb[warp][r + lane];
+      const float4* br = reinterpret_cast<const float4*>(s_rows[warp] + lane * kSelRowLd);
+      const float4* aq = reinterpret_cast<const float4*>(s_arow[warp]);
+      float acc = 0.f;
 #pragma unroll 4
-      for (int c4 = 0; c4 < Cp / 4; ++c4) {            // ascending channels, one accumulator: knn.cu's order
-        const float4 a4 = __ldg(ar + c4);
-        const float4 b4 = __ldg(br + c4);
+      for (int c4 = 0; c4 < nch; ++c4) {
+        const float4 a4 = aq[c4];
+        const float4 b4 = br[c4];
         acc = fmaf(a4.x, b4.x, acc);
         acc = fmaf(a4.y, b4.y, acc);
         acc = fmaf(a4.z, b4.z, acc);
         acc = fmaf(a4.w, b4.w, acc);
       }
+      const float d2 = __fmaf_rn(-2.f, acc, __fadd_rn(aa, __ldg(bnorm_g + j)));
+      s_keys[warp][r + lane] = ((unsigned long long)dist_bits(d2) << 32) | (unsigned)j;
     }
-    const float d2 = __fmaf_rn(-2.f, acc, __fadd_rn(aa, __ldg(bnorm_g + j)));
-    const unsigned db = dist_bits(d2);
-    if (r == 0) {                                       // n_amb >= need: the first `need` entries seed the set
-      top.fill(db, j, have && lane < need);
-      top.offer(db, j, have && lane >= need);
-    } else {
-      top.offer(db, j, have);
-    }
+    __syncwarp();
   }
-  if (top.active) idx_out[rowi * k + n_in + lane] = (I)top.i;
+  // the `need` smallest (distance, index) keys, by rank counting (keys are distinct: the indices are)
+  for (int t = lane; t < n_amb; t += 32) {
+    const unsigned long long mine = s_keys[warp][t];
+    int rank = 0;
+    for (int u = 0; u < n_amb; ++u) rank += s_keys[warp][u] < mine ? 1 : 0;
+    if (rank < need) idx_out[rowi * k + n_in + rank] = (I)(unsigned)(mine & 0xffffffffu);
+  }
 }
 
 // ---- host side ----

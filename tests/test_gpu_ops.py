@@ -285,3 +285,27 @@ def test_tensor_core_knn_hard_cases():
     (d0, i0), (d1, i1) = _knn_both(dup, dup, 32)
     assert torch.equal(i0, i1) and torch.equal(d0, d1)
     assert _same_sets_any_order(dup, dup, 32, i1)
+
+
+@pytest.mark.parametrize("shape", [(2, 2048, 0, 3, 32), (3, 1000, 0, 3, 20), (1, 300, 700, 2, 5), (2, 5000, 0, 3, 32), (1, 256, 0, 3, 32)],
+                         ids=lambda s: f"B{s[0]}_N{s[1]}x{s[2] or s[1]}_C{s[3]}_k{s[4]}")
+def test_two_pass_xyz_knn_is_bit_identical_to_kset_kernel(shape):
+    """knn_xyz2_kernel (group-minima threshold -> short list -> rank counting) vs knn_xyz_kernel (running k-set)."""
+    B, Nq, Nr, C, k = shape
+    a = cu(synthetic_features(B, Nq, C, 300 + Nq))
+    b = a if Nr == 0 else cu(synthetic_features(B, Nr, C, 400 + Nr))
+    (d0, i0), (d1, i1) = _knn_both(a, b, k)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+
+
+def test_two_pass_xyz_knn_duplicates_overflow_fallback():
+    # 300 copies of each of 8 points: every list overflows (all duplicates tie at distance 0) -> k-set fallback
+    base = synthetic_features(1, 8, 3, 5)
+    a = cu(base.repeat(1, 300, 1).contiguous())
+    (d0, i0), (d1, i1) = _knn_both(a, a, 32)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    # a regular grid: many exact ties at the k-th distance
+    g = torch.stack(torch.meshgrid(torch.arange(16.), torch.arange(16.), torch.arange(8.), indexing="ij"), -1).reshape(1, -1, 3)
+    g = cu(g.contiguous())
+    (d0, i0), (d1, i1) = _knn_both(g, g, 32)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
