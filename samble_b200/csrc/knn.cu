@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restr
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ stdv, float* __restrict__ out,
                                                             float* __restrict__ norms, unsigned* __restrict__ maxnorm,
-                                                            float* __restrict__ ext) {
+                                                            float* __restrict__ ext, float* __restrict__ out_tf32) {
   __shared__ float tile[32][33];
   const int b = blockIdx.y, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (n0 >= N) {                                        // padding rows of the last 128-candidate tile (ext only)
@@ -109,7 +109,15 @@ __global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restr
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       int n = n0 + ty + 8 * r, c = c0 + tx;
-      if (n < N && c < Cp) out[((long long)b * N + n) * Cp + c] = tile[tx][ty + 8 * r];
+      if (n < N && c < Cp) {
+        const float v = tile[tx][ty + 8 * r];
+        out[((long long)b * N + n) * Cp + c] = v;
+        if (out_tf32) {            // tensor-core operand copy, rounded to nearest tf32 (the MMA itself would truncate)
+          unsigned rbits;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rbits) : "f"(v));
+          out_tf32[((long long)b * N + n) * Cp + c] = __uint_as_float(rbits);
+        }
+      }
     }
     if (ty == 0) {
       int cmax = min(32, Cp - c0);
@@ -480,9 +488,9 @@ bool knn_tc_eligible(int Nq, int Nr, int C, int k);
 size_t knn_tc_workspace_bytes(int B, int Nq, int Nr);
 size_t knn_tc_ext_floats(int B, int Nr);
 template <class I>
-int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const float* bext,
-                  const unsigned* bbmax, int B, int Nq, int Nr, int Cp, int k, float* thr, uint32_t* cand, int* cnt,
-                  bool ordered, I* idx, float* dist, int* row_flags, cudaStream_t st);
+int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const float* an_tf32,
+                  const float* bn_tf32, const float* bext, const unsigned* bbmax, int B, int Nq, int Nr, int Cp, int k,
+                  float* thr, uint32_t* cand, int* cnt, bool ordered, I* idx, float* dist, int* row_flags, cudaStream_t st);
 
 static int g_knn_mode = 0;   // 0 auto, 1 exact FFMA kernel only, 2 tensor-core path wherever eligible
 
@@ -498,7 +506,9 @@ static KnnPlan knn_plan(int B, int Nq, int Nr, int C) {
   size_t per_pt = p.xyz ? sizeof(float4) : (size_t)(p.Cp + 1) * sizeof(float);
   p.bytes = 2 * align_up((size_t)B * C * sizeof(float), 256) + align_up((size_t)B * Nq * per_pt, 256) +
             align_up((size_t)B * Nr * per_pt, 256) + 2 * align_up((size_t)B * Nq * sizeof(float), 256) +
-            align_up((size_t)B * sizeof(unsigned), 256) + (p.xyz ? 0 : knn_tc_workspace_bytes(B, Nq, Nr)) + 12 * 256;
+            align_up((size_t)B * sizeof(unsigned), 256) + (p.xyz ? 0 : knn_tc_workspace_bytes(B, Nq, Nr)) +
+            (p.xyz ? 0 : align_up((size_t)B * Nq * per_pt, 256) + align_up((size_t)B * Nr * per_pt, 256)) /* tf32 copies */ +
+            14 * 256;
   return p;
 }
 
@@ -546,6 +556,8 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   uint32_t* cand = w.take<uint32_t>((size_t)B * Nq * 128);
   int* cand_cnt = w.take<int>((size_t)B * Nq);
   float* bext = w.take<float>(knn_tc_ext_floats(B, Nr));
+  float* an_r = w.take<float>((size_t)B * Nq * Cp);          // tf32-rounded operand copies for the tensor-core passes
+  float* bn_r = self ? an_r : w.take<float>((size_t)B * Nr * Cp);
   const bool use_tc = g_knn_mode != 1 && knn_tc_eligible(Nq, Nr, C, k);
   if (use_tc) {   // row_flags and bbmax are adjacent (256-byte granules): one memset node
     const size_t span = (size_t)((char*)(bbmax + B) - (char*)row_flags);
@@ -556,16 +568,18 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   // the candidate-side launch also covers the padding rows of the last 128-candidate tile (norm slice only)
   const bool a_is_cand = use_tc && self;
   knn_prep_feat_kernel<<<dim3(ceil_div(a_is_cand ? (int)align_up(Nq, 128) : Nq, 32), B), 256, 0, st>>>(
-      a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv, an, anorm, a_is_cand ? bbmax : nullptr, a_is_cand ? bext : nullptr);
+      a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv, an, anorm, a_is_cand ? bbmax : nullptr, a_is_cand ? bext : nullptr,
+      use_tc ? an_r : nullptr);
   SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   if (!self) {
     SAMBLE_PRE(st);
     knn_prep_feat_kernel<<<dim3(ceil_div(use_tc ? (int)align_up(Nr, 128) : Nr, 32), B), 256, 0, st>>>(
-        b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn, bnorm, use_tc ? bbmax : nullptr, use_tc ? bext : nullptr);
+        b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn, bnorm, use_tc ? bbmax : nullptr, use_tc ? bext : nullptr,
+        use_tc ? bn_r : nullptr);
     SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   }
   if (use_tc) {
-    if (int e = launch_knn_tc<I>(an, anorm, bn, bnorm, bext, bbmax, B, Nq, Nr, Cp, k, thr, cand, cand_cnt, ordered, idx_out,
+    if (int e = launch_knn_tc<I>(an, anorm, bn, bnorm, an_r, bn_r, bext, bbmax, B, Nq, Nr, Cp, k, thr, cand, cand_cnt, ordered, idx_out,
                                  dist_out, row_flags, st))
       return e;
     // rows whose candidate buffer overflowed are redone by the exact kernel (normally none: every tile exits at once)

@@ -40,11 +40,12 @@ static size_t tc_smem_bytes(int nkb, bool pass_b) {
          + (pass_b ? (size_t)kTcRows * kTcListSm * 4 : 0) + 1024 + 256;
 }
 
-// |d~ - d_fp32| <= e:  2 * |<a,b>_tf32 - <a,b>| <= 2 * (2^-10 + 2^-10 + 2^-20) |a||b|  (operand truncation)
+// |d~ - d_fp32| <= e:  the operands are ROUNDED to tf32 by the prep kernel (cvt.rna, |x - x_r| <= 2^-11 |x|; the MMA's own
+// truncation is then exact), so  2 * |<a_r,b_r> - <a,b>| <= 2 * (2^-11 + 2^-11 + 2^-22) |a||b| = (2^-9 + 2^-21) |a||b|,
 // + tensor-core fp32 accumulation slop + the tf32 split of |b|^2/2 + the fp32 rounding of the exact formula.
 __device__ __forceinline__ float knn_margin(float aa, float bbmax) {
   const float s = sqrtf(aa * bbmax);
-  return (0.00390625f + 0.00012207031f) * s + 3.0517578e-05f * (aa + bbmax);
+  return (0.001953125f + 0.00012207031f) * s + 3.0517578e-05f * (aa + bbmax);
 }
 
 // A list entry is one 32-bit word: candidate index in the low half, and in the high half the upper 16 bits (sign,
@@ -507,13 +508,13 @@ size_t knn_tc_workspace_bytes(int B, int Nq, int Nr) {
 size_t knn_tc_ext_floats(int B, int Nr) { return (size_t)B * ceil_div(Nr, kTcTile) * (kExt / 4); }
 
 template <class I>
-int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const float* bext,
-                  const unsigned* bbmax, int B, int Nq, int Nr, int Cp, int k, float* thr, uint32_t* cand, int* cnt,
-                  bool ordered, I* idx, float* dist, int* row_flags, cudaStream_t st) {
+int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const float* an_tf32,
+                  const float* bn_tf32, const float* bext, const unsigned* bbmax, int B, int Nq, int Nr, int Cp, int k,
+                  float* thr, uint32_t* cand, int* cnt, bool ordered, I* idx, float* dist, int* row_flags, cudaStream_t st) {
   const int nkb = Cp / 32;
   alignas(64) CUtensorMap map_a, map_b;
-  if (int e = make_tile_map(&map_a, an, Cp, Cp, Nq, B, kTcRows)) return e;
-  if (int e = make_tile_map(&map_b, bn, Cp, Cp, Nr, B, kTcTile)) return e;
+  if (int e = make_tile_map(&map_a, an_tf32, Cp, Cp, Nq, B, kTcRows)) return e;
+  if (int e = make_tile_map(&map_b, bn_tf32, Cp, Cp, Nr, B, kTcTile)) return e;
   dim3 grid(ceil_div(Nq, kTcRows), B);
   {
     size_t smem = tc_smem_bytes(nkb, false);
@@ -544,10 +545,11 @@ int launch_knn_tc(const float* an, const float* anorm, const float* bn, const fl
   return SAMBLE_OK;
 }
 
-template int launch_knn_tc<int>(const float*, const float*, const float*, const float*, const float*, const unsigned*, int, int,
-                                int, int, int, float*, uint32_t*, int*, bool, int*, float*, int*, cudaStream_t);
-template int launch_knn_tc<long long>(const float*, const float*, const float*, const float*, const float*, const unsigned*,
-                                      int, int, int, int, int, float*, uint32_t*, int*, bool, long long*, float*, int*,
-                                      cudaStream_t);
+template int launch_knn_tc<int>(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
+                                const unsigned*, int, int, int, int, int, float*, uint32_t*, int*, bool, int*, float*, int*,
+                                cudaStream_t);
+template int launch_knn_tc<long long>(const float*, const float*, const float*, const float*, const float*, const float*,
+                                      const float*, const unsigned*, int, int, int, int, int, float*, uint32_t*, int*, bool,
+                                      long long*, float*, int*, cudaStream_t);
 
 }  // namespace samble
