@@ -154,6 +154,74 @@ def knn_census(B, N):
     return [(N, N, 64, 1), (N, N, 128, 3), (N // 2, N // 2, 128, 3), (N // 4, N // 4, 128, 1)]
 
 
+def linear_census(model, x, cat):
+    """Algorithmic bytes / FLOPs of the point-wise linear layers of one forward: every call of ops.linear /
+    ops.linear_pool is intercepted once and its operands counted (activations in + weights + activations out
+    (+ residual); 2*M*K*Nout FLOPs)."""
+    from samble_b200 import ops
+
+    tot = {"bytes": 0.0, "flops": 0.0, "calls": 0}
+    real_linear, real_pool = ops.linear, ops.linear_pool
+
+    def lin(xx, w, **kw):
+        y = real_linear(xx, w, **kw)
+        nout, k = w.shape[0], w[0].numel()
+        m = xx.numel() // k
+        res = kw.get("residual")
+        tot["bytes"] += 4.0 * (xx.numel() + w.numel() + y.numel() + (res.numel() if res is not None else 0))
+        tot["flops"] += 2.0 * m * k * nout
+        tot["calls"] += 1
+        return y
+
+    def pool(xx, w, **kw):
+        r = real_pool(xx, w, **kw)
+        nout, k = w.shape[0], w[0].numel()
+        m = xx.numel() // k
+        tot["bytes"] += 4.0 * (xx.numel() + w.numel() + 2 * (m // 32) * nout)     # partial max/sum rows instead of y
+        tot["flops"] += 2.0 * m * k * nout
+        tot["calls"] += 1
+        return r
+
+    ops.linear, ops.linear_pool = lin, pool
+    try:
+        model(x, cat)
+        torch.cuda.synchronize()
+    finally:
+        ops.linear, ops.linear_pool = real_linear, real_pool
+    return tot
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per step of `kernel`, from the committed ncu --set full capture
+    (profiles/r1_traffic.json, written by tools/summarize_ncu.py traffic); None if that kernel was not captured."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get("dram_bytes_per_step", {}).get(kernel)
+
+
+def roofline_of(dom, ms, census, B, N, pk):
+    """Roofline block for the dominant kernel family of the step (DESIGN.md section 5 states the per-unit figures)."""
+    sec = ms * 1e-3
+    if dom.startswith("linear"):
+        # fp32 point-wise layers, K <= 1024: 2*K*Nout/(4*(K+Nout)) ~ 50-100 FLOP/B, i.e. memory-side at fp32-class
+        # tensor throughput (3 tf32 MMAs per product); reported against HBM, with the tensor-pipe share beside it
+        ach = census["bytes"] / sec / 1e9
+        t = ncu_traffic(dom)
+        return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "traffic": t, "algorithmic_bytes_per_step": census["bytes"], "calls_per_step": census["calls"],
+                "tensor_tflops_3xtf32": 3 * census["flops"] / sec / 1e12,
+                "note": "all linear_tma launches of the step; achieved = (X + W + Y [+ residual]) bytes / their summed duration"}
+    if dom.startswith("knn_tc") or dom.startswith("knn_select") or dom.startswith("knn_rerank"):
+        flops = sum(2.0 * nq * nr * (c + 8) * cnt for nq, nr, c, cnt in knn_census(B, N)) * B
+        ach = flops / sec / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"] / 2, "unit": "TFLOP/s",
+                "frac": ach / (pk["bf16_tflops_sustained"] / 2), "traffic": ncu_traffic(dom),
+                "note": "tf32 distance GEMM of one pass; peak = half the measured bf16 rate (kind::tf32 issues at half the bf16 rate)"}
+    return {"bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": ncu_traffic(dom)}
+
+
 def run_native(args):
     import torch.distributed as dist
 
@@ -254,6 +322,7 @@ def run_native(args):
         prof = L.profile_report()
         L.profile(False)
         prof_total_ms = t0.elapsed_time(t1) / 3
+        census = linear_census(model, x, cat)
 
     value = B * world * args.steps / (ms / 1e3)
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
@@ -266,18 +335,8 @@ def run_native(args):
     native_ms = {k: v[1] / 3 for k, v in prof.items()}
     dom = max(native_ms, key=native_ms.get)
     roof = {"kernel": dom, "ms_per_step": native_ms[dom], "share_of_step": native_ms[dom] / prof_total_ms,
-            "peak_source": pk_src}
-    if dom in ("knn_feat_kernel", "ds_row_stats_kernel"):
-        if dom == "knn_feat_kernel":
-            flops = sum(2.0 * nq * nr * c * cnt for nq, nr, c, cnt in knn_census(B, N)) * B
-        else:
-            flops = sum(2.0 * n * n * 128 for n in (N, N // 2)) * B
-        ach = flops / (native_ms[dom] * 1e-3) / 1e12
-        roof.update({"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
-                     "note": "fp32 FFMA tile engine (v1) measured against the bf16 tensor peak the tcgen05 version must approach"})
-    else:
-        roof.update({"bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None})
+            "launches_per_step": prof[dom][0] // 3, "peak_source": pk_src}
+    roof.update(roofline_of(dom, native_ms[dom], census, B, N, pk))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": sampler.result(),

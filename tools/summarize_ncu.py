@@ -62,5 +62,27 @@ def raw(path):
         print()
 
 
+def traffic(path):
+    """JSON for bench.py's roofline.traffic: DRAM bytes (read + write) per kernel family, summed over the launches of
+    ONE step captured with `ncu --set full` (units row of the raw page gives the scale of each column)."""
+    import json
+    import re
+
+    rows = list(csv.reader(open(path)))
+    h, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    cols = [(i, scale[units[i]]) for i, k in enumerate(h) if k in ("dram__bytes_read.sum", "dram__bytes_write.sum")]
+    ki = h.index("Kernel Name")
+    out = collections.defaultdict(float)
+    n = collections.defaultdict(int)
+    for r in rows[2:]:
+        m = re.search(r"(\w+_kernel)", r[ki])
+        name = m.group(1) if m else r[ki].split("(")[0]
+        out[name] += sum(float(r[i].replace(",", "")) * sc for i, sc in cols)
+        n[name] += 1
+    print(json.dumps({"source": path, "dram_bytes_per_step": {k: round(v) for k, v in out.items()},
+                      "launches_per_step": dict(n)}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "raw": raw, "traffic": traffic}[sys.argv[1]](sys.argv[2])
