@@ -135,6 +135,17 @@ int samble_linear(const float* X, long long ldx, int x_channel_major, const floa
  * the (M x Nout) activation: the epilogue reduces each 32-row group in registers, a second tiny kernel combines the
  * groups of a cloud in a fixed order (deterministic).  X row-major; points_per_cloud a multiple of 32.
  * out_max / out_mean: (M / points_per_cloud, Nout), either may be NULL. */
+/* Per-cloud products on the same kernel: rows m of cloud b = m / rows_per_cloud are multiplied by THAT cloud's matrix
+ * W[b] (Nout x K, row pitch ldw, cloud pitch Nout*ldw; W_lo its samble_split_tf32 companion):  out[m] = X[m] W[b]^T.
+ * With row_max/row_sum the epilogue turns the products into softmax rows whose statistics are already known,
+ *   out = exp(acc / logit_div - row_max[m]) / row_sum[m],
+ * which is how DownSampleToken's attention rows of the M selected points (models/downsample.py:242-252) are formed
+ * from the row statistics of samble_ds_row_stats; a second call (X = those rows, W[b] = V[b]^T) applies them to V.
+ * rows_per_cloud must be a multiple of 128. */
+int samble_cloud_matmul(const float* X, long long ldx, const float* W, const float* W_lo, long long ldw, int M, int K, int Nout,
+                        int rows_per_cloud, const float* row_max, const float* row_sum, float logit_div,
+                        float* out, long long ldo, samble_stream_t stream);
+
 size_t samble_linear_pool_workspace_bytes(int M, int Nout);
 int samble_linear_pool(const float* X, long long ldx, const float* W, const float* W_lo, long long ldw,
                        const float* scale, const float* shift, long long shift_cloud_stride, int lrelu,

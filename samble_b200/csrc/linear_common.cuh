@@ -30,6 +30,13 @@ struct LinArgs {
   // [M/32][Nout] (a group never straddles two clouds: npc % 32 == 0); samble_linear_pool reduces them per cloud
   float* pool_max;
   float* pool_sum;
+  // per-cloud weights (linear_tma.cu only): cloud b = m / npc multiplies by W[b] (Nout x K slices, pitch Nout*ldw)
+  int w_batched;
+  // row-softmax epilogue: y = exp(acc / logit_div - row_max[m]) / row_sum[m]   (row statistics known beforehand)
+  const float* row_max;
+  const float* row_sum;
+  float logit_div;
+  int chain;                          // K-blocks per accumulation chain (linear_tma.cu; 0 = kLinChain)
 };
 
 
@@ -96,6 +103,13 @@ __device__ __forceinline__ void linear_epilogue_tile(const LinArgs& a, uint32_t 
       }
       sc[i] = s4.x, sc[i + 1] = s4.y, sc[i + 2] = s4.z, sc[i + 3] = s4.w;
       sh[i] = h4.x, sh[i + 1] = h4.y, sh[i + 2] = h4.z, sh[i + 3] = h4.w;
+    }
+    if (a.row_max) {
+      // 4 instructions per element (FFMA, FMUL, MUFU.EX2, FMUL): the row statistics themselves were accumulated with
+      // the same ex2-based exponential (ds_rowstats_tc.cu), relative error ~2^-21
+      const float mu = __ldg(a.row_max + (live ? m : 0)), inv_s = 1.f / __ldg(a.row_sum + (live ? m : 0)), inv_div = 1.f / a.logit_div;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __expf(fmaf(v[i], inv_div, -mu)) * inv_s;
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -186,6 +200,11 @@ __device__ __forceinline__ void linear_epilogue_tile_staged(const LinArgs& a, ui
 #pragma unroll
           for (int j = 0; j < 4; ++j) res[j] = (c + j < a.Nout) ? __ldg(rp + j) : 0.f;
         }
+      }
+      if (a.row_max) {                                           // softmax row with known max / sum (downsample.py:242-250)
+        const float mu = __ldg(a.row_max + m), inv_s = 1.f / __ldg(a.row_sum + m), inv_div = 1.f / a.logit_div;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = __expf(fmaf(y[j], inv_div, -mu)) * inv_s;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

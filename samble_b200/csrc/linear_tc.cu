@@ -271,7 +271,7 @@ extern "C" int samble_linear(const float* X, long long ldx, int x_channel_major,
   SAMBLE_REQUIRE(ceil_div(Nout, 64) <= 65535, "samble_linear: Nout too large");
   LinArgs a{X, ldx, W, ldw, W_lo, scale, shift, residual, ldr, out, ldo, M, K, Nout, need_npc ? points_per_cloud : 0,
             lrelu, x_channel_major, out_channel_major, residual_first, residual_channel_major, shift_cloud_stride,
-            nullptr, nullptr};
+            nullptr, nullptr, 0, nullptr, nullptr, 1.f, 0};
   cudaStream_t st = (cudaStream_t)stream;
   const int nacc = ceil_div(ceil_div(K, 32), kLinChain);
   SAMBLE_REQUIRE(nacc * 64 <= 512, "samble_linear: K=%d too large (max %d)", K, 8 * kLinChain * 32);
@@ -319,7 +319,7 @@ extern "C" int samble_linear_pool(const float* X, long long ldx, const float* W,
   float* pmax = w.take<float>((size_t)ceil_div(M, 32) * Nout);
   float* psum = w.take<float>((size_t)ceil_div(M, 32) * Nout);
   LinArgs a{X, ldx, W, ldw, W_lo, scale, shift, nullptr, 0, nullptr, 0, M, K, Nout, points_per_cloud,
-            lrelu, 0, 0, 0, 0, shift_cloud_stride, pmax, out_mean ? psum : nullptr};
+            lrelu, 0, 0, 0, 0, shift_cloud_stride, pmax, out_mean ? psum : nullptr, 0, nullptr, nullptr, 1.f, 0};
   cudaStream_t st = (cudaStream_t)stream;
   if (int e = launch_linear_tma_auto(a, nacc, st)) return e;
   SAMBLE_PRE(st);
@@ -327,4 +327,29 @@ extern "C" int samble_linear_pool(const float* X, long long ldx, const float* W,
       pmax, out_mean ? psum : nullptr, points_per_cloud / 32, Nout, points_per_cloud, out_max, out_mean);
   SAMBLE_LAUNCHED("linear_pool_finalize_kernel");
   return SAMBLE_OK;
+}
+
+// ---- per-cloud products: out[b] = X[b] W[b]^T, optionally turned into softmax rows with known statistics ----
+extern "C" int samble_cloud_matmul(const float* X, long long ldx, const float* W, const float* W_lo, long long ldw, int M, int K,
+                                   int Nout, int rows_per_cloud, const float* row_max, const float* row_sum, float logit_div,
+                                   float* out, long long ldo, samble_stream_t stream) {
+  SAMBLE_REQUIRE(X && W && W_lo && out, "samble_cloud_matmul: null pointer");
+  SAMBLE_REQUIRE((row_max == nullptr) == (row_sum == nullptr), "samble_cloud_matmul: row_max and row_sum come together");
+  SAMBLE_REQUIRE(ldw % 4 == 0 && ldw >= ((K + 3) / 4) * 4 && ((uintptr_t)W | (uintptr_t)W_lo) % 16 == 0,
+                 "samble_cloud_matmul: weight rows must be 16-byte aligned and zero-padded to a multiple of 4 columns");
+  SAMBLE_REQUIRE(ldx % 4 == 0 && ldx >= ((K + 3) / 4) * 4 && (uintptr_t)X % 16 == 0,
+                 "samble_cloud_matmul: X needs 16-byte aligned rows, zero-padded to a multiple of 4 columns");
+  SAMBLE_REQUIRE(M > 0 && K > 0 && Nout > 0, "samble_cloud_matmul: bad shape M=%d K=%d Nout=%d", M, K, Nout);
+  SAMBLE_REQUIRE(rows_per_cloud > 0 && rows_per_cloud % 128 == 0 && M % rows_per_cloud == 0,
+                 "samble_cloud_matmul: %d rows per cloud (must be a multiple of 128 dividing M=%d)", rows_per_cloud, M);
+  SAMBLE_REQUIRE(ldo >= Nout, "samble_cloud_matmul: ldo < Nout");
+  // long contractions (attention rows x V: K = number of keys, outputs are convex combinations of O(1) values) run
+  // 16-block chains so that four accumulators of a 128-wide tile still fit TMEM; the truncation bias of the longer
+  // chain (~2e-5 abs) is far inside the activation tolerance
+  const int chain = K > 1024 ? 16 : kLinChain;
+  const int nacc = ceil_div(ceil_div(K, 32), chain);
+  SAMBLE_REQUIRE(nacc * 64 <= 512, "samble_cloud_matmul: K=%d too large (max %d)", K, 8 * 16 * 32);
+  LinArgs a{X, ldx, W, ldw, W_lo, nullptr, nullptr, nullptr, 0, out, ldo, M, K, Nout, rows_per_cloud,
+            0, 0, 0, 0, 0, 0, nullptr, nullptr, 1, row_max, row_sum, logit_div, chain};
+  return launch_linear_tma_auto(a, nacc, (cudaStream_t)stream);
 }

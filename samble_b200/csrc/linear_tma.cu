@@ -88,9 +88,11 @@ __global__ void __launch_bounds__(kLtThreads, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mtiles = (a.M + 127) / 128, ntiles = (a.Nout + NT - 1) / NT;
   const int total = mtiles * ntiles;
+  const int nclouds = a.w_batched ? a.M / a.npc : 1;
   int t0, t1;
   lt_range(total, t0, t1);
-  const int nacc = (nkb + kLinChain - 1) / kLinChain;
+  const int chain = a.chain > 0 ? a.chain : kLinChain;
+  const int nacc = (nkb + chain - 1) / chain;
   const int nsets = (2 * nacc * NT <= 512) ? 2 : 1;
   uint32_t tcols = 32;
   while (tcols < (uint32_t)(nsets * nacc * NT)) tcols <<= 1;
@@ -124,14 +126,16 @@ __global__ void __launch_bounds__(kLtThreads, 1)
       int s = 0, ph = 0, cur_n = -1, wruns = 0;
       for (int tile = t0; tile < t1; ++tile) {
         const int nt = tile / mtiles, m0 = (tile % mtiles) * 128, n0 = nt * NT;
-        if (w_res && nt != cur_n) {
+        const int cloud = a.w_batched ? m0 / a.npc : 0;       // weight slice of this tile (npc % 128 == 0)
+        const int wkey = nt * nclouds + cloud;
+        if (w_res && wkey != cur_n) {
           tc::mbar_wait(wempty, (wruns & 1) ^ 1);             // MMAs of the previous run retired
           tc::mbar_arrive_expect_tx(wfull, (uint32_t)(2 * nkb * wtile));
           for (int kb = 0; kb < nkb; ++kb) {
-            tc::tma_load_3d(wres + (size_t)kb * wtile, &map_w, wfull, kb * 32, n0, 0);
-            tc::tma_load_3d(wres + (size_t)(nkb + kb) * wtile, &map_wlo, wfull, kb * 32, n0, 0);
+            tc::tma_load_3d(wres + (size_t)kb * wtile, &map_w, wfull, kb * 32, n0, cloud);
+            tc::tma_load_3d(wres + (size_t)(nkb + kb) * wtile, &map_wlo, wfull, kb * 32, n0, cloud);
           }
-          cur_n = nt;
+          cur_n = wkey;
           ++wruns;
         }
         for (int kb = 0; kb < nkb; ++kb) {
@@ -140,8 +144,8 @@ __global__ void __launch_bounds__(kLtThreads, 1)
           tc::mbar_arrive_expect_tx(&landed[s], 16384u + (w_res ? 0u : 2u * wtile));
           tc::tma_load_3d(st, &map_x, &landed[s], kb * 32, m0, 0);
           if (!w_res) {
-            tc::tma_load_3d(st + 32768, &map_w, &landed[s], kb * 32, n0, 0);
-            tc::tma_load_3d(st + 32768 + wtile, &map_wlo, &landed[s], kb * 32, n0, 0);
+            tc::tma_load_3d(st + 32768, &map_w, &landed[s], kb * 32, n0, cloud);
+            tc::tma_load_3d(st + 32768 + wtile, &map_wlo, &landed[s], kb * 32, n0, cloud);
           }
           if (++s == stages) { s = 0; ph ^= 1; }
         }
@@ -181,11 +185,12 @@ __global__ void __launch_bounds__(kLtThreads, 1)
       const uint32_t wbase = tc::smem_u32(wres);
       for (int tile = t0; tile < t1; ++tile, ++it) {
         const int nt = tile / mtiles;
+        const int wkey = nt * nclouds + (a.w_batched ? ((tile % mtiles) * 128) / a.npc : 0);
         const int set = (nsets == 2) ? (it & 1) : 0;
         const int use = (nsets == 2) ? (it >> 1) : it;
-        if (w_res && nt != cur_n) {
+        if (w_res && wkey != cur_n) {
           tc::mbar_wait(wfull, wruns & 1);
-          cur_n = nt;
+          cur_n = wkey;
           ++wruns;
         }
         tc::mbar_wait(&tempty[set], (use & 1) ^ 1);
@@ -197,10 +202,10 @@ __global__ void __launch_bounds__(kLtThreads, 1)
           const uint64_t xh = tc::smem_desc_sw128(st), xl = tc::smem_desc_sw128(st + 16384);
           const uint64_t wh = tc::smem_desc_sw128(w_res ? wbase + kb * wtile : st + 32768);
           const uint64_t wl = tc::smem_desc_sw128(w_res ? wbase + (nkb + kb) * wtile : st + 32768 + wtile);
-          const uint32_t acc = tmem + (set * nacc + kb / kLinChain) * NT;
+          const uint32_t acc = tmem + (set * nacc + kb / chain) * NT;
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) {
-            tc::mma_tf32(acc, xh + 2 * k8, wh + 2 * k8, idesc, ((kb % kLinChain) | k8) != 0);
+            tc::mma_tf32(acc, xh + 2 * k8, wh + 2 * k8, idesc, ((kb % chain) | k8) != 0);
             tc::mma_tf32(acc, xl + 2 * k8, wh + 2 * k8, idesc, 1);
             tc::mma_tf32(acc, xh + 2 * k8, wl + 2 * k8, idesc, 1);
           }
@@ -208,8 +213,12 @@ __global__ void __launch_bounds__(kLtThreads, 1)
           if (++s == stages) { s = 0; ph ^= 1; }
         }
         tc::mma_commit(&tfull[set]);
-        // last tile of this n-run: the resident weights may be replaced once these MMAs retire
-        if (w_res && (tile + 1 == t1 || (tile + 1) / mtiles != nt)) tc::mma_commit(wempty);
+        // last tile of this weight run: the resident slice may be replaced once these MMAs retire
+        if (w_res) {
+          const int nxt = tile + 1;
+          const int nkey = nxt < t1 ? (nxt / mtiles) * nclouds + (a.w_batched ? ((nxt % mtiles) * 128) / a.npc : 0) : -1;
+          if (nkey != wkey) tc::mma_commit(wempty);
+        }
       }
     }
     __syncwarp();
@@ -245,8 +254,9 @@ int launch_linear_tma(const LinArgs& a, cudaStream_t st) {
   // inner extent = K rounded up to 4 (the zero padding the ABI asks for); the rest of a 32-channel box reads as zero
   const int k4 = (a.K + 3) / 4 * 4;
   if (int e = make_tile_map(&mx, a.X, k4, a.ldx, a.M, 1, 128)) return e;
-  if (int e = make_tile_map(&mw, a.W, k4, a.ldw, a.Nout, 1, NT)) return e;
-  if (int e = make_tile_map(&mwl, a.Wlo, k4, a.ldw, a.Nout, 1, NT)) return e;
+  const int wb = a.w_batched ? a.M / a.npc : 1;
+  if (int e = make_tile_map(&mw, a.W, k4, a.ldw, a.Nout, wb, NT)) return e;
+  if (int e = make_tile_map(&mwl, a.Wlo, k4, a.ldw, a.Nout, wb, NT)) return e;
   auto kern = linear_tma_kernel<NT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
     return check_launch("linear_tma smem attribute");

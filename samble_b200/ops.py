@@ -279,6 +279,32 @@ def linear(x: Tensor, weight: Tensor, *, x_layout: str = "rows", out_layout: str
     return out
 
 
+def cloud_matmul(x: Tensor, w: Tensor, *, row_max: Optional[Tensor] = None, row_sum: Optional[Tensor] = None,
+                 logit_div: float = 1.0) -> Tensor:
+    """Per-cloud products on the tensor cores (3xTF32, samble_cloud_matmul): x (B,R,K), w (B,Nout,K) -> (B,R,Nout) with
+    out[b] = x[b] w[b]^T; R a multiple of 128.  With row_max/row_sum (B,R) the result is
+    exp(out / logit_div - row_max) / row_sum, i.e. softmax rows whose statistics are already known."""
+    dev = L.need_cuda(x, w, row_max, row_sum)
+    L.no_grad_check(x, w)
+    x, w = _f32(x, "x"), _f32(w, "w")
+    B, R, K = x.shape
+    Bw, Nout, Kw = w.shape
+    if Bw != B or Kw != K:
+        raise RuntimeError(f"cloud_matmul: x {tuple(x.shape)} vs w {tuple(w.shape)}")
+    if K % 4 != 0:
+        x, w = torch.nn.functional.pad(x, (0, (-K) % 4)), torch.nn.functional.pad(w, (0, (-K) % 4))
+    x, w = x.contiguous(), w.contiguous()
+    w_lo = torch.empty_like(w)
+    lib = L.lib()
+    L.check(lib.samble_split_tf32(L.ptr(w), L.ptr(w_lo), w.numel(), L.stream()), "samble_split_tf32")
+    out = torch.empty(B, R, Nout, dtype=torch.float32, device=dev)
+    if row_max is not None:
+        row_max, row_sum = _f32(row_max, "row_max").contiguous(), _f32(row_sum, "row_sum").contiguous()
+    L.check(lib.samble_cloud_matmul(L.ptr(x), x.stride(1), L.ptr(w), L.ptr(w_lo), w.stride(1), B * R, K, Nout, R, L.ptr(row_max),
+                                    L.ptr(row_sum), float(logit_div), L.ptr(out), Nout, L.stream()), "samble_cloud_matmul")
+    return out
+
+
 def linear_pool(x: Tensor, weight: Tensor, *, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None,
                 lrelu: bool = False, want_max: bool = True, want_mean: bool = True):
     """max / mean over the points of each cloud of  lrelu(x W^T * scale + shift)  without storing the activation

@@ -127,3 +127,25 @@ def test_linear_pool_matches_fp64(case):
     mx2, mean2 = ops.linear_pool(x.cuda(), w.cuda(), scale=None if scale is None else scale.cuda(),
                                  shift=None if shift is None else shift.cuda(), lrelu=lrelu)
     assert torch.equal(mx, mx2) and torch.equal(mean, mean2)
+
+
+@pytest.mark.parametrize("case", [(2, 256, 128, 640), (3, 128, 64, 100), (2, 512, 1024, 128)], ids=lambda c: f"B{c[0]}_R{c[1]}_K{c[2]}_N{c[3]}")
+def test_cloud_matmul_matches_fp64(case):
+    """samble_cloud_matmul: per-cloud weights, and the softmax-row epilogue with known row statistics."""
+    from samble_b200 import ops
+
+    B, R, K, Nout = case
+    g = torch.Generator().manual_seed(B + R + K)
+    x = torch.randn(B, R, K, generator=g)
+    w = torch.randn(B, Nout, K, generator=g) / K ** 0.5
+    ref = torch.matmul(x.double(), w.double().transpose(1, 2))
+    y = ops.cloud_matmul(x.cuda(), w.cuda())
+    assert (y.double().cpu() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    div = 3.0
+    logits = ref / div
+    rmax = logits.max(dim=-1)[0]
+    rsum = torch.exp(logits - rmax.unsqueeze(-1)).sum(-1)
+    p = ops.cloud_matmul(x.cuda(), w.cuda(), row_max=rmax.float().cuda(), row_sum=rsum.float().cuda(), logit_div=div)
+    pref = torch.softmax(logits, dim=-1)
+    assert (p.double().cpu() - pref).abs().max().item() < 2e-6
+    assert (p.double().cpu().sum(-1) - 1).abs().max().item() < 1e-5
