@@ -110,6 +110,13 @@ int samble_group(const float* pcd, const void* idx, int idx_bits, int B, int C, 
 int samble_gather_by_idx(const float* pcd, const void* idx, int idx_bits, int B, int C, int N, int M,
                          float* out, samble_stream_t stream);
 
+/* (B,R,C) -> contiguous (B,C,R); input rows in_row_stride floats apart (unit inner stride), matrices in_batch_stride
+ * floats apart (so a column slice of a wider row-major buffer is accepted): the change between the
+ * reference's channel-major (B,C,N) clouds and the point-major rows the kernels consume (x.permute(0,2,1) in
+ * utils/ops.py:50, models/attention.py:165-170). */
+int samble_transpose(const float* in, long long in_batch_stride, long long in_row_stride, int B, int R, int C, float* out,
+                     samble_stream_t stream);
+
 /* utils/ops.py:125-133  neighbor_mask: dense 0/1 (B,N,N) from idx (B,N,K) (zeros + scatter_). */
 int samble_neighbor_mask(const void* idx, int idx_bits, int B, int N, int K, float* out, samble_stream_t stream);
 
@@ -240,6 +247,11 @@ size_t samble_interpolate3_workspace_bytes(int B, int N, int M);
 int samble_interpolate3(const float* xyz_up, const float* xyz_sel, const float* feat,
                         int B, int N, int M, int C, float* out, long long* idx_out, float* dist_out,
                         void* ws, size_t ws_bytes, samble_stream_t stream);
+/* Same with point-major features: feat (B,M,C) rows ld_feat apart -> out (B,N,C) rows ld_out apart (so the result can be
+ * written straight into the right half of the (B,N,2C) buffer that models/upsample.py:158 concatenates). */
+int samble_interpolate3_rows(const float* xyz_up, const float* xyz_sel, const float* feat, long long ld_feat,
+                             int B, int N, int M, int C, float* out, long long ld_out,
+                             void* ws, size_t ws_bytes, samble_stream_t stream);
 
 #ifdef __cplusplus
 }

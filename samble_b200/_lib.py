@@ -36,6 +36,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_index_points": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
     "samble_group": (_i, (_p, _p, _i, _i, _i, _i, _i, _i, _p, _p)),
     "samble_gather_by_idx": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
+    "samble_transpose": (_i, (_p, _ll, _ll, _i, _i, _i, _p, _p)),
     "samble_neighbor_mask": (_i, (_p, _i, _i, _i, _i, _p, _p)),
     "samble_split_tf32": (_i, (_p, _p, _ll, _p)),
     "samble_cloud_matmul": (_i, (_p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p, _p, C.c_float, _p, _ll, _p)),
@@ -56,6 +57,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_ds_sample": (_i, (_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p)),
     "samble_interpolate3_workspace_bytes": (_sz, (_i, _i, _i)),
     "samble_interpolate3": (_i, (_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p)),
+    "samble_interpolate3_rows": (_i, (_p, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p, _sz, _p)),
 }
 
 _lib = None

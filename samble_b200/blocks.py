@@ -65,7 +65,7 @@ def cbl_pool(seq: nn.Sequential, x: Tensor, x_layout: str = "bcn", want_max: boo
     """(cbl(seq, x).max over points, .mean over points) with the activation never stored (ops.linear_pool).
     Falls back to the unfused form when a cloud is not a whole number of 32-point groups."""
     a, b = folded(seq[1])
-    x_rows = x.transpose(1, 2).contiguous() if x_layout == "bcn" else x
+    x_rows = ops.rows_of(x) if x_layout == "bcn" else x
     if x_rows.shape[1] % 32:
         y = ops.linear(x_rows, seq[0].weight, scale=a, shift=b, lrelu=True)
         return (y.max(dim=1)[0] if want_max else None), (y.mean(dim=1) if want_mean else None)
@@ -199,14 +199,14 @@ class Neighbor2PointAttention(nn.Module):
             x = self.bn1(x + y.transpose(1, 2))
             return self.bn2(x + self.ff(x))
         # eval: everything point-major, projections / feed-forward on the tensor cores, BatchNorms folded into epilogues
-        x_pm = x.transpose(1, 2).contiguous()                                   # (B,N,C)
+        x_pm = ops.rows_of(x)                                                   # (B,N,C)
         qkv = ops.linear(x_pm, w)                                               # (B,N,3C)
         a1, b1 = folded(self.bn1)
         a2, b2 = folded(self.bn2)
         x1 = ops.n2p_attend(qkv, idx, self.num_heads, residual=x_pm, scale=a1, shift=b1)     # bn1(x + attention)
         h = ops.linear(x1, self.ff[0].weight, lrelu=True)                       # (B,N,4C)
-        return ops.linear(h, self.ff[2].weight, scale=a2, shift=b2, residual=x1, residual_first=True, residual_layout="rows",
-                          out_layout="bcn")
+        y = ops.linear(h, self.ff[2].weight, scale=a2, shift=b2, residual=x1, residual_first=True)      # (B,N,C)
+        return y.transpose(1, 2)          # the reference's (B,C,N) shape as a view of point-major storage (ops.rows_of)
 
 
 class DownSampleToken(nn.Module):
@@ -356,6 +356,15 @@ class UpSampleInterpolation(nn.Module):
     @fp32_forward
     def forward(self, pcd_up, pcd_down, pcd_up_xyz):
         (points_select, idx_select, points_select_xyz), (points_drop, idx_drop) = pcd_down
+        if not self.training and self.distance_type == "xyz" and self.K == 3 and points_select.shape[1] % 4 == 0:
+            # point-major throughout: [pcd_up | interpolated] is assembled as rows (the interpolation writes its half in
+            # place), res_conv reads it as a GEMM operand, the result is handed on as a (B,C,N) view of rows
+            B, C, N = pcd_up.shape
+            feat = cbl(self.conv, points_select, out_layout="rows")                        # (B,M,C')
+            both = torch.empty(B, N, C + feat.shape[2], dtype=torch.float32, device=pcd_up.device)
+            both[..., :C].copy_(ops.rows_of(pcd_up))
+            ops.interpolate3_rows(pcd_up_xyz, points_select_xyz, feat, both[..., C:])
+            return cbl(self.res_conv, both, x_layout="rows", out_layout="rows").transpose(1, 2)
         interpolated = self.interpolate(pcd_up, points_select, pcd_up_xyz, points_select_xyz,
                                         distance_type=self.distance_type, K=self.K)
         x = torch.cat([pcd_up, interpolated], dim=1)

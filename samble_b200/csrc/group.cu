@@ -204,3 +204,38 @@ extern "C" int samble_neighbor_mask(const void* idx, int idx_bits, int B, int N,
   SAMBLE_LAUNCHED("mask_scatter_kernel");
   return SAMBLE_OK;
 }
+
+// ---- layout change between the reference's channel-major clouds (B,C,N) and the point-major rows (B,N,C) the
+// gathers and GEMM operand tiles want.  32x32 tiles through padded shared memory: both sides coalesced.
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, long long in_sb, long long in_ld, int R,
+                                                        int Cc, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = in + (long long)b * in_sb;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    if (r < R && c < Cc) tile[ty + 8 * i][tx] = src[(long long)r * in_ld + c];
+  }
+  __syncthreads();
+  float* dst = out + (long long)b * R * Cc;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (r < R && c < Cc) dst[(long long)c * R + r] = tile[tx][ty + 8 * i];
+  }
+}
+
+extern "C" int samble_transpose(const float* in, long long in_batch_stride, long long in_row_stride, int B, int R, int C,
+                                float* out, samble_stream_t stream) {
+  SAMBLE_REQUIRE(in && out, "samble_transpose: null pointer");
+  SAMBLE_REQUIRE(B > 0 && R > 0 && C > 0 && B <= 65535 && (R + 31) / 32 <= 65535 && in_row_stride >= C,
+                 "samble_transpose: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAMBLE_PRE(st);
+  transpose_kernel<<<dim3((C + 31) / 32, (R + 31) / 32, B), 256, 0, st>>>(in, in_batch_stride, in_row_stride, R, C, out);
+  SAMBLE_LAUNCHED("transpose_kernel");
+  return SAMBLE_OK;
+}
+

@@ -46,6 +46,48 @@ __global__ void __launch_bounds__(256) knn_stats_kernel(const float* __restrict_
   }
 }
 
+// Point-major input (unit channel stride): lane = channel, so a warp reads 128 contiguous bytes of one point; the 16
+// warps of the CTA take points w, w+16, ... and their fp64 partial sums are combined in warp order (deterministic).
+__global__ void __launch_bounds__(512) knn_stats_pm_kernel(const float* __restrict__ a, long long sb, long long sn, int N,
+                                                           int C, float* __restrict__ mean, float* __restrict__ stdv) {
+  __shared__ double ps[16][32], pq[16][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane, b = blockIdx.y;
+  const bool live = c < C;
+  const float* p = a + b * sb + (live ? c : 0);
+  double sa[4] = {0.0, 0.0, 0.0, 0.0}, qa[4] = {0.0, 0.0, 0.0, 0.0};
+  int n = warp;
+  for (; n + 48 < N; n += 64) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = p[(long long)(n + 16 * u) * sn];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      sa[u] += (double)v[u];
+      qa[u] += (double)v[u] * (double)v[u];
+    }
+  }
+  for (; n < N; n += 16) {
+    const double v = (double)p[(long long)n * sn];
+    sa[0] += v;
+    qa[0] += v * v;
+  }
+  ps[warp][lane] = (sa[0] + sa[1]) + (sa[2] + sa[3]);
+  pq[warp][lane] = (qa[0] + qa[1]) + (qa[2] + qa[3]);
+  __syncthreads();
+  if (warp == 0 && live) {
+    double s = 0.0, s2 = 0.0;
+    for (int w = 0; w < 16; ++w) {
+      s += ps[w][lane];
+      s2 += pq[w][lane];
+    }
+    const double m = s / N;
+    const double var = (s2 - s * m) / (double)(N - 1);
+    mean[b * C + c] = (float)m;
+    stdv[b * C + c] = (float)sqrt(var > 0.0 ? var : 0.0);
+  }
+}
+
 // sigma = mean over channels of the per-channel std (ops.py:27), summed in channel order.
 __device__ __forceinline__ float cloud_sigma(const float* stdv, int C) {
   float s = 0.f;
@@ -98,12 +140,22 @@ __global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restr
   const float sigma = cloud_sigma(stdv + b * C, C);
   float nn = 0.f;
   for (int c0 = 0; c0 < Cp; c0 += 32) {
+    if (sc == 1) {               // point-major input: lanes across channels (coalesced), tile[c][n] filled column-wise
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int c = c0 + ty + 8 * r, n = n0 + tx;
-      float v = 0.f;
-      if (c < C && n < N) v = __fdiv_rn(__fsub_rn(x[b * sb + n * sn + c * sc], mean[b * C + c]), sigma);
-      tile[ty + 8 * r][tx] = v;
+      for (int r = 0; r < 4; ++r) {
+        int c = c0 + tx, n = n0 + ty + 8 * r;
+        float v = 0.f;
+        if (c < C && n < N) v = __fdiv_rn(__fsub_rn(x[b * sb + n * sn + c], mean[b * C + c]), sigma);
+        tile[tx][ty + 8 * r] = v;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        int c = c0 + ty + 8 * r, n = n0 + tx;
+        float v = 0.f;
+        if (c < C && n < N) v = __fdiv_rn(__fsub_rn(x[b * sb + n * sn + c * sc], mean[b * C + c]), sigma);
+        tile[ty + 8 * r][tx] = v;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -471,7 +523,10 @@ static int launch_knn_feat(const float* an, const float* anorm, const float* bn,
 int launch_knn_stats(const float* a, long long sb, long long sn, long long sc, int B, int N, int C, float* mean,
                      float* stdv, cudaStream_t st) {
   SAMBLE_PRE(st);
-  knn_stats_kernel<<<dim3(ceil_div(C, 8), B), 256, 0, st>>>(a, sb, sn, sc, N, C, mean, stdv);
+  if (sc == 1 && C >= 8)      // point-major rows (the blocks' own activations)
+    knn_stats_pm_kernel<<<dim3(ceil_div(C, 32), B), 512, 0, st>>>(a, sb, sn, N, C, mean, stdv);
+  else
+    knn_stats_kernel<<<dim3(ceil_div(C, 8), B), 256, 0, st>>>(a, sb, sn, sc, N, C, mean, stdv);
   SAMBLE_LAUNCHED("knn_stats_kernel");
   return SAMBLE_OK;
 }

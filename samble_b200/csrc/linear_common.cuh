@@ -178,6 +178,26 @@ __device__ __forceinline__ void linear_epilogue_tile_staged(const LinArgs& a, ui
       if (a.shift && a.shift_ldb == 0) sh[j] = __ldg(a.shift + cc);
     }
     const bool full4 = c + 4 <= a.Nout;
+    // residual rows of the 8 row groups: all eight loads are issued before any is used (one latency, not eight)
+    float4 res4[8];
+    if (a.residual) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int m = m0 + warp * 32 + it * 4 + rq;
+        res4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < a.M && c < a.Nout) {
+          const float* rp = a.residual + (long long)m * a.ldr + c;
+          if (full4 && vec_ok) {
+            res4[it] = __ldg(reinterpret_cast<const float4*>(rp));
+          } else {
+            res4[it].x = __ldg(rp);
+            if (c + 1 < a.Nout) res4[it].y = __ldg(rp + 1);
+            if (c + 2 < a.Nout) res4[it].z = __ldg(rp + 2);
+            if (c + 3 < a.Nout) res4[it].w = __ldg(rp + 3);
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = it * 4 + rq;
@@ -190,17 +210,7 @@ __device__ __forceinline__ void linear_epilogue_tile_staged(const LinArgs& a, ui
 #pragma unroll
         for (int j = 0; j < 4; ++j) sh[j] = __ldg(shp + min(c + j, a.Nout - 1));
       }
-      float res[4] = {0.f, 0.f, 0.f, 0.f};
-      if (a.residual) {
-        const float* rp = a.residual + (long long)m * a.ldr + c;
-        if (full4 && vec_ok) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(rp));
-          res[0] = q.x, res[1] = q.y, res[2] = q.z, res[3] = q.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) res[j] = (c + j < a.Nout) ? __ldg(rp + j) : 0.f;
-        }
-      }
+      const float res[4] = {res4[it].x, res4[it].y, res4[it].z, res4[it].w};
       if (a.row_max) {                                           // softmax row with known max / sum (downsample.py:242-250)
         const float mu = __ldg(a.row_max + m), inv_s = 1.f / __ldg(a.row_sum + m), inv_div = 1.f / a.logit_div;
 #pragma unroll

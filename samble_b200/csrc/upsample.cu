@@ -16,7 +16,8 @@ constexpr int kUpChunk = 2048;
 __global__ void __launch_bounds__(128) interpolate3_kernel(const float4* __restrict__ up, const float4* __restrict__ sel,
                                                            const float* __restrict__ feat, int N, int M, int C,
                                                            float* __restrict__ out, long long* __restrict__ idx_out,
-                                                           float* __restrict__ dist_out) {
+                                                           float* __restrict__ dist_out, int* __restrict__ nn_idx,
+                                                           float* __restrict__ nn_w) {
   __shared__ float4 cand[kUpChunk];
   const int b = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = n < N;
@@ -65,6 +66,13 @@ __global__ void __launch_bounds__(128) interpolate3_kernel(const float4* __restr
     float* o = dist_out + ((long long)b * N + n) * 3;
     o[0] = e0, o[1] = e1, o[2] = e2;
   }
+  if (nn_idx) {                                       // point-major form: the gather runs in interp3_rows_kernel
+    int* o = nn_idx + ((long long)b * N + n) * 3;
+    float* ow = nn_w + ((long long)b * N + n) * 3;
+    o[0] = i0, o[1] = i1, o[2] = i2;
+    ow[0] = w0, ow[1] = w1, ow[2] = w2;
+  }
+  if (!feat) return;
   const float* f = feat + (long long)b * C * M;
   float* y = out + (long long)b * C * N + n;
   for (int c = 0; c < C; ++c) {
@@ -77,9 +85,34 @@ __global__ void __launch_bounds__(128) interpolate3_kernel(const float4* __restr
   }
 }
 
+// point-major features: warp per up-point, lanes across 16-byte channel chunks -- three coalesced row reads, one
+// coalesced row write (possibly into a column slice of a wider buffer: ld_out), same per-element arithmetic
+__global__ void __launch_bounds__(256) interp3_rows_kernel(const int* __restrict__ nn_idx, const float* __restrict__ nn_w,
+                                                           const float* __restrict__ feat, long long ld_feat, int N, int M,
+                                                           int C, float* __restrict__ out, long long ld_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, n = blockIdx.x * 8 + warp;
+  if (n >= N) return;
+  const long long p = (long long)b * N + n;
+  const int i0 = nn_idx[p * 3], i1 = nn_idx[p * 3 + 1], i2 = nn_idx[p * 3 + 2];
+  const float w0 = nn_w[p * 3], w1 = nn_w[p * 3 + 1], w2 = nn_w[p * 3 + 2];
+  const float* f = feat + (long long)b * M * ld_feat;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(f + i0 * ld_feat + c));
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(f + i1 * ld_feat + c));
+    const float4 cq = __ldg(reinterpret_cast<const float4*>(f + i2 * ld_feat + c));
+    float4 v;
+    v.x = __fadd_rn(__fadd_rn(__fmul_rn(a.x, w0), __fmul_rn(bq.x, w1)), __fmul_rn(cq.x, w2));
+    v.y = __fadd_rn(__fadd_rn(__fmul_rn(a.y, w0), __fmul_rn(bq.y, w1)), __fmul_rn(cq.y, w2));
+    v.z = __fadd_rn(__fadd_rn(__fmul_rn(a.z, w0), __fmul_rn(bq.z, w1)), __fmul_rn(cq.z, w2));
+    v.w = __fadd_rn(__fadd_rn(__fmul_rn(a.w, w0), __fmul_rn(bq.w, w1)), __fmul_rn(cq.w, w2));
+    *reinterpret_cast<float4*>(out + p * ld_out + c) = v;
+  }
+}
+
 static size_t interp_bytes(int B, int N, int M) {
   return 2 * align_up((size_t)B * 3 * sizeof(float), 256) + align_up((size_t)B * N * sizeof(float4), 256) +
-         align_up((size_t)B * M * sizeof(float4), 256) + 1024;
+         align_up((size_t)B * M * sizeof(float4), 256) + 2 * align_up((size_t)B * N * 3 * sizeof(float), 256) + 1024;
 }
 
 }  // namespace samble
@@ -109,7 +142,40 @@ extern "C" int samble_interpolate3(const float* xyz_up, const float* xyz_sel, co
   if (int e = launch_knn_prep_xyz(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, up, st)) return e;
   if (int e = launch_knn_prep_xyz(xyz_sel, 3LL * M, 1, M, B, M, 3, mean, stdv, sel, st)) return e;
   SAMBLE_PRE(st);
-  interpolate3_kernel<<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(up, sel, feat, N, M, C, out, idx_out, dist_out);
+  interpolate3_kernel<<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(up, sel, feat, N, M, C, out, idx_out, dist_out, nullptr,
+                                                                  nullptr);
   SAMBLE_LAUNCHED("interpolate3_kernel");
   return SAMBLE_OK;
 }
+
+extern "C" int samble_interpolate3_rows(const float* xyz_up, const float* xyz_sel, const float* feat, long long ld_feat, int B,
+                                        int N, int M, int C, float* out, long long ld_out, void* ws, size_t ws_bytes,
+                                        samble_stream_t stream) {
+  SAMBLE_REQUIRE(xyz_up && xyz_sel && feat && out && ws, "samble_interpolate3_rows: null pointer");
+  SAMBLE_REQUIRE(B > 0 && N > 0 && C > 0 && B <= 65535, "samble_interpolate3_rows: bad shape");
+  SAMBLE_REQUIRE(M >= 3, "samble_interpolate3_rows: need at least 3 selected points, got %d", M);
+  SAMBLE_REQUIRE(C % 4 == 0 && ld_feat % 4 == 0 && ld_out % 4 == 0 && ld_feat >= C && ld_out >= C &&
+                     ((uintptr_t)feat | (uintptr_t)out) % 16 == 0,
+                 "samble_interpolate3_rows: rows must be 16-byte aligned, C a multiple of 4");
+  SAMBLE_REQUIRE(ws_bytes >= interp_bytes(B, N, M), "samble_interpolate3_rows: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w(ws, ws_bytes);
+  float* mean = w.take<float>((size_t)B * 3);
+  float* stdv = w.take<float>((size_t)B * 3);
+  float4* up = w.take<float4>((size_t)B * N);
+  float4* sel = w.take<float4>((size_t)B * M);
+  int* nn_idx = w.take<int>((size_t)B * N * 3);
+  float* nn_w = w.take<float>((size_t)B * N * 3);
+  if (int e = launch_knn_stats(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, st)) return e;
+  if (int e = launch_knn_prep_xyz(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, up, st)) return e;
+  if (int e = launch_knn_prep_xyz(xyz_sel, 3LL * M, 1, M, B, M, 3, mean, stdv, sel, st)) return e;
+  SAMBLE_PRE(st);
+  interpolate3_kernel<<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(up, sel, nullptr, N, M, C, nullptr, nullptr, nullptr, nn_idx,
+                                                                  nn_w);
+  SAMBLE_LAUNCHED("interpolate3_kernel");
+  SAMBLE_PRE(st);
+  interp3_rows_kernel<<<dim3(ceil_div(N, 8), B), 256, 0, st>>>(nn_idx, nn_w, feat, ld_feat, N, M, C, out, ld_out);
+  SAMBLE_LAUNCHED("interp3_rows_kernel");
+  return SAMBLE_OK;
+}
+

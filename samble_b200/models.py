@@ -162,7 +162,7 @@ class ShapeNetModel(nn.Module):
             # W_g g (one vector per cloud, folded into a per-cloud shift) + W_f f (per point)
             # The head stays point-major between its layers (one transpose in, the last GEMM writes (B,50,N)); the
             # 1024-channel global branch is pooled inside the GEMM epilogue and never stored.
-            f_rows = f.transpose(1, 2).contiguous()                           # (B,N,C)
+            f_rows = ops.rows_of(f)                               # (B,N,C)
             gmax, gmean = blocks.cbl_pool(self.conv, f_rows, x_layout="rows")
             g = torch.cat([gmax, gmean, self.conv1(category_id).squeeze(-1)], dim=1)     # (B, 2048+64)
             w2 = self.conv2[0].weight
@@ -196,7 +196,7 @@ class ClsFeatureLearningBlock(_BlockBase):
         """conv(x).max(dim=-1)[0] (cls_model.py:104,133); eval mode pools inside the GEMM epilogue."""
         if self.training or x.shape[-1] % 32:
             return conv(x).max(dim=-1)[0]
-        return ops.linear_pool(x.transpose(1, 2).contiguous(), conv.weight, want_mean=False)[0]
+        return ops.linear_pool(ops.rows_of(x), conv.weight, want_mean=False)[0]
 
     @fp32_forward
     def forward(self, x: Tensor):

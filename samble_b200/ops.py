@@ -176,6 +176,29 @@ def gather_by_idx(pcd: Tensor, idx: Tensor) -> Tensor:
 _W_SPLIT: dict = {}      # id(base tensor) -> (weakref(base), version, {view key: (W padded, W_lo)})
 
 
+def rows_of(x: Tensor) -> Tensor:
+    """Point-major rows (B,N,C), contiguous, of a cloud given in the reference's (B,C,N) shape.  Block outputs are
+    (B,C,N) VIEWS of point-major storage (stride(1) == 1), so between our own blocks this is free; a genuinely
+    channel-major tensor is transposed once (samble_transpose)."""
+    if x.dim() == 3 and x.stride(1) == 1 and x.stride(2) == x.shape[1] and x.stride(0) == x.shape[1] * x.shape[2]:
+        return x.transpose(1, 2)
+    return transpose12(x)
+
+
+def transpose12(x: Tensor) -> Tensor:
+    """x (B,R,C) -> contiguous (B,C,R) (samble_transpose); x.transpose(1,2).contiguous() without ATen's strided copy."""
+    dev = L.need_cuda(x)
+    x = _f32(x, "x")
+    if x.dim() != 3:
+        raise RuntimeError("transpose12: expected a 3-D tensor")
+    B, R, Cc = x.shape
+    if x.stride(2) != 1 or x.stride(1) < Cc:
+        x = x.contiguous()
+    out = torch.empty(B, Cc, R, dtype=torch.float32, device=dev)
+    L.check(L.lib().samble_transpose(L.ptr(x), x.stride(0), x.stride(1), B, R, Cc, L.ptr(out), L.stream()), "samble_transpose")
+    return out
+
+
 def _split_weight(weight: Tensor):
     """(W padded to a multiple of 4 columns, W_lo = W - tf32_trunc(W)).  Cached per LIVE base tensor (weak reference:
     an address recycled by the allocator for a new tensor never hits), its in-place version, and the view taken of it."""
@@ -225,7 +248,7 @@ def linear(x: Tensor, weight: Tensor, *, x_layout: str = "rows", out_layout: str
     if x_layout == "bcn" and x.shape[1] >= 32:
         # measured: the row-major loader (cp.async, two stages ahead) is 2x faster than the channel-major one even
         # after paying for this transposing copy (tools/time_linear_calls.py)
-        x, x_layout = _f32(x, "x").transpose(1, 2).contiguous(), "rows"
+        x, x_layout = rows_of(x), "rows"
     if x_layout == "bcn":
         x = _f32(x, "x").contiguous()
         B, Kx, P = x.shape
@@ -293,7 +316,10 @@ def cloud_matmul(x: Tensor, w: Tensor, *, row_max: Optional[Tensor] = None, row_
         raise RuntimeError(f"cloud_matmul: x {tuple(x.shape)} vs w {tuple(w.shape)}")
     if K % 4 != 0:
         x, w = torch.nn.functional.pad(x, (0, (-K) % 4)), torch.nn.functional.pad(w, (0, (-K) % 4))
-    x, w = x.contiguous(), w.contiguous()
+    x = x.contiguous()
+    if not w.is_contiguous():       # a (B,K,Nout) tensor viewed as (B,Nout,K): one tiled transpose instead of a strided copy
+        wt = w.transpose(1, 2)
+        w = transpose12(wt) if (wt.stride(2) == 1 and wt.stride(1) >= wt.shape[2]) else w.contiguous()
     w_lo = torch.empty_like(w)
     lib = L.lib()
     L.check(lib.samble_split_tf32(L.ptr(w), L.ptr(w_lo), w.numel(), L.stream()), "samble_split_tf32")
@@ -448,6 +474,29 @@ def interpolate3(xyz_up: Tensor, xyz_sel: Tensor, feat: Tensor, want_idx: bool =
     L.check(lib.samble_interpolate3(L.ptr(xyz_up), L.ptr(xyz_sel), L.ptr(feat), B, N, M, Cc, L.ptr(out), L.ptr(idx),
                                     L.ptr(dist), L.ptr(ws), ws.numel(), L.stream()), "samble_interpolate3")
     return (out, idx, dist) if want_idx else out
+
+
+def interpolate3_rows(xyz_up: Tensor, xyz_sel: Tensor, feat_rows: Tensor, out: Tensor) -> Tensor:
+    """interpolate3 with point-major features: feat_rows (B,M,C) -> written into `out` (B,N,C), which may be a column
+    slice of a wider row-major buffer (unit inner stride)."""
+    dev = L.need_cuda(xyz_up, xyz_sel, feat_rows, out)
+    L.no_grad_check(xyz_up, xyz_sel, feat_rows)
+    xyz_up, xyz_sel = (_f32(t, "xyz").contiguous() for t in (xyz_up, xyz_sel))
+    feat_rows = _f32(feat_rows, "feat")
+    if feat_rows.stride(2) != 1:
+        feat_rows = feat_rows.contiguous()
+    B, three, N = xyz_up.shape
+    M, Cc = xyz_sel.shape[2], feat_rows.shape[2]
+    if three != 3 or xyz_sel.shape[1] != 3:
+        raise ValueError("interpolate3: xyz tensors must be (B,3,N)")
+    if tuple(out.shape) != (B, N, Cc) or out.stride(2) != 1 or out.stride(0) != N * out.stride(1) or \
+            feat_rows.stride(0) != M * feat_rows.stride(1):
+        raise RuntimeError("interpolate3_rows: out must be (B,N,C) rows with a common pitch")
+    lib = L.lib()
+    ws = L.workspace(lib.samble_interpolate3_workspace_bytes(B, N, M), dev)
+    L.check(lib.samble_interpolate3_rows(L.ptr(xyz_up), L.ptr(xyz_sel), L.ptr(feat_rows), feat_rows.stride(1), B, N, M, Cc,
+                                         L.ptr(out), out.stride(1), L.ptr(ws), ws.numel(), L.stream()), "samble_interpolate3_rows")
+    return out
 
 
 # ------------------------------------------------------------------ bins (reference signatures)

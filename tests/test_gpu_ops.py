@@ -309,3 +309,13 @@ def test_two_pass_xyz_knn_duplicates_overflow_fallback():
     g = cu(g.contiguous())
     (d0, i0), (d1, i1) = _knn_both(g, g, 32)
     assert torch.equal(i0, i1) and torch.equal(d0, d1)
+
+
+def test_transpose12():
+    x = torch.randn(3, 1000, 130, generator=torch.Generator().manual_seed(1))
+    assert torch.equal(ops.transpose12(cu(x)).cpu(), x.transpose(1, 2).contiguous())
+    wide = torch.randn(2, 257, 384, generator=torch.Generator().manual_seed(2))
+    sl = cu(wide)[..., 128:256]                                     # column slice of a wider row-major buffer
+    assert torch.equal(ops.transpose12(sl).cpu(), wide[..., 128:256].transpose(1, 2).contiguous())
+    bcn = cu(torch.randn(2, 64, 300, generator=torch.Generator().manual_seed(3)))
+    assert torch.equal(ops.transpose12(bcn), bcn.transpose(1, 2).contiguous())
