@@ -10,7 +10,7 @@
 
 namespace samble {
 
-constexpr int kEtThreads = 288;
+constexpr int kEtThreads = 416;      // 4 epilogue warps, MMA issuer, 2 x 4 loader warps
 constexpr int kEtStages = 4;
 
 __device__ __forceinline__ unsigned f2ord(float f) {       // order-preserving float -> uint
@@ -74,11 +74,15 @@ __global__ void __launch_bounds__(kEtThreads, 1)
 
   if (warp >= 5) {
     // ================= loaders: thread = edge row (point lw of the tile, edge `lane`) =================
-    const int lw = warp - 5;
+    // Two groups of four warps take alternate stages, so one group's gathers (an L2 round trip that registers cannot
+    // prefetch more than one stage deep) are in flight while the other group builds its stage.
+    const int grp = (warp - 5) >> 2, lw = (warp - 5) & 3;
     const int row = lw * 32 + lane;
-    int g = 0;
+    const int ntl = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+    const int G = ntl * nkb;
     float4 pv[8], rv[8];
-    auto fetch = [&](int tile, int kb) {            // loads for one stage into registers
+    auto fetch = [&](int g) {                       // loads for stage g into registers
+      const int tile = blockIdx.x + (g / nkb) * gridDim.x, kb = g % nkb;
       const int b = tile / tiles_per_cloud, n = (tile % tiles_per_cloud) * 4 + lw;
       const bool ok = n < N;
       const long long prow = (long long)b * N + (ok ? n : 0);
@@ -91,9 +95,8 @@ __global__ void __launch_bounds__(kEtThreads, 1)
         rv[c] = ok ? __ldg(rp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    int tile = blockIdx.x, kb = 0;
-    if (tile < total) fetch(tile, 0);
-    while (tile < total) {
+    if (grp < G) fetch(grp);
+    for (int g = grp; g < G; g += 2) {
       const int s = g % kEtStages;
       tc::mbar_wait(&empty[s], ((g / kEtStages) & 1) ^ 1);
       uint8_t* hh = sH + (size_t)s * 32768;
@@ -115,14 +118,11 @@ __global__ void __launch_bounds__(kEtThreads, 1)
         *reinterpret_cast<float4*>(hh + off) = h;
         *reinterpret_cast<float4*>(hl + off) = lo;
       }
-      // next stage's gathers fly while the fence / arrive / next barrier wait happen
-      int ntile = tile, nkb_i = kb + 1;
-      if (nkb_i == nkb) nkb_i = 0, ntile += gridDim.x;
-      if (ntile < total) fetch(ntile, nkb_i);
+      // this group's next stage: its gathers fly while the fence / arrive / next barrier wait happen
+      if (g + 2 < G) fetch(g + 2);
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full[s]);
-      tile = ntile, kb = nkb_i, ++g;
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
