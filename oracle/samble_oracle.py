@@ -29,6 +29,7 @@ live in tests/test_oracle_vs_reference.py.
 from __future__ import annotations
 
 import math
+import numbers
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -176,17 +177,51 @@ def calculate_num_points_to_choose(bin_prob: Tensor, max_num_points: Tensor, tot
     return k
 
 
-def generating_downsampled_index(M: int, score: Tensor, mask: Tensor, mode: str, boltzmann_t,
-                                 k: Tensor) -> Tensor:
-    """utils/ops.py:467-505, `topk` branch only (the bit-exact target; the
-    multinomial branches :507-613 are SURVEY 8f "next").  Returns (B,1,M) int64:
-    bins in order, within a bin descending score+1e-8."""
-    if mode != "topk":
-        raise NotImplementedError("oracle covers sample_mode='topk' only")
+def sampling_probabilities(score: Tensor, mask: Tensor, mode: str, boltzmann_t) -> Tensor:
+    """utils/ops.py:507-592: per-(cloud, bin) categorical distribution over the N points, (B*nb, N).
+    'uniform': the bin's membership mask (an empty bin -> all ones, :511-513).
+    'random' : z-score -> tanh -> exp(score * 1/T) restricted to the bin and normalised; NaN -> 1e-8 (:515-590)."""
     B, _, N, nb = mask.shape
-    masked = (score + 1e-8).unsqueeze(3) * mask
-    order = torch.sort(masked, dim=2, descending=True)[1].squeeze(1)      # (B,N,nb)
-    rows = [torch.cat([order[b, : int(k[b, j]), j] for j in range(nb)]) for b in range(B)]
+    if mode == "uniform":
+        p = mask.float().squeeze(dim=1)
+        p = p + (torch.sum(p, dim=1, keepdim=True) == 0)
+    elif mode == "random":
+        z = (score - torch.mean(score, dim=2, keepdim=True)) / torch.std(score, dim=2, unbiased=False, keepdim=True)
+        z = torch.tanh(z)
+        if boltzmann_t in ("mode_1", "mode_3"):
+            inv_t = torch.sum(mask, dim=2, keepdim=True).float() / (100.0 if boltzmann_t == "mode_1" else 200.0)
+        elif boltzmann_t == "mode_2":
+            inv_t = N / (100.0 * nb)
+        elif boltzmann_t == "mode_4":
+            inv_t = N / (200.0 * nb)
+        elif isinstance(boltzmann_t, numbers.Number):
+            inv_t = 1 / boltzmann_t
+        else:
+            raise NotImplementedError
+        p = torch.exp(z.unsqueeze(3) * inv_t) * mask
+        p = p / torch.sum(p, dim=2, keepdim=True)
+        p = p.squeeze(dim=1)
+        p[torch.isnan(p)] = 1e-8
+    else:
+        raise ValueError("Please check the setting of bin sample mode. It must be topk, multinomial or random!")
+    return p.permute(0, 2, 1).reshape(-1, N)
+
+
+def generating_downsampled_index(M: int, score: Tensor, mask: Tensor, mode: str, boltzmann_t,
+                                 k: Tensor, generator=None) -> Tensor:
+    """utils/ops.py:467-619.  Returns (B,1,M) int64: bins in order; within a bin `topk` takes descending
+    score+1e-8 (:476-505), `uniform`/`random` take the first k of M draws without replacement from
+    sampling_probabilities (:594-612; torch.multinomial, so bit-equal to the reference only under the same
+    CPU RNG state -- tests/test_oracle_vs_reference.py seeds both)."""
+    B, _, N, nb = mask.shape
+    if mode == "topk":
+        masked = (score + 1e-8).unsqueeze(3) * mask
+        order = torch.sort(masked, dim=2, descending=True)[1].squeeze(1)      # (B,N,nb)
+        rows = [torch.cat([order[b, : int(k[b, j]), j] for j in range(nb)]) for b in range(B)]
+        return torch.stack(rows).reshape(B, 1, M)
+    p = sampling_probabilities(score, mask, mode, boltzmann_t)
+    draws = torch.multinomial(p, M, generator=generator).reshape(B, nb, M)
+    rows = [torch.cat([draws[b, j, : int(k[b, j])] for j in range(nb)]) for b in range(B)]
     return torch.stack(rows).reshape(B, 1, M)
 
 

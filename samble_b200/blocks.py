@@ -275,8 +275,8 @@ class DownSampleToken(nn.Module):
         if self.asm != "dot" or self.idx_mode != "sparse_col_sqr" or self.relu_mean_order != "mean_relu" or self.num_heads != 1:
             raise NotImplementedError("native DownSampleToken covers asm='dot', idx_mode='sparse_col_sqr', "
                                       "relu_mean_order='mean_relu', one head (the shipped configs)")
-        if self.bin_sample_mode != "topk":
-            raise NotImplementedError(f"bin sample_mode '{self.bin_sample_mode}' is SURVEY 8f item f3; use 'topk'")
+        if self.bin_sample_mode not in ("topk", "uniform", "random"):
+            raise ValueError("Please check the setting of bin sample mode. It must be topk, multinomial or random!")
         B, C, N = x.shape
         D, nb = self.q_depth, self.num_bins
         # projections of the points and of the nb bin tokens (shared by the whole batch, :116-118)
@@ -298,8 +298,11 @@ class DownSampleToken(nn.Module):
             self.bin_boundaries = ops.update_sampling_score_bin_boundary(
                 self.bin_boundaries, z.view(B, 1, N, 1), nb, self.momentum_update_factor)
         s = ops.ds_sample(score, tok_logits, self._cuts(x.device), self.M)
-        index_down = s["idx"].view(B, 1, self.M)
         self.bin_points_mask = (s["bin_id"].view(B, 1, N, 1) == torch.arange(nb, device=x.device, dtype=torch.uint8))
+        if self.bin_sample_mode != "topk":           # stochastic modes (ops.py:507-613): bins and k as above, indices drawn
+            s["idx"] = ops.generating_downsampled_index(self.M, score.view(B, 1, N), self.bin_points_mask, self.bin_sample_mode,
+                                                        self.boltzmann_T, s["k"]).view(B, self.M)
+        index_down = s["idx"].view(B, 1, self.M)
         self.k_point_to_choose = s["k"]
         self.bin_weights_beforerelu = s["w_raw"]
 

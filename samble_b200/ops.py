@@ -557,13 +557,50 @@ def calculate_num_points_to_choose(bin_prob: Tensor, max_num_points: Tensor, tot
     return k
 
 
+def sampling_probabilities(attention_point_score: Tensor, bin_points_mask: Tensor, bin_sample_mode: str, boltzmann_t) -> Tensor:
+    """utils/ops.py:507-592: the per-(cloud, bin) categorical distribution the 'uniform' / 'random' sampling modes
+    draw from, (B*nb, N) on the device.  A handful of element-wise ops over (B,N,nb): latency-bound, left to ATen."""
+    import numbers
+
+    B, _, N, nb = bin_points_mask.shape
+    if bin_sample_mode == "uniform":
+        p = bin_points_mask.float().squeeze(dim=1)
+        p = p + (torch.sum(p, dim=1, keepdim=True) == 0)
+    elif bin_sample_mode == "random":
+        z = (attention_point_score - torch.mean(attention_point_score, dim=2, keepdim=True)) / torch.std(
+            attention_point_score, dim=2, unbiased=False, keepdim=True)
+        z = torch.tanh(z)
+        if boltzmann_t in ("mode_1", "mode_3"):
+            inv_t = torch.sum(bin_points_mask, dim=2, keepdim=True).float() / (100.0 if boltzmann_t == "mode_1" else 200.0)
+        elif boltzmann_t == "mode_2":
+            inv_t = N / (100.0 * nb)
+        elif boltzmann_t == "mode_4":
+            inv_t = N / (200.0 * nb)
+        elif isinstance(boltzmann_t, numbers.Number):
+            inv_t = 1 / boltzmann_t
+        else:
+            raise NotImplementedError
+        p = torch.exp(z.unsqueeze(3) * inv_t) * bin_points_mask
+        p = p / torch.sum(p, dim=2, keepdim=True)
+        p = p.squeeze(dim=1)
+        p = torch.where(torch.isnan(p), torch.full_like(p, 1e-8), p)
+    else:
+        raise ValueError("Please check the setting of bin sample mode. It must be topk, multinomial or random!")
+    return p.permute(0, 2, 1).reshape(-1, N)
+
+
 def generating_downsampled_index(M: int, attention_point_score: Tensor, bin_points_mask: Tensor, bin_sample_mode: str,
                                  boltzmann_t, k_point_to_choose: Tensor) -> Tensor:
-    """utils/ops.py:467-619.  'topk' (:476-505) is native; 'uniform'/'random' (:507-613) draw from
-    torch.multinomial in the reference and are SURVEY 8f item f3 (not built yet)."""
+    """utils/ops.py:467-619.  'topk' (:476-505) is the native per-bin top-k kernel.  'uniform' / 'random' (:507-613)
+    draw M indices per (cloud, bin) without replacement with torch.multinomial -- the reference's own sampler, so
+    the stream of random numbers is the device generator's -- and keep the first k of each bin, bins in order."""
     if bin_sample_mode in ("uniform", "random"):
-        raise NotImplementedError(f"bin_sample_mode '{bin_sample_mode}' is not implemented natively yet "
-                                  "(SURVEY 8f f3); use 'topk'")
+        L.need_cuda(attention_point_score, bin_points_mask, k_point_to_choose)
+        B, H, N, nb = bin_points_mask.shape
+        p = sampling_probabilities(attention_point_score, bin_points_mask, bin_sample_mode, boltzmann_t)
+        draws = torch.multinomial(p, M).reshape(B, nb, M)
+        keep = torch.arange(M, device=draws.device).view(1, 1, M) < k_point_to_choose.view(B, nb, 1)
+        return draws[keep].reshape(B, 1, M)            # row-major over (cloud, bin, draw): bins in order, sum_k = M
     if bin_sample_mode != "topk":
         raise ValueError("Please check the setting of bin sample mode. It must be topk, multinomial or random!")
     dev = L.need_cuda(attention_point_score, bin_points_mask, k_point_to_choose)

@@ -313,3 +313,33 @@ def test_seg_forward_full_size_properties():
         for a, ds in zip(idx1, m.block.downsample_list):
             ov = np.mean([len(set(a[4 + b, 0].tolist()) & set(ds.idx[b, 0].tolist())) / a.shape[-1] for b in range(4)])
             assert ov >= 0.9, ov
+
+
+@pytest.mark.parametrize("mode", ["random", "uniform"])
+def test_stochastic_sample_modes_run_and_respect_bins(mode):
+    """sample_mode 'random' (the reference's YAML default) / 'uniform', utils/ops.py:507-613: the scores, bins and the
+    k per bin are the deterministic native path; the indices are torch.multinomial draws that must fall into their
+    bin, be distinct, and number k per bin."""
+    from samble_b200 import models
+    from samble_b200.config import seg_config
+    from samble_b200.testing import fill_state_dict_, synthetic_clouds
+
+    B, N = 2, 512
+    m = models.ShapeNetModel(seg_config(M=(N // 2, N // 4), sample_mode=mode))
+    m.load_state_dict(fill_state_dict_(m.state_dict(), seed=1, sharpen=4.0))
+    m = m.eval().cuda()
+    x, cat = synthetic_clouds(B, N, 2)
+    with torch.no_grad():
+        y = m(x.cuda(), cat.cuda())
+    assert tuple(y.shape) == (B, 50, N) and torch.isfinite(y).all()
+    for ds in m.block.downsample_list:
+        idx, mask, k = ds.idx.cpu(), ds.bin_points_mask.cpu(), ds.k_point_to_choose.cpu()
+        nb = mask.shape[-1]
+        for b in range(B):
+            assert len(set(idx[b, 0].tolist())) == idx.shape[-1]              # bins are disjoint, draws without replacement
+            off = 0
+            for j in range(nb):
+                seg = idx[b, 0, off:off + int(k[b, j])]
+                assert bool(mask[b, 0, seg, j].all())
+                off += int(k[b, j])
+            assert off == idx.shape[-1]

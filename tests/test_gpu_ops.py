@@ -198,8 +198,18 @@ def test_bin_partition_and_topk_ops(N, nb, M):
     score_nt = torch.rand(B, 1, N, generator=g) * 1e-3                          # no ties: bit-exact
     idx_nt = ops.generating_downsampled_index(M, cu(score_nt), cu(mask_s_ref), "topk", 0.1, cu(kk))
     assert torch.equal(idx_nt.cpu(), O.generating_downsampled_index(M, score_nt, mask_s_ref, "topk", 0.1, kk))
-    with pytest.raises(NotImplementedError):
-        ops.generating_downsampled_index(M, cu(score), cu(mask_s_ref), "random", 0.1, cu(kk))
+    # stochastic modes: same distributions as the oracle; draws come from the right bin, distinct, k per bin
+    for mode, bt in (("uniform", 0.1), ("random", 0.1), ("random", "mode_1"), ("random", "mode_2")):
+        p = ops.sampling_probabilities(cu(score), cu(mask_s_ref), mode, bt)
+        torch.testing.assert_close(p.cpu(), O.sampling_probabilities(score, mask_s_ref, mode, bt), rtol=2e-5, atol=1e-9)
+        idx_r = ops.generating_downsampled_index(M, cu(score), cu(mask_s_ref), mode, bt, cu(kk)).cpu()
+        assert tuple(idx_r.shape) == (B, 1, M)
+        for b in range(B):
+            off = 0
+            for j in range(nb):
+                seg = idx_r[b, 0, off:off + int(kk[b, j])]
+                assert len(set(seg.tolist())) == len(seg) and bool(mask_s_ref[b, 0, seg, j].all())
+                off += int(kk[b, j])
     with pytest.raises(ValueError):
         ops.generating_downsampled_index(M, cu(score), cu(mask_s_ref), "bogus", 0.1, cu(kk))
 

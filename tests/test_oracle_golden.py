@@ -89,8 +89,24 @@ def test_bin_partition_and_topk(ops_gold):
     np.testing.assert_array_equal(kk.numpy(), ops_gold["bin.static.k"])
     idx = O.generating_downsampled_index(100, score2, mask3, "topk", 0.1, kk)
     np.testing.assert_array_equal(idx.numpy(), ops_gold["bin.static.idx"])
-    with pytest.raises(NotImplementedError):
-        O.generating_downsampled_index(100, score2, mask3, "random", 0.1, kk)
+    # stochastic modes (utils/ops.py:507-613): distributions live on the right bins; draws respect bins and counts
+    for mode, bt in (("uniform", 0.1), ("random", 0.1), ("random", "mode_1"), ("random", "mode_4")):
+        p = O.sampling_probabilities(score2, mask3, mode, bt).reshape(3, 4, 200)
+        inbin = mask3.squeeze(1).permute(0, 2, 1)
+        nonempty = inbin.sum(-1, keepdim=True) > 0
+        assert torch.all((p > 0) == torch.where(nonempty, inbin, torch.ones_like(inbin)))
+        if mode == "random":
+            assert torch.allclose(p.sum(-1)[nonempty.squeeze(-1)], torch.tensor(1.0), atol=1e-5)
+        idx_r = O.generating_downsampled_index(100, score2, mask3, mode, bt, kk, generator=torch.Generator().manual_seed(7))
+        assert tuple(idx_r.shape) == (3, 1, 100)
+        for b in range(3):
+            off = 0
+            for j in range(4):
+                seg = idx_r[b, 0, off:off + int(kk[b, j])]
+                assert len(set(seg.tolist())) == len(seg) and bool(mask3[b, 0, seg, j].all())
+                off += int(kk[b, j])
+    with pytest.raises(ValueError):
+        O.generating_downsampled_index(100, score2, mask3, "bogus", 0.1, kk)
 
 
 def _block_sd():

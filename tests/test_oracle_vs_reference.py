@@ -76,3 +76,26 @@ def test_patch_swaps_the_reference_entry_points():
         m = R.build_model("seg", R.reference_config("seg"))          # reference wiring builds OUR blocks
         assert isinstance(m.block.downsample_list[0], blocks.DownSampleToken)
     assert ref_ops.group is not ops.group and downsample.DownSampleToken is not blocks.DownSampleToken
+
+
+@pytest.mark.parametrize("mode,bt", [("uniform", 0.1), ("random", 0.1), ("random", "mode_1"), ("random", "mode_3"), ("random", 0.05)])
+def test_stochastic_sampling_modes_match_the_reference_under_the_same_rng(mode, bt):
+    """utils/ops.py:507-613: with the CPU generator in the same state the oracle draws the reference's indices, which
+    pins its sampling distributions bit for bit (torch.multinomial consumes them directly)."""
+    import torch
+
+    from oracle import samble_oracle as O
+
+    ref_ops = R.modules()[0]
+    g = torch.Generator().manual_seed(11)
+    B, N, nb, M = 3, 256, 4, 96
+    score = torch.rand(B, 1, N, generator=g) * 1e-3
+    bins = torch.randint(0, nb, (B, 1, N, 1), generator=g)
+    mask = bins == torch.arange(nb).view(1, 1, 1, nb)
+    k = O.calculate_num_points_to_choose(torch.rand(B, nb, generator=g), mask.squeeze(1).sum(1), M)
+    torch.manual_seed(5)
+    want = ref_ops.generating_downsampled_index(M, score.clone(), mask, mode, bt, k)
+    torch.manual_seed(5)
+    got = O.generating_downsampled_index(M, score.clone(), mask, mode, bt, k)
+    assert torch.equal(want, got)
+
