@@ -191,6 +191,35 @@ def linear_census(model, x, cat):
     return tot
 
 
+def downsample_block_ms(model, x, cat, reps=3):
+    """Device time of the DownSampleToken blocks of one forward (their kNN, scoring, sampler and selected-row
+    attention): BASELINE's secondary figure 'kNN+sampling us/batch' and the 'kNN+DownSample path' of SURVEY 8d."""
+    ds_list = list(model.block.downsample_list)
+    spans = []
+    originals = [ds.forward for ds in ds_list]
+
+    def wrap(fn):
+        def timed(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            spans.append((e0, e1))
+            return out
+        return timed
+
+    for ds, fn in zip(ds_list, originals):
+        ds.forward = wrap(fn)
+    try:
+        for _ in range(reps):
+            model(x, cat)
+        torch.cuda.synchronize()
+    finally:
+        for ds in ds_list:
+            del ds.forward                       # back to the class method
+    return sum(a.elapsed_time(b) for a, b in spans) / reps
+
+
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per step of `kernel`, from the committed ncu --set full capture
     (profiles/r1_traffic.json, written by tools/summarize_ncu.py traffic); None if that kernel was not captured."""
@@ -199,6 +228,24 @@ def ncu_traffic(kernel):
         return None
     with open(p) as f:
         return json.load(f).get("dram_bytes_per_step", {}).get(kernel)
+
+
+def knn_sampling_block(ds_ms, B, N, pk):
+    """BASELINE.json's secondary metric and SURVEY 8d's 'kNN + DownSample path': both DownSampleToken blocks of the
+    step (feature kNN + q/k/v + QK^T row statistics + edge scores + bins / k / per-bin top-k + selected rows x V).
+    Algorithmic FLOPs per cloud from SURVEY 8d: kNN 2*N^2*C plus DS 6*N*D^2 + 2*N*(N+nb)*D + 2*N*K*D + 2*M*(N+nb)*D, for
+    N -> N/2 and N/2 -> N/4 (3.68 GFLOP at N=2048).  Peak = tf32 tensor rate (half the measured bf16 rate); the
+    kernels spend 3 tf32 MMAs per fp32-class product (linear layers, QK^T) or 2 passes (kNN), stated so the fraction
+    can be read either way."""
+    def ds_flops(n, m, d=128, nb=4, k=32):
+        return 2.0 * n * n * d + 6.0 * n * d * d + 2.0 * n * (n + nb) * d + 2.0 * n * k * d + 2.0 * m * (n + nb) * d
+
+    flops = (ds_flops(N, N // 2) + ds_flops(N // 2, N // 4)) * B
+    tf32_peak = pk["bf16_tflops_sustained"] / 2
+    ach = flops / (ds_ms * 1e-3) / 1e12
+    return {"us_per_batch": ds_ms * 1e3, "clouds": B, "algorithmic_gflop_per_batch": flops / 1e9, "achieved_tflops": ach,
+            "tf32_peak_tflops": tf32_peak, "frac_of_tf32_peak": ach / tf32_peak,
+            "note": "both DownSampleToken blocks (2048->1024, 1024->512) incl. their feature kNN, eager launches"}
 
 
 def roofline_of(dom, ms, census, B, N, pk):
@@ -323,6 +370,7 @@ def run_native(args):
         L.profile(False)
         prof_total_ms = t0.elapsed_time(t1) / 3
         census = linear_census(model, x, cat)
+        ds_ms = downsample_block_ms(model, x, cat)
 
     value = B * world * args.steps / (ms / 1e3)
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
@@ -345,6 +393,7 @@ def run_native(args):
                     "h2d_bytes_per_step": int(xh.numel() * 4 + cath.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
             "gpu_launches": launches_per_step * args.steps, "launch_mode": "eager" if args.no_graph else "cuda_graph",
             "roofline": roof,
+            "knn_plus_sampling": knn_sampling_block(ds_ms, B, N, pk),
             "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(native_ms.items(), key=lambda kv: -kv[1])},
             "native_share_of_step": min(1.0, sum(native_ms.values()) / step_ms)}
     if not args.no_cpu_baseline and world == 1:
