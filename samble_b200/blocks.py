@@ -289,7 +289,8 @@ class DownSampleToken(nn.Module):
         v_tok = torch.matmul(tok, self.v_conv.weight.view(C, C).t())
 
         idx = ops.knn_indices(x, self.K, ordered=False)                                       # neighbor_mask's kNN (:301)
-        rowmax, rowsum, tok_logits = ops.ds_row_stats(q, k, k_tok)
+        k_split = ops.split_operand(k) if self.M % 128 == 0 else None          # k's tf32 split, for the selected rows
+        rowmax, rowsum, tok_logits = ops.ds_row_stats(q, k, k_tok, k_split=k_split)
         score = ops.ds_edge_score(q, k, rowmax, rowsum, idx)                   # (B,N)
         self.attention_point_score = score.view(B, 1, N)
 
@@ -316,7 +317,7 @@ class DownSampleToken(nn.Module):
         l_tok = torch.gather(tok_logits, 1, sel.unsqueeze(-1).expand(-1, -1, nb))                 # already / scale
         p_tok = torch.exp(l_tok - m_sel.unsqueeze(-1)) / s_sel.unsqueeze(-1)
         if self.M % 128 == 0:
-            att = ops.cloud_matmul(q_sel, k, row_max=m_sel, row_sum=s_sel, logit_div=scale)          # (B,M,N)
+            att = ops.cloud_matmul(q_sel, k, row_max=m_sel, row_sum=s_sel, logit_div=scale, w_split=k_split)     # (B,M,N)
             x_ds = ops.cloud_matmul(att, v.transpose(1, 2)) + torch.matmul(p_tok, v_tok)           # (B,M,C)
         else:
             att = torch.exp(torch.matmul(q_sel, k.transpose(1, 2)) / scale - m_sel.unsqueeze(-1)) / s_sel.unsqueeze(-1)

@@ -37,6 +37,9 @@ struct LinArgs {
   const float* row_sum;
   float logit_div;
   int chain;                          // K-blocks per accumulation chain (linear_tma.cu; 0 = kLinChain)
+  // row-statistics mode (linear_tma.cu): nothing is stored but, per row and 128-column tile, the maximum of
+  // acc / logit_div and the sum of exp(. - max):  stat_out[m * ntiles + n_tile] = (max, sum)
+  float2* stat_out;
 };
 
 
@@ -295,6 +298,42 @@ __device__ __forceinline__ void linear_epilogue_tile_pool(const LinArgs& a, uint
       if (a.pool_sum) a.pool_sum[(long long)grp * a.Nout + c] = v[0];
     }
   }
+}
+
+// Row-statistics epilogue (DownSampleToken pass 1, models/downsample.py:139-153): the N x N logits are never stored;
+// each row keeps an online (max, sum of exp) over the tile's columns.
+template <int NT>
+__device__ __forceinline__ void linear_epilogue_tile_rowstat(const LinArgs& a, uint32_t tmem, int set, int nacc, int m0, int n0,
+                                                             int warp, int lane, int ntiles) {
+  const int m = m0 + warp * 32 + lane;
+  const uint32_t lane_base = ((uint32_t)(warp * 32) << 16) + set * nacc * NT;
+  const float inv_div = 1.f / a.logit_div;
+  float mx = -INFINITY, sum = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < NT; c0 += 32) {
+    float v[32];
+    tc::tmem_ld32(tmem + lane_base + c0, v);
+    for (int ac = 1; ac < nacc; ++ac) {
+      float w[32];
+      tc::tmem_ld32(tmem + lane_base + ac * NT + c0, w);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += w[i];
+    }
+    if (n0 + c0 >= a.Nout) continue;
+    float cm = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] = (n0 + c0 + i < a.Nout) ? v[i] * inv_div : -INFINITY;
+      cm = fmaxf(cm, v[i]);
+    }
+    const float mn = fmaxf(mx, cm);
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) part += __expf(v[i] - mn);
+    sum = sum * __expf(mx - mn) + part;
+    mx = mn;
+  }
+  if (m < a.M) a.stat_out[(long long)m * ntiles + n0 / NT] = make_float2(mx, sum);
 }
 
 }  // namespace samble

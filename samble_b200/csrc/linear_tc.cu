@@ -232,6 +232,8 @@ static int launch_linear(const LinArgs& a, cudaStream_t st) {
 }
 
 int launch_linear_tma_auto(const LinArgs& a, int nacc, cudaStream_t st);   // linear_tma.cu
+template <int NT>
+int launch_linear_tma(const LinArgs& a, cudaStream_t st);
 
 }  // namespace samble
 
@@ -271,7 +273,7 @@ extern "C" int samble_linear(const float* X, long long ldx, int x_channel_major,
   SAMBLE_REQUIRE(ceil_div(Nout, 64) <= 65535, "samble_linear: Nout too large");
   LinArgs a{X, ldx, W, ldw, W_lo, scale, shift, residual, ldr, out, ldo, M, K, Nout, need_npc ? points_per_cloud : 0,
             lrelu, x_channel_major, out_channel_major, residual_first, residual_channel_major, shift_cloud_stride,
-            nullptr, nullptr, 0, nullptr, nullptr, 1.f, 0};
+            nullptr, nullptr, 0, nullptr, nullptr, 1.f, 0, nullptr};
   cudaStream_t st = (cudaStream_t)stream;
   const int nacc = ceil_div(ceil_div(K, 32), kLinChain);
   SAMBLE_REQUIRE(nacc * 64 <= 512, "samble_linear: K=%d too large (max %d)", K, 8 * kLinChain * 32);
@@ -319,7 +321,7 @@ extern "C" int samble_linear_pool(const float* X, long long ldx, const float* W,
   float* pmax = w.take<float>((size_t)ceil_div(M, 32) * Nout);
   float* psum = w.take<float>((size_t)ceil_div(M, 32) * Nout);
   LinArgs a{X, ldx, W, ldw, W_lo, scale, shift, nullptr, 0, nullptr, 0, M, K, Nout, points_per_cloud,
-            lrelu, 0, 0, 0, 0, shift_cloud_stride, pmax, out_mean ? psum : nullptr, 0, nullptr, nullptr, 1.f, 0};
+            lrelu, 0, 0, 0, 0, shift_cloud_stride, pmax, out_mean ? psum : nullptr, 0, nullptr, nullptr, 1.f, 0, nullptr};
   cudaStream_t st = (cudaStream_t)stream;
   if (int e = launch_linear_tma_auto(a, nacc, st)) return e;
   SAMBLE_PRE(st);
@@ -350,6 +352,95 @@ extern "C" int samble_cloud_matmul(const float* X, long long ldx, const float* W
   const int nacc = ceil_div(ceil_div(K, 32), chain);
   SAMBLE_REQUIRE(nacc * 64 <= 512, "samble_cloud_matmul: K=%d too large (max %d)", K, 8 * 16 * 32);
   LinArgs a{X, ldx, W, ldw, W_lo, nullptr, nullptr, nullptr, 0, out, ldo, M, K, Nout, rows_per_cloud,
-            0, 0, 0, 0, 0, 0, nullptr, nullptr, 1, row_max, row_sum, logit_div, chain};
+            0, 0, 0, 0, 0, 0, nullptr, nullptr, 1, row_max, row_sum, logit_div, chain, nullptr};
   return launch_linear_tma_auto(a, nacc, (cudaStream_t)stream);
 }
+
+// ---- DownSampleToken pass 1 on the same kernel: row statistics of softmax(q [k | k_tok]^T / sqrt(D)) ----
+// The point columns run as a per-cloud product (W[b] = k[b]) with the row-statistics epilogue: one (max, sum) pair per
+// row and 128-key tile.  The finalize kernel merges the pairs in tile order, adds the nb token columns (exact fp32
+// dot products, written out as token_logits) and leaves rowmax / rowsum.
+__global__ void __launch_bounds__(256) ds_rowstats_finalize_kernel(const float2* __restrict__ part, int ntiles,
+                                                                   const float* __restrict__ q, long long ldq,
+                                                                   const float* __restrict__ k_tok, int M, int D, int nb,
+                                                                   float scale, float* __restrict__ rowmax,
+                                                                   float* __restrict__ rowsum, float* __restrict__ token_logits) {
+  extern __shared__ float fsm[];                       // [nb*D] tokens | [8][D] query rows
+  float* s_tok = fsm;
+  float* s_q = fsm + nb * D + (threadIdx.x >> 5) * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < nb * D; i += blockDim.x) s_tok[i] = k_tok[i];
+  const long long m = (long long)blockIdx.x * 8 + warp;
+  if (m < M)
+    for (int c = lane; c < D; c += 32) s_q[c] = q[m * ldq + c];          // coalesced
+  __syncthreads();
+  if (m >= M) return;
+  // merge this row's tile pairs: lanes take tiles lane, lane+32, ...; butterfly over (max, sum) pairs
+  float mx = -INFINITY, sum = 0.f;
+  for (int t = lane; t < ntiles; t += 32) {
+    const float2 p = part[m * ntiles + t];
+    const float mn = fmaxf(mx, p.x);
+    sum = sum * __expf(mx - mn) + p.y * __expf(p.x - mn);
+    mx = mn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(kFull, mx, o), os = __shfl_xor_sync(kFull, sum, o);
+    const float mn = fmaxf(mx, om);
+    sum = (mx == -INFINITY ? 0.f : sum * __expf(mx - mn)) + (om == -INFINITY ? 0.f : os * __expf(om - mn));
+    mx = mn;
+  }
+  // token columns: lane j < nb owns token j; ascending channel order, one accumulator (= the exact FFMA kernel's bits)
+  float lt = -INFINITY;
+  if (lane < nb) {
+    float acc = 0.f;
+    const float* kt = s_tok + lane * D;
+    for (int c = 0; c < D; ++c) acc = fmaf(s_q[c], kt[c], acc);
+    lt = __fdiv_rn(acc, scale);
+    token_logits[m * nb + lane] = lt;
+  }
+  float tmax = lt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(kFull, tmax, o));
+  const float m_new = fmaxf(mx, tmax);
+  float ps = lane < nb ? expf(lt - m_new) : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(kFull, ps, o);
+  if (lane == 0) {
+    rowsum[m] = sum * expf(mx - m_new) + ps;
+    rowmax[m] = m_new;
+  }
+}
+
+extern "C" size_t samble_ds_row_stats_fast_workspace_bytes(int B, int N) {
+  if (B <= 0 || N <= 0) return 0;
+  return align_up((size_t)B * N * ceil_div(N, 128) * sizeof(float2), 256) + 256;
+}
+
+extern "C" int samble_ds_row_stats_fast(const float* q, long long ldq, const float* k, const float* k_lo, long long ldk,
+                                        const float* k_tok, int B, int N, int D, int nb, float* rowmax, float* rowsum,
+                                        float* token_logits, void* ws, size_t ws_bytes, samble_stream_t stream) {
+  SAMBLE_REQUIRE(q && k && k_lo && rowmax && rowsum && ws, "samble_ds_row_stats_fast: null pointer");
+  SAMBLE_REQUIRE(nb == 0 || (k_tok && token_logits), "samble_ds_row_stats_fast: token pointers required when nb > 0");
+  SAMBLE_REQUIRE(B > 0 && N > 0 && N % 128 == 0, "samble_ds_row_stats_fast: N=%d must be a multiple of 128", N);
+  SAMBLE_REQUIRE(D > 0 && D % 4 == 0 && D <= 256, "samble_ds_row_stats_fast: D=%d must be a multiple of 4, <= 256", D);
+  SAMBLE_REQUIRE(nb >= 0 && nb <= 32, "samble_ds_row_stats_fast: nb=%d outside [0,32]", nb);
+  SAMBLE_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldq >= D && ldk >= D && ((uintptr_t)q | (uintptr_t)k | (uintptr_t)k_lo) % 16 == 0,
+                 "samble_ds_row_stats_fast: q/k need 16-byte aligned rows");
+  SAMBLE_REQUIRE(ws_bytes >= samble_ds_row_stats_fast_workspace_bytes(B, N), "samble_ds_row_stats_fast: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w(ws, ws_bytes);
+  const int ntiles = ceil_div(N, 128);
+  float2* part = w.take<float2>((size_t)B * N * ntiles);
+  const float scale = sqrtf((float)D);
+  LinArgs a{q, ldq, k, ldk, k_lo, nullptr, nullptr, nullptr, 0, nullptr, 0, B * N, D, N, N,
+            0, 0, 0, 0, 0, 0, nullptr, nullptr, 1, nullptr, nullptr, scale, 2 /* short chains: sharp logits, see ds_rowstats_tc.cu */,
+            part};
+  if (int e = launch_linear_tma<128>(a, st)) return e;
+  SAMBLE_PRE(st);
+  ds_rowstats_finalize_kernel<<<ceil_div(B * N, 8), 256, (size_t)(nb + 8) * D * sizeof(float), st>>>(
+      part, ntiles, q, ldq, k_tok, B * N, D, nb, scale, rowmax, rowsum, token_logits);
+  SAMBLE_LAUNCHED("ds_rowstats_finalize_kernel");
+  return SAMBLE_OK;
+}
+

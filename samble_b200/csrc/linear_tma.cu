@@ -63,8 +63,8 @@ __device__ __forceinline__ void lt_range(int total, int& t0, int& t1) {
   t1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
 }
 
-// EPI selects the one epilogue compiled into an instantiation (0 direct, 1 smem-staged row-major, 2 pooling): with all
-// three in one function ptxas sized the kernel for their union and spilled.
+// EPI selects the one epilogue compiled into an instantiation (0 direct, 1 smem-staged row-major, 2 pooling, 3 row
+// statistics): with all of them in one function ptxas sized the kernel for their union and spilled.
 template <int NT, int EPI>
 __global__ void __launch_bounds__(kLtThreads, 1)
     linear_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -233,7 +233,9 @@ __global__ void __launch_bounds__(kLtThreads, 1)
       const int m0 = (tile % mtiles) * 128, n0 = (tile / mtiles) * NT;
       tc::mbar_wait(&tfull[set], use & 1);
       tc::tc_fence_after();
-      if (EPI == 2)
+      if (EPI == 3)
+        linear_epilogue_tile_rowstat<NT>(a, tmem, set, nacc, m0, n0, warp, lane, ntiles);
+      else if (EPI == 2)
         linear_epilogue_tile_pool<NT>(a, tmem, set, nacc, m0, n0, warp, lane);
       else if (EPI == 0)
         linear_epilogue_tile<NT>(a, tmem, set, nacc, m0, n0, warp, lane);
@@ -259,8 +261,9 @@ int launch_linear_tma(const LinArgs& a, cudaStream_t st) {
   const int wb = a.w_batched ? a.M / a.npc : 1;
   if (int e = make_tile_map(&mw, a.W, k4, a.ldw, a.Nout, wb, NT)) return e;
   if (int e = make_tile_map(&mwl, a.Wlo, k4, a.ldw, a.Nout, wb, NT)) return e;
-  const int epi = a.pool_max ? 2 : ((a.out_cm || (a.residual && a.res_cm) || !p.staged) ? 0 : 1);
-  auto kern = epi == 2 ? linear_tma_kernel<NT, 2> : (epi == 1 ? linear_tma_kernel<NT, 1> : linear_tma_kernel<NT, 0>);
+  const int epi = a.stat_out ? 3 : (a.pool_max ? 2 : ((a.out_cm || (a.residual && a.res_cm) || !p.staged) ? 0 : 1));
+  auto kern = epi == 3 ? linear_tma_kernel<NT, 3>
+                       : (epi == 2 ? linear_tma_kernel<NT, 2> : (epi == 1 ? linear_tma_kernel<NT, 1> : linear_tma_kernel<NT, 0>));
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
     return check_launch("linear_tma smem attribute");
   const long long total = (long long)ceil_div(a.M, 128) * ceil_div(a.Nout, NT);
@@ -270,6 +273,9 @@ int launch_linear_tma(const LinArgs& a, cudaStream_t st) {
   SAMBLE_LAUNCHED("linear_tma_kernel");
   return SAMBLE_OK;
 }
+
+template int launch_linear_tma<128>(const LinArgs&, cudaStream_t);
+template int launch_linear_tma<64>(const LinArgs&, cudaStream_t);
 
 int launch_linear_tma_auto(const LinArgs& a, int nacc, cudaStream_t st) {
   const bool wide_ok = a.Nout > 64 && nacc * 128 <= 512;

@@ -303,7 +303,7 @@ def linear(x: Tensor, weight: Tensor, *, x_layout: str = "rows", out_layout: str
 
 
 def cloud_matmul(x: Tensor, w: Tensor, *, row_max: Optional[Tensor] = None, row_sum: Optional[Tensor] = None,
-                 logit_div: float = 1.0) -> Tensor:
+                 logit_div: float = 1.0, w_split=None) -> Tensor:
     """Per-cloud products on the tensor cores (3xTF32, samble_cloud_matmul): x (B,R,K), w (B,Nout,K) -> (B,R,Nout) with
     out[b] = x[b] w[b]^T; R a multiple of 128.  With row_max/row_sum (B,R) the result is
     exp(out / logit_div - row_max) / row_sum, i.e. softmax rows whose statistics are already known."""
@@ -315,14 +315,10 @@ def cloud_matmul(x: Tensor, w: Tensor, *, row_max: Optional[Tensor] = None, row_
     if Bw != B or Kw != K:
         raise RuntimeError(f"cloud_matmul: x {tuple(x.shape)} vs w {tuple(w.shape)}")
     if K % 4 != 0:
-        x, w = torch.nn.functional.pad(x, (0, (-K) % 4)), torch.nn.functional.pad(w, (0, (-K) % 4))
+        x = torch.nn.functional.pad(x, (0, (-K) % 4))
     x = x.contiguous()
-    if not w.is_contiguous():       # a (B,K,Nout) tensor viewed as (B,Nout,K): one tiled transpose instead of a strided copy
-        wt = w.transpose(1, 2)
-        w = transpose12(wt) if (wt.stride(2) == 1 and wt.stride(1) >= wt.shape[2]) else w.contiguous()
-    w_lo = torch.empty_like(w)
+    w, w_lo = w_split if w_split is not None else split_operand(w)     # a (B,K,Nout) view is transposed by one tiled kernel
     lib = L.lib()
-    L.check(lib.samble_split_tf32(L.ptr(w), L.ptr(w_lo), w.numel(), L.stream()), "samble_split_tf32")
     out = torch.empty(B, R, Nout, dtype=torch.float32, device=dev)
     if row_max is not None:
         row_max, row_sum = _f32(row_max, "row_max").contiguous(), _f32(row_sum, "row_sum").contiguous()
@@ -396,9 +392,30 @@ def n2p_attend(qkv: Tensor, idx: Tensor, heads: int, residual: Optional[Tensor] 
     return out
 
 
-def ds_row_stats(q: Tensor, k: Tensor, k_tok: Tensor):
+def split_operand(w: Tensor):
+    """(w contiguous, w_lo = w - trunc_tf32(w)) for an ACTIVATION used as the per-cloud weight of cloud_matmul /
+    ds_row_stats (weights proper go through the cached _split_weight).  w: (B,R,K) rows, or its (B,K,R) transpose."""
+    w = _f32(w, "w")
+    if not w.is_contiguous():
+        wt = w.transpose(1, 2)
+        w = transpose12(wt) if (wt.stride(2) == 1 and wt.stride(1) >= wt.shape[2]) else w.contiguous()
+    if w.shape[-1] % 4 != 0:
+        w = torch.nn.functional.pad(w, (0, (-w.shape[-1]) % 4))
+    w_lo = torch.empty_like(w)
+    L.check(L.lib().samble_split_tf32(L.ptr(w), L.ptr(w_lo), w.numel(), L.stream()), "samble_split_tf32")
+    return w, w_lo
+
+
+# Two tensor-core kernels compute the row statistics: ds_rowstats_tc.cu (default: measured 1% faster on the whole step)
+# and the row-statistics epilogue of linear_tma.cu (samble_ds_row_stats_fast; shares k's tf32 split with cloud_matmul).
+# Tests flip this to cross-check one against the other.
+_DS_FAST = False
+
+
+def ds_row_stats(q: Tensor, k: Tensor, k_tok: Tensor, k_split=None):
     """q,k: (B,N,D) point-major views (last stride 1, row stride ld); k_tok (nb,D).
-    -> rowmax (B,N), rowsum (B,N), token_logits (B,N,nb).  models/downsample.py:139-153."""
+    -> rowmax (B,N), rowsum (B,N), token_logits (B,N,nb).  models/downsample.py:139-153.
+    k_split = split_operand(k) lets the caller share k's tf32 split with cloud_matmul."""
     dev = L.need_cuda(q, k, k_tok)
     B, N, D = q.shape
     nb = k_tok.shape[0]
@@ -406,6 +423,14 @@ def ds_row_stats(q: Tensor, k: Tensor, k_tok: Tensor):
     rowmax = torch.empty(B, N, dtype=torch.float32, device=dev)
     rowsum = torch.empty(B, N, dtype=torch.float32, device=dev)
     tok = torch.empty(B, N, nb, dtype=torch.float32, device=dev)
+    if _DS_FAST and N % 128 == 0 and D % 4 == 0 and q.stride(2) == 1 and q.stride(0) == N * q.stride(1):
+        kc, klo = k_split if k_split is not None else split_operand(k)
+        lib = L.lib()
+        ws = L.workspace(lib.samble_ds_row_stats_fast_workspace_bytes(B, N), dev)
+        L.check(lib.samble_ds_row_stats_fast(L.ptr(q), q.stride(1), L.ptr(kc), L.ptr(klo), kc.stride(1), L.ptr(k_tok), B, N, D, nb,
+                                             L.ptr(rowmax), L.ptr(rowsum), L.ptr(tok), L.ptr(ws), ws.numel(), L.stream()),
+                "samble_ds_row_stats_fast")
+        return rowmax, rowsum, tok
     L.check(L.lib().samble_ds_row_stats(L.ptr(q), q.stride(1), L.ptr(k), k.stride(1), L.ptr(k_tok), B, N, D, nb,
                                         L.ptr(rowmax), L.ptr(rowsum), L.ptr(tok), L.stream()), "samble_ds_row_stats")
     return rowmax, rowsum, tok

@@ -72,6 +72,14 @@ def test_ds_row_stats_and_edge_score(B, N, nb, sharp):
     lse = rowmax.cpu().double() + torch.log(rowsum.cpu().double())
     torch.testing.assert_close(lse, lse_ref, atol=2e-4, rtol=1e-5)
     torch.testing.assert_close(tok.cpu().double(), logits[..., N:], atol=1e-4, rtol=1e-5)
+    # the two tensor-core kernels (linear_tma.cu row-statistics epilogue vs ds_rowstats_tc.cu) agree
+    ops._DS_FAST = not ops._DS_FAST
+    try:
+        rm_o, rs_o, tok_o = ops.ds_row_stats(cu(q), cu(k), cu(k_tok))
+    finally:
+        ops._DS_FAST = not ops._DS_FAST
+    assert torch.equal(tok_o, tok)
+    torch.testing.assert_close(rm_o.cpu().double() + torch.log(rs_o.cpu().double()), lse, atol=2e-5, rtol=1e-6)
     for bits in (torch.int64, torch.int32):
         score = ops.ds_edge_score(cu(q), cu(k), rowmax, rowsum, cu(idx.to(bits)))
         torch.testing.assert_close(score.cpu().double(), score_ref, atol=1e-12, rtol=2e-4)
