@@ -351,3 +351,27 @@ def test_stochastic_sample_modes_run_and_respect_bins(mode):
                 assert bool(mask[b, 0, seg, j].all())
                 off += int(k[b, j])
             assert off == idx.shape[-1]
+
+
+def test_host_pipeline_returns_the_graph_results_in_order():
+    """runtime.HostPipeline: pinned host inputs in, pinned host results out, D2H of a step overlapping the next step."""
+    from samble_b200.runtime import GraphedForward, HostPipeline
+
+    cfg, m, _ = _sd(512, seed=4)
+    batches = [synthetic_clouds(2, 512, 20 + i) for i in range(5)]
+    with torch.no_grad():
+        m(cu(batches[0][0]), cu(batches[0][1]))
+        models.freeze_boundaries(m)
+        want = [m(cu(x), cu(c)).cpu() for x, c in batches]
+        g = GraphedForward(m, cu(batches[0][0]), cu(batches[0][1]))
+        pipe = HostPipeline(g)
+        got = []
+        for x, c in batches:
+            host, done = pipe.submit(x.pin_memory(), c.pin_memory())
+            pipe.wait_previous()
+            done.synchronize()                      # a consumer reads a result only after its event
+            got.append(host.clone())
+        pipe.wait_all()
+        torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
