@@ -289,7 +289,7 @@ class DownSampleToken(nn.Module):
         v_tok = torch.matmul(tok, self.v_conv.weight.view(C, C).t())
 
         idx = ops.knn_indices(x, self.K, ordered=False)                                       # neighbor_mask's kNN (:301)
-        k_split = ops.split_operand(k) if self.M % 128 == 0 else None          # k's tf32 split, for the selected rows
+        k_split = ops.split_operand(k) if (N % 128 == 0 or self.M % 128 == 0) else None   # shared by pass 1 and the M rows
         rowmax, rowsum, tok_logits = ops.ds_row_stats(q, k, k_tok, k_split=k_split)
         score = ops.ds_edge_score(q, k, rowmax, rowsum, idx)                   # (B,N)
         self.attention_point_score = score.view(B, 1, N)

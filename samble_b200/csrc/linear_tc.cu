@@ -360,54 +360,97 @@ extern "C" int samble_cloud_matmul(const float* X, long long ldx, const float* W
 // The point columns run as a per-cloud product (W[b] = k[b]) with the row-statistics epilogue: one (max, sum) pair per
 // row and 128-key tile.  The finalize kernel merges the pairs in tile order, adds the nb token columns (exact fp32
 // dot products, written out as token_logits) and leaves rowmax / rowsum.
+// One warp finalises 8 rows.  Phase 1 merges each row's (max, sum) tile pairs (lanes across tiles, butterfly).  Phase 2
+// runs the nb token dot products with lane = (row, token): every lane owns one sequential 128-term FMA chain (ascending
+// channels, one accumulator = the exact FFMA kernel's bits) fed by 16-byte shared-memory reads -- the first version
+// used 4 active lanes and scalar reads per row and saturated the shared-memory pipe (85 us; ncu: mio_throttle 25).
+constexpr int kFinRows = 8;          // rows per warp
+constexpr int kFinPad = 4;           // floats of padding per staged row (16-byte aligned, conflict-free)
+
 __global__ void __launch_bounds__(256) ds_rowstats_finalize_kernel(const float2* __restrict__ part, int ntiles,
                                                                    const float* __restrict__ q, long long ldq,
                                                                    const float* __restrict__ k_tok, int M, int D, int nb,
                                                                    float scale, float* __restrict__ rowmax,
                                                                    float* __restrict__ rowsum, float* __restrict__ token_logits) {
-  extern __shared__ float fsm[];                       // [nb*D] tokens | [8][D] query rows
+  extern __shared__ __align__(16) float fsm[];         // [nb][D+pad] tokens | [8 warps][8 rows][D+pad] query rows
+  const int ld = D + kFinPad;
   float* s_tok = fsm;
-  float* s_q = fsm + nb * D + (threadIdx.x >> 5) * D;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < nb * D; i += blockDim.x) s_tok[i] = k_tok[i];
-  const long long m = (long long)blockIdx.x * 8 + warp;
-  if (m < M)
-    for (int c = lane; c < D; c += 32) s_q[c] = q[m * ldq + c];          // coalesced
+  float* s_q = fsm + (size_t)nb * ld + (size_t)warp * kFinRows * ld;
+  for (int i = threadIdx.x; i < nb * D; i += blockDim.x) s_tok[(i / D) * ld + (i % D)] = k_tok[i];
+  const long long m_base = ((long long)blockIdx.x * 8 + warp) * kFinRows;
+  for (int r = 0; r < kFinRows; ++r) {
+    const long long m = m_base + r;
+    if (m < M)
+      for (int c = lane; c < D; c += 32) s_q[r * ld + c] = q[m * ldq + c];          // coalesced
+  }
   __syncthreads();
-  if (m >= M) return;
-  // merge this row's tile pairs: lanes take tiles lane, lane+32, ...; butterfly over (max, sum) pairs
-  float mx = -INFINITY, sum = 0.f;
-  for (int t = lane; t < ntiles; t += 32) {
-    const float2 p = part[m * ntiles + t];
-    const float mn = fmaxf(mx, p.x);
-    sum = sum * __expf(mx - mn) + p.y * __expf(p.x - mn);
-    mx = mn;
-  }
+  if (m_base >= M) return;
+  // ---- phase 1: merged point-column statistics of the 8 rows (every lane ends up with all eight pairs) ----
+  float mxr[kFinRows], sumr[kFinRows];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float om = __shfl_xor_sync(kFull, mx, o), os = __shfl_xor_sync(kFull, sum, o);
-    const float mn = fmaxf(mx, om);
-    sum = (mx == -INFINITY ? 0.f : sum * __expf(mx - mn)) + (om == -INFINITY ? 0.f : os * __expf(om - mn));
-    mx = mn;
-  }
-  // token columns: lane j < nb owns token j; ascending channel order, one accumulator (= the exact FFMA kernel's bits)
-  float lt = -INFINITY;
-  if (lane < nb) {
-    float acc = 0.f;
-    const float* kt = s_tok + lane * D;
-    for (int c = 0; c < D; ++c) acc = fmaf(s_q[c], kt[c], acc);
-    lt = __fdiv_rn(acc, scale);
-    token_logits[m * nb + lane] = lt;
-  }
-  float tmax = lt;
+  for (int r = 0; r < kFinRows; ++r) {
+    const long long m = m_base + r;
+    float mx = -INFINITY, sum = 0.f;
+    if (m < M) {
+      for (int t = lane; t < ntiles; t += 32) {
+        const float2 p = part[m * ntiles + t];
+        const float mn = fmaxf(mx, p.x);
+        sum = sum * __expf(mx - mn) + p.y * __expf(p.x - mn);
+        mx = mn;
+      }
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(kFull, tmax, o));
-  const float m_new = fmaxf(mx, tmax);
-  float ps = lane < nb ? expf(lt - m_new) : 0.f;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(kFull, mx, o), os = __shfl_xor_sync(kFull, sum, o);
+      const float mn = fmaxf(mx, om);
+      sum = (mx == -INFINITY ? 0.f : sum * __expf(mx - mn)) + (om == -INFINITY ? 0.f : os * __expf(om - mn));
+      mx = mn;
+    }
+    mxr[r] = mx, sumr[r] = sum;
+  }
+  // ---- phase 2: lane = (row r, token j of the current group of 4) ----
+  const int r = lane >> 2, jj = lane & 3;
+  const long long m = m_base + r;
+  float my_mx = mxr[0], my_sum = sumr[0];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(kFull, ps, o);
-  if (lane == 0) {
-    rowsum[m] = sum * expf(mx - m_new) + ps;
+  for (int i = 1; i < kFinRows; ++i)
+    if (r == i) my_mx = mxr[i], my_sum = sumr[i];
+  float lt[8];                                        // up to 8 groups of 4 tokens (nb <= 32)
+  float tmax = -INFINITY;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    lt[g] = -INFINITY;
+    const int j = g * 4 + jj;
+    if (g * 4 < nb) {                                 // warp-uniform
+      if (j < nb && m < M) {
+        const float4* qr = reinterpret_cast<const float4*>(s_q + r * ld);
+        const float4* kt = reinterpret_cast<const float4*>(s_tok + j * ld);
+        float acc = 0.f;
+        for (int c4 = 0; c4 < D / 4; ++c4) {
+          const float4 a = qr[c4], b = kt[c4];
+          acc = fmaf(a.x, b.x, acc);
+          acc = fmaf(a.y, b.y, acc);
+          acc = fmaf(a.z, b.z, acc);
+          acc = fmaf(a.w, b.w, acc);
+        }
+        lt[g] = __fdiv_rn(acc, scale);
+        token_logits[m * nb + j] = lt[g];
+      }
+      tmax = fmaxf(tmax, lt[g]);
+    }
+  }
+  tmax = fmaxf(tmax, __shfl_xor_sync(kFull, tmax, 1));        // over the row's 4 lanes
+  tmax = fmaxf(tmax, __shfl_xor_sync(kFull, tmax, 2));
+  const float m_new = fmaxf(my_mx, tmax);
+  float ps = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    if (g * 4 < nb && lt[g] != -INFINITY) ps += expf(lt[g] - m_new);
+  ps += __shfl_xor_sync(kFull, ps, 1);
+  ps += __shfl_xor_sync(kFull, ps, 2);
+  if (jj == 0 && m < M) {
+    rowsum[m] = (my_mx == -INFINITY ? 0.f : my_sum * expf(my_mx - m_new)) + ps;
     rowmax[m] = m_new;
   }
 }
@@ -438,8 +481,11 @@ extern "C" int samble_ds_row_stats_fast(const float* q, long long ldq, const flo
             part};
   if (int e = launch_linear_tma<128>(a, st)) return e;
   SAMBLE_PRE(st);
-  ds_rowstats_finalize_kernel<<<ceil_div(B * N, 8), 256, (size_t)(nb + 8) * D * sizeof(float), st>>>(
-      part, ntiles, q, ldq, k_tok, B * N, D, nb, scale, rowmax, rowsum, token_logits);
+  const size_t fsmem = (size_t)(nb + 8 * kFinRows) * (D + kFinPad) * sizeof(float);
+  if (cudaFuncSetAttribute(ds_rowstats_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem) != cudaSuccess)
+    return check_launch("ds_rowstats_finalize smem attribute");
+  ds_rowstats_finalize_kernel<<<ceil_div(B * N, 8 * kFinRows), 256, fsmem, st>>>(part, ntiles, q, ldq, k_tok, B * N, D, nb, scale,
+                                                                                  rowmax, rowsum, token_logits);
   SAMBLE_LAUNCHED("ds_rowstats_finalize_kernel");
   return SAMBLE_OK;
 }

@@ -406,10 +406,10 @@ def split_operand(w: Tensor):
     return w, w_lo
 
 
-# Two tensor-core kernels compute the row statistics: ds_rowstats_tc.cu (default: measured 1% faster on the whole step)
-# and the row-statistics epilogue of linear_tma.cu (samble_ds_row_stats_fast; shares k's tf32 split with cloud_matmul).
+# Two tensor-core kernels compute the row statistics: the row-statistics epilogue of linear_tma.cu (default:
+# samble_ds_row_stats_fast; TMA-fed, shares k's tf32 split with cloud_matmul) and ds_rowstats_tc.cu (cp.async loaders).
 # Tests flip this to cross-check one against the other.
-_DS_FAST = False
+_DS_FAST = True
 
 
 def ds_row_stats(q: Tensor, k: Tensor, k_tok: Tensor, k_split=None):
