@@ -466,6 +466,7 @@ __global__ void __launch_bounds__(256, Cfg::MQ == 4 ? 2 : 1)
   const int b = blockIdx.y, q0 = blockIdx.x * Cfg::TQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (row_flags) {   // repair mode: only tiles holding a row the tensor-core path could not finish
+    if (!row_flags[(long long)gridDim.y * Nq]) return;          // nothing flagged anywhere: the usual case
     int any = 0;
     for (int r = threadIdx.x; r < Cfg::TQ; r += blockDim.x) any |= (q0 + r < Nq) ? row_flags[(long long)b * Nq + q0 + r] : 0;
     if (!__syncthreads_or(any)) return;
@@ -606,7 +607,7 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   float* bnorm = self ? anorm : w.take<float>((size_t)B * Nr);
   SAMBLE_PRE(st);
   float* thr = w.take<float>((size_t)B * Nq);
-  int* row_flags = w.take<int>((size_t)B * Nq);
+  int* row_flags = w.take<int>((size_t)B * Nq + 1);          // + one "any row flagged" word
   unsigned* bbmax = w.take<unsigned>((size_t)B);
   uint32_t* cand = w.take<uint32_t>((size_t)B * Nq * 128);
   int* cand_cnt = w.take<int>((size_t)B * Nq);

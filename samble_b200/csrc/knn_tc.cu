@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   const size_t rowi = (size_t)b * Nq + q;
   const int cnt = cnt_in[rowi];
   if (cnt >= kTcCap) {                                  // saturated list: hand the row to the exact kernel
-    if (lane == 0) row_flags[rowi] = 1;
+    if (lane == 0) row_flags[rowi] = 1, row_flags[(size_t)gridDim.y * Nq] = 1;   // (last slot: "some row needs repair")
     return;
   }
   const float aa = anorm[rowi];
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict
   const size_t rowi = (size_t)b * Nq + q;
   const int cnt = cnt_in[rowi];
   if (cnt >= kTcCap) {                                  // saturated list: hand the row to the exact kernel
-    if (lane == 0) row_flags[rowi] = 1;
+    if (lane == 0) row_flags[rowi] = 1, row_flags[(size_t)gridDim.y * Nq] = 1;   // (last slot: "some row needs repair")
     return;
   }
   const float aa = anorm[rowi];
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict
   const int need = k - n_in;
   if (need <= 0) return;                                // (n_in <= k always: an "in" entry has at most k-1 rivals)
   if (n_amb < need) {                                   // cannot happen while the margin holds; stay safe
-    if (lane == 0) row_flags[rowi] = 1;
+    if (lane == 0) row_flags[rowi] = 1, row_flags[(size_t)gridDim.y * Nq] = 1;   // (last slot: "some row needs repair")
     return;
   }
   __syncwarp();
