@@ -187,6 +187,68 @@ __global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restr
   }
 }
 
+// Point-major input (the blocks' own activations): no transpose to do, so every thread moves one 16-byte chunk per
+// 32-channel block -- one LDG.128, two STG.128 (fp32 copy and tf32-rounded copy) -- and only the squared norms go through
+// shared memory, to be summed per point in channel order exactly as above.
+__global__ void __launch_bounds__(256) knn_prep_feat_pm_kernel(const float* __restrict__ x, long long sb, long long sn, int N,
+                                                               int C, int Cp, const float* __restrict__ mean,
+                                                               const float* __restrict__ stdv, float* __restrict__ out,
+                                                               float* __restrict__ norms, unsigned* __restrict__ maxnorm,
+                                                               float* __restrict__ ext, float* __restrict__ out_tf32) {
+  __shared__ float tile[32][33];                        // [channel of the block][point]
+  const int b = blockIdx.y, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (n0 >= N) {
+    if (ty == 0) knn_store_ext(ext, b, N, n0 + tx, -1e30f);
+    return;
+  }
+  const float sigma = cloud_sigma(stdv + b * C, C);
+  const int row = threadIdx.x >> 3, f4 = threadIdx.x & 7;
+  const int n = n0 + row;
+  float nn = 0.f;
+  for (int c0 = 0; c0 < Cp; c0 += 32) {
+    const int c = c0 + f4 * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N && c < C) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + b * sb + n * sn + c));
+      const float4 mv = __ldg(reinterpret_cast<const float4*>(mean + b * C + c));
+      v.x = __fdiv_rn(__fsub_rn(xv.x, mv.x), sigma);
+      v.y = __fdiv_rn(__fsub_rn(xv.y, mv.y), sigma);
+      v.z = __fdiv_rn(__fsub_rn(xv.z, mv.z), sigma);
+      v.w = __fdiv_rn(__fsub_rn(xv.w, mv.w), sigma);
+    }
+    if (n < N && c < Cp) {
+      const long long o = ((long long)b * N + n) * Cp + c;
+      *reinterpret_cast<float4*>(out + o) = v;
+      if (out_tf32) {
+        uint4 r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.x) : "f"(v.x));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.y) : "f"(v.y));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.z) : "f"(v.z));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.w) : "f"(v.w));
+        *reinterpret_cast<uint4*>(out_tf32 + o) = r;
+      }
+    }
+    tile[f4 * 4 + 0][row] = v.x;
+    tile[f4 * 4 + 1][row] = v.y;
+    tile[f4 * 4 + 2][row] = v.z;
+    tile[f4 * 4 + 3][row] = v.w;
+    __syncthreads();
+    if (ty == 0) {
+      const int cmax = min(32, Cp - c0);
+      for (int cc = 0; cc < cmax; ++cc) nn = __fadd_rn(nn, __fmul_rn(tile[cc][tx], tile[cc][tx]));
+    }
+    __syncthreads();
+  }
+  if (ty == 0) {
+    if (n0 + tx < N) norms[(long long)b * N + n0 + tx] = nn;
+    if (ext) knn_store_ext(ext, b, N, n0 + tx, n0 + tx < N ? -0.5f * nn : -1e30f);
+    if (maxnorm) {
+      const unsigned m = __reduce_max_sync(kFull, n0 + tx < N ? __float_as_uint(nn) : 0u);
+      if (tx == 0) atomicMax(maxnorm + b, m);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: xyz kNN.  One warp per query (QW queries per warp in flight), lanes across candidates
 // staged in shared memory; the running k-set lives one entry per lane (LaneTopK).
@@ -568,6 +630,16 @@ static KnnPlan knn_plan(int B, int Nq, int Nr, int C) {
   return p;
 }
 
+static void launch_prep_feat(dim3 grid, cudaStream_t st, const float* x, long long sb, long long sn, long long sc, int N, int C,
+                             int Cp, const float* mean, const float* stdv, float* out, float* norms, unsigned* maxnorm,
+                             float* ext, float* out_tf32) {
+  const bool pm = sc == 1 && C % 4 == 0 && sn % 4 == 0 && sb % 4 == 0 && (uintptr_t)x % 16 == 0;
+  if (pm)
+    knn_prep_feat_pm_kernel<<<grid, 256, 0, st>>>(x, sb, sn, N, C, Cp, mean, stdv, out, norms, maxnorm, ext, out_tf32);
+  else
+    knn_prep_feat_kernel<<<grid, 256, 0, st>>>(x, sb, sn, sc, N, C, Cp, mean, stdv, out, norms, maxnorm, ext, out_tf32);
+}
+
 template <class I>
 static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_sc, const float* b, long long b_sb,
                     long long b_sn, long long b_sc, int B, int Nq, int Nr, int C, int k, I* idx_out, float* dist_out,
@@ -623,15 +695,13 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   SAMBLE_PRE(st);
   // the candidate-side launch also covers the padding rows of the last 128-candidate tile (norm slice only)
   const bool a_is_cand = use_tc && self;
-  knn_prep_feat_kernel<<<dim3(ceil_div(a_is_cand ? (int)align_up(Nq, 128) : Nq, 32), B), 256, 0, st>>>(
-      a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv, an, anorm, a_is_cand ? bbmax : nullptr, a_is_cand ? bext : nullptr,
-      use_tc ? an_r : nullptr);
+  launch_prep_feat(dim3(ceil_div(a_is_cand ? (int)align_up(Nq, 128) : Nq, 32), B), st, a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv,
+                   an, anorm, a_is_cand ? bbmax : nullptr, a_is_cand ? bext : nullptr, use_tc ? an_r : nullptr);
   SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   if (!self) {
     SAMBLE_PRE(st);
-    knn_prep_feat_kernel<<<dim3(ceil_div(use_tc ? (int)align_up(Nr, 128) : Nr, 32), B), 256, 0, st>>>(
-        b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn, bnorm, use_tc ? bbmax : nullptr, use_tc ? bext : nullptr,
-        use_tc ? bn_r : nullptr);
+    launch_prep_feat(dim3(ceil_div(use_tc ? (int)align_up(Nr, 128) : Nr, 32), B), st, b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn,
+                     bnorm, use_tc ? bbmax : nullptr, use_tc ? bext : nullptr, use_tc ? bn_r : nullptr);
     SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   }
   if (use_tc) {
