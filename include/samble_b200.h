@@ -151,7 +151,15 @@ int samble_linear(const float* X, long long ldx, int x_channel_major, const floa
  * rows_per_cloud must be a multiple of 128. */
 int samble_cloud_matmul(const float* X, long long ldx, const float* W, const float* W_lo, long long ldw, int M, int K, int Nout,
                         int rows_per_cloud, const float* row_max, const float* row_sum, float logit_div,
-                        float* out, long long ldo, samble_stream_t stream);
+                        const float* residual, long long ldr, float* out, long long ldo, samble_stream_t stream);
+/* residual (M x Nout, row pitch ldr) or NULL is added to the result (after the softmax transform, if any).
+ *
+ * samble_ds_select_rows gathers, for the M selected points idx (B,M) int64 of each cloud, what those two products need:
+ * q_sel (B,M,D) = q rows, m_sel / s_sel (B,M) = their softmax statistics, and tok_mix (B,M,C) = the nb token columns'
+ * share of the output, sum_t softmax(row)[N+t] * v_tok[t] (v_tok: (nb,C)), which the second product takes as residual. */
+int samble_ds_select_rows(const float* q, long long ldq, const float* rowmax, const float* rowsum, const float* token_logits,
+                          const float* v_tok, const long long* idx, int B, int N, int M, int D, int nb, int C,
+                          float* q_sel, float* m_sel, float* s_sel, float* tok_mix, samble_stream_t stream);
 
 size_t samble_linear_pool_workspace_bytes(int M, int Nout);
 int samble_linear_pool(const float* X, long long ldx, const float* W, const float* W_lo, long long ldw,

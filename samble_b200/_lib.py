@@ -41,7 +41,8 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_split_tf32": (_i, (_p, _p, _ll, _p)),
     "samble_ds_row_stats_fast_workspace_bytes": (_sz, (_i, _i)),
     "samble_ds_row_stats_fast": (_i, (_p, _ll, _p, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p)),
-    "samble_cloud_matmul": (_i, (_p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p, _p, C.c_float, _p, _ll, _p)),
+    "samble_cloud_matmul": (_i, (_p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p, _p, C.c_float, _p, _ll, _p, _ll, _p)),
+    "samble_ds_select_rows": (_i, (_p, _ll, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p)),
     "samble_linear_pool_workspace_bytes": (_sz, (_i, _i)),
     "samble_linear_pool": (_i, (_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p)),
     "samble_linear": (_i, (_p, _ll, _i, _p, _p, _ll, _p, _p, _ll, _i, _p, _ll, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p)),

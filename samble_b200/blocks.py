@@ -311,17 +311,14 @@ class DownSampleToken(nn.Module):
         # row are already known (pass 1), so the rows are formed directly in the GEMM epilogue and applied to V by a
         # second per-cloud GEMM (tcgen05, 3xTF32); the nb token columns are a (B,M,nb) side computation.
         sel = s["idx"]
-        q_sel = torch.gather(q, 1, sel.unsqueeze(-1).expand(-1, -1, D))        # (B,M,D)
         scale = math.sqrt(D)
-        m_sel, s_sel = torch.gather(rowmax, 1, sel), torch.gather(rowsum, 1, sel)
-        l_tok = torch.gather(tok_logits, 1, sel.unsqueeze(-1).expand(-1, -1, nb))                 # already / scale
-        p_tok = torch.exp(l_tok - m_sel.unsqueeze(-1)) / s_sel.unsqueeze(-1)
+        q_sel, m_sel, s_sel, tok_mix = ops.ds_select_rows(q, rowmax, rowsum, tok_logits, v_tok, sel)
         if self.M % 128 == 0:
             att = ops.cloud_matmul(q_sel, k, row_max=m_sel, row_sum=s_sel, logit_div=scale, w_split=k_split)     # (B,M,N)
-            x_ds = ops.cloud_matmul(att, v.transpose(1, 2)) + torch.matmul(p_tok, v_tok)           # (B,M,C)
+            x_ds = ops.cloud_matmul(att, v.transpose(1, 2), residual=tok_mix)                     # (B,M,C)
         else:
             att = torch.exp(torch.matmul(q_sel, k.transpose(1, 2)) / scale - m_sel.unsqueeze(-1)) / s_sel.unsqueeze(-1)
-            x_ds = torch.matmul(att, v) + torch.matmul(p_tok, v_tok)
+            x_ds = torch.matmul(att, v) + tok_mix
         x_ds = x_ds.transpose(1, 2)
 
         self.idx = index_down

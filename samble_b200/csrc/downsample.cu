@@ -266,3 +266,51 @@ extern "C" int samble_ds_edge_score(const float* q, long long ldq, const float* 
   SAMBLE_LAUNCHED("ds_edge_finalize_kernel");
   return SAMBLE_OK;
 }
+
+// ---- the M selected rows (models/downsample.py:242-252): one pass gathers what the two per-cloud GEMMs need ----
+// warp per selected row: q row -> q_sel; its softmax statistics -> m_sel / s_sel; and the nb token columns' share of
+// the output, tok_mix = sum_t softmax(row)[N + t] * v_tok[t], which the second GEMM takes as its residual.
+__global__ void __launch_bounds__(256) ds_select_rows_kernel(const float* __restrict__ q, long long ldq,
+                                                             const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                                                             const float* __restrict__ token_logits,
+                                                             const float* __restrict__ v_tok, const long long* __restrict__ idx,
+                                                             int N, int M, int D, int nb, int C, float* __restrict__ q_sel,
+                                                             float* __restrict__ m_sel, float* __restrict__ s_sel,
+                                                             float* __restrict__ tok_mix) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, i = blockIdx.x * 8 + warp;
+  if (i >= M) return;
+  const long long o = (long long)b * M + i;
+  const long long src = (long long)b * N + idx[o];
+  for (int c = lane * 4; c < D; c += 128)
+    *reinterpret_cast<float4*>(q_sel + o * D + c) = __ldg(reinterpret_cast<const float4*>(q + src * ldq + c));
+  const float mx = rowmax[src], sm = rowsum[src];
+  if (lane == 0) m_sel[o] = mx, s_sel[o] = sm;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < nb; ++t) {
+      const float p = __fdiv_rn(expf(token_logits[src * nb + t] - mx), sm);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(v_tok + (long long)t * C + c));
+      acc.x = fmaf(p, v.x, acc.x), acc.y = fmaf(p, v.y, acc.y), acc.z = fmaf(p, v.z, acc.z), acc.w = fmaf(p, v.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(tok_mix + o * C + c) = acc;
+  }
+}
+
+extern "C" int samble_ds_select_rows(const float* q, long long ldq, const float* rowmax, const float* rowsum,
+                                     const float* token_logits, const float* v_tok, const long long* idx, int B, int N, int M,
+                                     int D, int nb, int C, float* q_sel, float* m_sel, float* s_sel, float* tok_mix,
+                                     samble_stream_t stream) {
+  SAMBLE_REQUIRE(q && rowmax && rowsum && idx && q_sel && m_sel && s_sel && tok_mix, "samble_ds_select_rows: null pointer");
+  SAMBLE_REQUIRE(nb == 0 || (token_logits && v_tok), "samble_ds_select_rows: token pointers required when nb > 0");
+  SAMBLE_REQUIRE(B > 0 && N > 0 && M > 0 && B <= 65535, "samble_ds_select_rows: bad shape");
+  SAMBLE_REQUIRE(D % 4 == 0 && C % 4 == 0 && ldq % 4 == 0 && ((uintptr_t)q | (uintptr_t)q_sel | (uintptr_t)tok_mix | (uintptr_t)v_tok) % 16 == 0,
+                 "samble_ds_select_rows: 16-byte aligned rows, D and C multiples of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAMBLE_PRE(st);
+  ds_select_rows_kernel<<<dim3(ceil_div(M, 8), B), 256, 0, st>>>(q, ldq, rowmax, rowsum, token_logits, v_tok, idx, N, M, D, nb, C,
+                                                                 q_sel, m_sel, s_sel, tok_mix);
+  SAMBLE_LAUNCHED("ds_select_rows_kernel");
+  return SAMBLE_OK;
+}
+

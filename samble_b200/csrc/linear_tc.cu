@@ -334,7 +334,7 @@ extern "C" int samble_linear_pool(const float* X, long long ldx, const float* W,
 // ---- per-cloud products: out[b] = X[b] W[b]^T, optionally turned into softmax rows with known statistics ----
 extern "C" int samble_cloud_matmul(const float* X, long long ldx, const float* W, const float* W_lo, long long ldw, int M, int K,
                                    int Nout, int rows_per_cloud, const float* row_max, const float* row_sum, float logit_div,
-                                   float* out, long long ldo, samble_stream_t stream) {
+                                   const float* residual, long long ldr, float* out, long long ldo, samble_stream_t stream) {
   SAMBLE_REQUIRE(X && W && W_lo && out, "samble_cloud_matmul: null pointer");
   SAMBLE_REQUIRE((row_max == nullptr) == (row_sum == nullptr), "samble_cloud_matmul: row_max and row_sum come together");
   SAMBLE_REQUIRE(ldw % 4 == 0 && ldw >= ((K + 3) / 4) * 4 && ((uintptr_t)W | (uintptr_t)W_lo) % 16 == 0,
@@ -351,7 +351,8 @@ extern "C" int samble_cloud_matmul(const float* X, long long ldx, const float* W
   const int chain = K > 1024 ? 16 : kLinChain;
   const int nacc = ceil_div(ceil_div(K, 32), chain);
   SAMBLE_REQUIRE(nacc * 64 <= 512, "samble_cloud_matmul: K=%d too large (max %d)", K, 8 * 16 * 32);
-  LinArgs a{X, ldx, W, ldw, W_lo, nullptr, nullptr, nullptr, 0, out, ldo, M, K, Nout, rows_per_cloud,
+  SAMBLE_REQUIRE(!residual || ldr >= Nout, "samble_cloud_matmul: ldr < Nout");
+  LinArgs a{X, ldx, W, ldw, W_lo, nullptr, nullptr, residual, ldr, out, ldo, M, K, Nout, rows_per_cloud,
             0, 0, 0, 0, 0, 0, nullptr, nullptr, 1, row_max, row_sum, logit_div, chain, nullptr};
   return launch_linear_tma_auto(a, nacc, (cudaStream_t)stream);
 }

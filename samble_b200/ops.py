@@ -302,8 +302,25 @@ def linear(x: Tensor, weight: Tensor, *, x_layout: str = "rows", out_layout: str
     return out
 
 
+def ds_select_rows(q: Tensor, rowmax: Tensor, rowsum: Tensor, tok_logits: Tensor, v_tok: Tensor, idx: Tensor):
+    """For the selected points idx (B,M) int64: q_sel (B,M,D), m_sel, s_sel (B,M) and tok_mix (B,M,C) = the token
+    columns' share softmax(row)[N:] @ v_tok of the block's output (samble_ds_select_rows)."""
+    dev = L.need_cuda(q, rowmax, rowsum, tok_logits, v_tok, idx)
+    B, N, D = q.shape
+    M, nb, Cc = idx.shape[1], tok_logits.shape[-1], v_tok.shape[-1]
+    v_tok, idx = _f32(v_tok, "v_tok").contiguous(), idx.contiguous()
+    q_sel = torch.empty(B, M, D, dtype=torch.float32, device=dev)
+    m_sel = torch.empty(B, M, dtype=torch.float32, device=dev)
+    s_sel = torch.empty(B, M, dtype=torch.float32, device=dev)
+    tok_mix = torch.empty(B, M, Cc, dtype=torch.float32, device=dev)
+    L.check(L.lib().samble_ds_select_rows(L.ptr(q), q.stride(1), L.ptr(rowmax), L.ptr(rowsum), L.ptr(tok_logits), L.ptr(v_tok),
+                                          L.ptr(idx), B, N, M, D, nb, Cc, L.ptr(q_sel), L.ptr(m_sel), L.ptr(s_sel),
+                                          L.ptr(tok_mix), L.stream()), "samble_ds_select_rows")
+    return q_sel, m_sel, s_sel, tok_mix
+
+
 def cloud_matmul(x: Tensor, w: Tensor, *, row_max: Optional[Tensor] = None, row_sum: Optional[Tensor] = None,
-                 logit_div: float = 1.0, w_split=None) -> Tensor:
+                 logit_div: float = 1.0, w_split=None, residual: Optional[Tensor] = None) -> Tensor:
     """Per-cloud products on the tensor cores (3xTF32, samble_cloud_matmul): x (B,R,K), w (B,Nout,K) -> (B,R,Nout) with
     out[b] = x[b] w[b]^T; R a multiple of 128.  With row_max/row_sum (B,R) the result is
     exp(out / logit_div - row_max) / row_sum, i.e. softmax rows whose statistics are already known."""
@@ -322,8 +339,13 @@ def cloud_matmul(x: Tensor, w: Tensor, *, row_max: Optional[Tensor] = None, row_
     out = torch.empty(B, R, Nout, dtype=torch.float32, device=dev)
     if row_max is not None:
         row_max, row_sum = _f32(row_max, "row_max").contiguous(), _f32(row_sum, "row_sum").contiguous()
+    if residual is not None:
+        residual = _f32(residual, "residual").contiguous()
+        if tuple(residual.shape) != (B, R, Nout):
+            raise RuntimeError(f"cloud_matmul: residual {tuple(residual.shape)} != {(B, R, Nout)}")
     L.check(lib.samble_cloud_matmul(L.ptr(x), x.stride(1), L.ptr(w), L.ptr(w_lo), w.stride(1), B * R, K, Nout, R, L.ptr(row_max),
-                                    L.ptr(row_sum), float(logit_div), L.ptr(out), Nout, L.stream()), "samble_cloud_matmul")
+                                    L.ptr(row_sum), float(logit_div), L.ptr(residual), Nout, L.ptr(out), Nout, L.stream()),
+            "samble_cloud_matmul")
     return out
 
 
