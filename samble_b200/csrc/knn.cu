@@ -49,15 +49,17 @@ __global__ void __launch_bounds__(256) knn_stats_kernel(const float* __restrict_
 // Point-major input (unit channel stride): lane = channel, so a warp reads 128 contiguous bytes of one point; the 16
 // warps of the CTA take points w, w+16, ... and their fp64 partial sums are combined in warp order (deterministic).
 __global__ void __launch_bounds__(512) knn_stats_pm_kernel(const float* __restrict__ a, long long sb, long long sn, int N,
-                                                           int C, float* __restrict__ mean, float* __restrict__ stdv) {
+                                                           int C, double* __restrict__ part) {
   __shared__ double ps[16][32], pq[16][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 32 + lane, b = blockIdx.y;
+  const int c = blockIdx.x * 32 + lane, b = blockIdx.y, z = blockIdx.z, Z = gridDim.z;
   const bool live = c < C;
   const float* p = a + b * sb + (live ? c : 0);
+  // this CTA's slice of the points: [n_lo, n_hi)
+  const int per = (N + Z - 1) / Z, n_lo = z * per, n_hi = min(N, n_lo + per);
   double sa[4] = {0.0, 0.0, 0.0, 0.0}, qa[4] = {0.0, 0.0, 0.0, 0.0};
-  int n = warp;
-  for (; n + 48 < N; n += 64) {
+  int n = n_lo + warp;
+  for (; n + 48 < n_hi; n += 64) {
     float v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = p[(long long)(n + 16 * u) * sn];
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(512) knn_stats_pm_kernel(const float* __restri
       qa[u] += (double)v[u] * (double)v[u];
     }
   }
-  for (; n < N; n += 16) {
+  for (; n < n_hi; n += 16) {
     const double v = (double)p[(long long)n * sn];
     sa[0] += v;
     qa[0] += v * v;
@@ -81,11 +83,25 @@ __global__ void __launch_bounds__(512) knn_stats_pm_kernel(const float* __restri
       s += ps[w][lane];
       s2 += pq[w][lane];
     }
-    const double m = s / N;
-    const double var = (s2 - s * m) / (double)(N - 1);
-    mean[b * C + c] = (float)m;
-    stdv[b * C + c] = (float)sqrt(var > 0.0 ? var : 0.0);
+    double* o = part + (((long long)b * Z + z) * C + c) * 2;
+    o[0] = s, o[1] = s2;
   }
+}
+
+// slices combined in slice order (deterministic)
+__global__ void knn_stats_pm_combine_kernel(const double* __restrict__ part, int Z, int N, int C, float* __restrict__ mean,
+                                            float* __restrict__ stdv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (c >= C) return;
+  double s = 0.0, s2 = 0.0;
+  for (int z = 0; z < Z; ++z) {
+    const double* o = part + (((long long)b * Z + z) * C + c) * 2;
+    s += o[0], s2 += o[1];
+  }
+  const double m = s / N;
+  const double var = (s2 - s * m) / (double)(N - 1);
+  mean[b * C + c] = (float)m;
+  stdv[b * C + c] = (float)sqrt(var > 0.0 ? var : 0.0);
 }
 
 // sigma = mean over channels of the per-channel std (ops.py:27), summed in channel order.
@@ -583,13 +599,22 @@ static int launch_knn_feat(const float* an, const float* anorm, const float* bn,
 }
 
 // shared with upsample.cu
+constexpr int kStatsSlices = 4;     // point slices per (cloud, 32-channel block) in the point-major form
+size_t knn_stats_scratch_bytes(int B, int C) { return (size_t)B * kStatsSlices * C * 2 * sizeof(double); }
+
 int launch_knn_stats(const float* a, long long sb, long long sn, long long sc, int B, int N, int C, float* mean,
-                     float* stdv, cudaStream_t st) {
+                     float* stdv, cudaStream_t st, double* scratch) {
+  if (sc == 1 && C >= 8 && scratch) {     // point-major rows (the blocks' own activations)
+    SAMBLE_PRE(st);
+    knn_stats_pm_kernel<<<dim3(ceil_div(C, 32), B, kStatsSlices), 512, 0, st>>>(a, sb, sn, N, C, scratch);
+    SAMBLE_LAUNCHED("knn_stats_kernel");
+    SAMBLE_PRE(st);
+    knn_stats_pm_combine_kernel<<<dim3(ceil_div(C, 128), B), 128, 0, st>>>(scratch, kStatsSlices, N, C, mean, stdv);
+    SAMBLE_LAUNCHED("knn_stats_combine_kernel");
+    return SAMBLE_OK;
+  }
   SAMBLE_PRE(st);
-  if (sc == 1 && C >= 8)      // point-major rows (the blocks' own activations)
-    knn_stats_pm_kernel<<<dim3(ceil_div(C, 32), B), 512, 0, st>>>(a, sb, sn, N, C, mean, stdv);
-  else
-    knn_stats_kernel<<<dim3(ceil_div(C, 8), B), 256, 0, st>>>(a, sb, sn, sc, N, C, mean, stdv);
+  knn_stats_kernel<<<dim3(ceil_div(C, 8), B), 256, 0, st>>>(a, sb, sn, sc, N, C, mean, stdv);
   SAMBLE_LAUNCHED("knn_stats_kernel");
   return SAMBLE_OK;
 }
@@ -626,7 +651,7 @@ static KnnPlan knn_plan(int B, int Nq, int Nr, int C) {
             align_up((size_t)B * Nr * per_pt, 256) + 2 * align_up((size_t)B * Nq * sizeof(float), 256) +
             align_up((size_t)B * sizeof(unsigned), 256) + (p.xyz ? 0 : knn_tc_workspace_bytes(B, Nq, Nr)) +
             (p.xyz ? 0 : align_up((size_t)B * Nq * per_pt, 256) + align_up((size_t)B * Nr * per_pt, 256)) /* tf32 copies */ +
-            14 * 256;
+            align_up((size_t)B * 4 * C * 2 * sizeof(double), 256) /* stats slices */ + 14 * 256;
   return p;
 }
 
@@ -650,7 +675,8 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   Workspace w(ws, ws_bytes);
   float* mean = w.take<float>((size_t)B * C);
   float* stdv = w.take<float>((size_t)B * C);
-  if (int e = launch_knn_stats(a, a_sb, a_sn, a_sc, B, Nq, C, mean, stdv, st)) return e;
+  double* stats_scratch = w.take<double>(knn_stats_scratch_bytes(B, C) / sizeof(double));
+  if (int e = launch_knn_stats(a, a_sb, a_sn, a_sc, B, Nq, C, mean, stdv, st, stats_scratch)) return e;
   if (plan.xyz) {
     float4* qa = w.take<float4>((size_t)B * Nq);
     float4* qb = self ? qa : w.take<float4>((size_t)B * Nr);

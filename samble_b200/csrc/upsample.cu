@@ -7,7 +7,7 @@
 namespace samble {
 
 int launch_knn_stats(const float* a, long long sb, long long sn, long long sc, int B, int N, int C, float* mean,
-                     float* stdv, cudaStream_t st);
+                     float* stdv, cudaStream_t st, double* scratch);
 int launch_knn_prep_xyz(const float* x, long long sb, long long sn, long long sc, int B, int N, int C,
                         const float* mean, const float* stdv, float4* out, cudaStream_t st);
 
@@ -30,22 +30,32 @@ __global__ void __launch_bounds__(128) interpolate3_kernel(const float4* __restr
     __syncthreads();
     for (int j = threadIdx.x; j < cn; j += blockDim.x) cand[j] = sel[(long long)b * M + c0 + j];
     __syncthreads();
-    for (int j = 0; j < cn; ++j) {
-      const float4 p = cand[j];
-      // same 5-term row as the xyz kNN (knn.cu), ascending j so ties keep the lower index
-      float acc = __fmul_rn(ax, p.x);
-      acc = __fmaf_rn(ay, p.y, acc);
-      acc = __fmaf_rn(az, p.z, acc);
-      acc = __fadd_rn(acc, q.w);
-      acc = __fadd_rn(acc, p.w);
-      const float d = acc > 0.f ? acc : 0.f;
-      if (d < d2) {
-        if (d < d1) {
-          d2 = d1, i2 = i1;
-          if (d < d0) d1 = d0, i1 = i0, d0 = d, i0 = c0 + j;
-          else d1 = d, i1 = c0 + j;
-        } else {
-          d2 = d, i2 = c0 + j;
+    // four candidates per trip: their distance chains are independent (the kernel has only ~2 warps per scheduler, so
+    // instruction-level parallelism is what hides the FMA latency); the inserts stay in ascending-j order
+    for (int j = 0; j < cn; j += 4) {
+      float d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 p = cand[min(j + u, cn - 1)];
+        // same 5-term row as the xyz kNN (knn.cu), ascending j so ties keep the lower index
+        float acc = __fmul_rn(ax, p.x);
+        acc = __fmaf_rn(ay, p.y, acc);
+        acc = __fmaf_rn(az, p.z, acc);
+        acc = __fadd_rn(acc, q.w);
+        acc = __fadd_rn(acc, p.w);
+        d[u] = (j + u < cn) ? (acc > 0.f ? acc : 0.f) : INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float dd = d[u];
+        if (dd < d2) {
+          if (dd < d1) {
+            d2 = d1, i2 = i1;
+            if (dd < d0) d1 = d0, i1 = i0, d0 = dd, i0 = c0 + j + u;
+            else d1 = dd, i1 = c0 + j + u;
+          } else {
+            d2 = dd, i2 = c0 + j + u;
+          }
         }
       }
     }
@@ -138,7 +148,7 @@ extern "C" int samble_interpolate3(const float* xyz_up, const float* xyz_sel, co
   float4* up = w.take<float4>((size_t)B * N);
   float4* sel = w.take<float4>((size_t)B * M);
   // channel-major (B,3,N): strides (3N, 1, N)
-  if (int e = launch_knn_stats(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, st)) return e;
+  if (int e = launch_knn_stats(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, st, nullptr)) return e;
   if (int e = launch_knn_prep_xyz(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, up, st)) return e;
   if (int e = launch_knn_prep_xyz(xyz_sel, 3LL * M, 1, M, B, M, 3, mean, stdv, sel, st)) return e;
   SAMBLE_PRE(st);
@@ -166,7 +176,7 @@ extern "C" int samble_interpolate3_rows(const float* xyz_up, const float* xyz_se
   float4* sel = w.take<float4>((size_t)B * M);
   int* nn_idx = w.take<int>((size_t)B * N * 3);
   float* nn_w = w.take<float>((size_t)B * N * 3);
-  if (int e = launch_knn_stats(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, st)) return e;
+  if (int e = launch_knn_stats(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, st, nullptr)) return e;
   if (int e = launch_knn_prep_xyz(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, up, st)) return e;
   if (int e = launch_knn_prep_xyz(xyz_sel, 3LL * M, 1, M, B, M, 3, mean, stdv, sel, st)) return e;
   SAMBLE_PRE(st);
