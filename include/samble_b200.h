@@ -75,13 +75,13 @@ int samble_selftest_mma_rate(int n_tile, int iters, int ctas, long long* cycles_
  * distance in normalised units (what :43 returns), or NULL.
  * Limits: 1 <= k <= 32, k <= Nr, C <= 512.
  *
- * C <= 3 runs the FFMA xyz kernel.  4 <= C <= 128 runs the tcgen05 path (tf32 contraction -> candidate set ->
+ * C <= 3 runs the FFMA xyz kernel.  4 <= C <= 128 runs the tcgen05 path (split-bf16 contraction -> candidate set ->
  * exact fp32 re-rank; output identical to the exact kernel); larger C runs the exact FFMA tile kernel.
  * samble_set_knn_mode: 0 = auto (default), 1 = exact FFMA kernels only (used by the tests as the cross-check).
  *
  * flags: 0, or SAMBLE_KNN_ANY_ORDER (dist_out must be NULL): the k indices of each row are the same SET but in no
  * particular order.  Every consumer on the path reduces over the neighbours (max, softmax-weighted sum, scatter),
- * so the blocks ask for this; the tcgen05 path then computes exact distances only for the few candidates whose tf32
+ * so the blocks ask for this; the tcgen05 path then computes exact distances only for the few candidates whose approximate
  * score is within the error margin of the k-th (knn_select_kernel) instead of for the whole candidate list. */
 #define SAMBLE_KNN_ANY_ORDER 1
 void samble_set_knn_mode(int mode);

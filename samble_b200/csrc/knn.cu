@@ -1,6 +1,8 @@
 // kNN for SAMBLE clouds: replaces reference utils/ops.py:17-44 (mean/std normalisation, torch.cdist,
 // topk) with   stats -> normalise -> fused (distance tile + k-selection)   kernels.
 // The (B,Nq,Nr) distance matrix is never written to HBM.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "gemm_tile.cuh"
 
@@ -127,16 +129,29 @@ __global__ void __launch_bounds__(256) knn_prep_xyz_kernel(const float* __restri
   out[(long long)b * N + n] = make_float4(v[0], v[1], v[2], nn);
 }
 
-// Norm slice of the tensor-core path (knn_tc.cu): candidate n contributes the K=8 operand row (h_hi, h_lo, 0, ..., 0),
-// h = -|b|^2/2 split into two tf32 terms, stored per (cloud, tile of 128) in the compact no-swizzle operand layout
-// [chunk][row][16 B]; only chunk 0 is non-zero (chunk 1 is all zero).
+// Tensor-core operand planes (knn_tc.cu): x = hi + lo + eps with hi = bf16(x), lo = bf16(x - hi), |eps| <= 2^-18 |x|.
+__device__ __forceinline__ void bf16_split(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// Norm slice of the tensor-core path: candidate n contributes the K=16 operand row (h1, h2, h3, 0, ..., 0),
+// h = -|b|^2/2 split into three bf16 terms (24 bits), stored per (cloud, tile of 128) in the compact no-swizzle operand
+// layout [chunk][row][16 B]; only chunk 0 is non-zero.
 __device__ __forceinline__ void knn_store_ext(float* ext, int b, int N, int n, float h) {
   const int ntiles = (N + 127) >> 7;
   if (n >= ntiles * 128) return;
-  const float hi = __uint_as_float(__float_as_uint(h) & 0xffffe000u);
+  const __nv_bfloat16 h1 = __float2bfloat16_rn(h);
+  const float r1 = h - __bfloat162float(h1);
+  const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
   float* blk = ext + ((size_t)b * ntiles + (n >> 7)) * 1024;
-  *reinterpret_cast<float4*>(blk + (n & 127) * 4) = make_float4(hi, h - hi, 0.f, 0.f);
-  *reinterpret_cast<float4*>(blk + 512 + (n & 127) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint4 row;
+  row.x = (uint32_t)__bfloat16_as_ushort(h1) | ((uint32_t)__bfloat16_as_ushort(h2) << 16);
+  row.y = (uint32_t)__bfloat16_as_ushort(h3);
+  row.z = 0u, row.w = 0u;
+  *reinterpret_cast<uint4*>(blk + (n & 127) * 4) = row;
+  *reinterpret_cast<uint4*>(blk + 512 + (n & 127) * 4) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // feature path: point-major normalised copy (B,N,Cp) (channels >= C zero) + squared norms (B,N).
@@ -146,7 +161,8 @@ __global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restr
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ stdv, float* __restrict__ out,
                                                             float* __restrict__ norms, unsigned* __restrict__ maxnorm,
-                                                            float* __restrict__ ext, float* __restrict__ out_tf32) {
+                                                            float* __restrict__ ext, __nv_bfloat16* __restrict__ out_hi,
+                                                            __nv_bfloat16* __restrict__ out_lo) {
   __shared__ float tile[32][33];
   const int b = blockIdx.y, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (n0 >= N) {                                        // padding rows of the last 128-candidate tile (ext only)
@@ -180,10 +196,11 @@ __global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restr
       if (n < N && c < Cp) {
         const float v = tile[tx][ty + 8 * r];
         out[((long long)b * N + n) * Cp + c] = v;
-        if (out_tf32) {            // tensor-core operand copy, rounded to nearest tf32 (the MMA itself would truncate)
-          unsigned rbits;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rbits) : "f"(v));
-          out_tf32[((long long)b * N + n) * Cp + c] = __uint_as_float(rbits);
+        if (out_hi) {              // tensor-core operand planes
+          __nv_bfloat16 h, l;
+          bf16_split(v, h, l);
+          out_hi[((long long)b * N + n) * Cp + c] = h;
+          out_lo[((long long)b * N + n) * Cp + c] = l;
         }
       }
     }
@@ -204,13 +221,14 @@ __global__ void __launch_bounds__(256) knn_prep_feat_kernel(const float* __restr
 }
 
 // Point-major input (the blocks' own activations): no transpose to do, so every thread moves one 16-byte chunk per
-// 32-channel block -- one LDG.128, two STG.128 (fp32 copy and tf32-rounded copy) -- and only the squared norms go through
+// 32-channel block -- one LDG.128, one STG.128 (fp32 copy) and two 8-byte stores (bf16 hi / lo planes) -- and only the squared norms go through
 // shared memory, to be summed per point in channel order exactly as above.
 __global__ void __launch_bounds__(256) knn_prep_feat_pm_kernel(const float* __restrict__ x, long long sb, long long sn, int N,
                                                                int C, int Cp, const float* __restrict__ mean,
                                                                const float* __restrict__ stdv, float* __restrict__ out,
                                                                float* __restrict__ norms, unsigned* __restrict__ maxnorm,
-                                                               float* __restrict__ ext, float* __restrict__ out_tf32) {
+                                                               float* __restrict__ ext, __nv_bfloat16* __restrict__ out_hi,
+                                                               __nv_bfloat16* __restrict__ out_lo) {
   __shared__ float tile[32][33];                        // [channel of the block][point]
   const int b = blockIdx.y, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (n0 >= N) {
@@ -235,13 +253,19 @@ __global__ void __launch_bounds__(256) knn_prep_feat_pm_kernel(const float* __re
     if (n < N && c < Cp) {
       const long long o = ((long long)b * N + n) * Cp + c;
       *reinterpret_cast<float4*>(out + o) = v;
-      if (out_tf32) {
-        uint4 r;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.x) : "f"(v.x));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.y) : "f"(v.y));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.z) : "f"(v.z));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r.w) : "f"(v.w));
-        *reinterpret_cast<uint4*>(out_tf32 + o) = r;
+      if (out_hi) {
+        __nv_bfloat16 h[4], l[4];
+        bf16_split(v.x, h[0], l[0]);
+        bf16_split(v.y, h[1], l[1]);
+        bf16_split(v.z, h[2], l[2]);
+        bf16_split(v.w, h[3], l[3]);
+        uint2 ph, pl;
+        ph.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+        ph.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+        pl.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+        pl.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+        *reinterpret_cast<uint2*>(out_hi + o) = ph;
+        *reinterpret_cast<uint2*>(out_lo + o) = pl;
       }
     }
     tile[f4 * 4 + 0][row] = v.x;
@@ -631,9 +655,10 @@ bool knn_tc_eligible(int Nq, int Nr, int C, int k);
 size_t knn_tc_workspace_bytes(int B, int Nq, int Nr);
 size_t knn_tc_ext_floats(int B, int Nr);
 template <class I>
-int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const float* an_tf32,
-                  const float* bn_tf32, const float* bext, const unsigned* bbmax, int B, int Nq, int Nr, int Cp, int k,
-                  float* thr, uint32_t* cand, int* cnt, bool ordered, I* idx, float* dist, int* row_flags, cudaStream_t st);
+int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const __nv_bfloat16* a_hi,
+                  const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, const float* bext,
+                  const unsigned* bbmax, int B, int Nq, int Nr, int Cp, int k, float* thr, uint32_t* cand, int* cnt, bool ordered,
+                  I* idx, float* dist, int* row_flags, cudaStream_t st);
 
 static int g_knn_mode = 0;   // 0 auto, 1 exact FFMA kernel only, 2 tensor-core path wherever eligible
 
@@ -650,19 +675,19 @@ static KnnPlan knn_plan(int B, int Nq, int Nr, int C) {
   p.bytes = 2 * align_up((size_t)B * C * sizeof(float), 256) + align_up((size_t)B * Nq * per_pt, 256) +
             align_up((size_t)B * Nr * per_pt, 256) + 2 * align_up((size_t)B * Nq * sizeof(float), 256) +
             align_up((size_t)B * sizeof(unsigned), 256) + (p.xyz ? 0 : knn_tc_workspace_bytes(B, Nq, Nr)) +
-            (p.xyz ? 0 : align_up((size_t)B * Nq * per_pt, 256) + align_up((size_t)B * Nr * per_pt, 256)) /* tf32 copies */ +
+            (p.xyz ? 0 : align_up((size_t)B * Nq * per_pt, 256) + align_up((size_t)B * Nr * per_pt, 256) + 4 * 256) /* bf16 planes */ +
             align_up((size_t)B * 4 * C * 2 * sizeof(double), 256) /* stats slices */ + 14 * 256;
   return p;
 }
 
 static void launch_prep_feat(dim3 grid, cudaStream_t st, const float* x, long long sb, long long sn, long long sc, int N, int C,
                              int Cp, const float* mean, const float* stdv, float* out, float* norms, unsigned* maxnorm,
-                             float* ext, float* out_tf32) {
+                             float* ext, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
   const bool pm = sc == 1 && C % 4 == 0 && sn % 4 == 0 && sb % 4 == 0 && (uintptr_t)x % 16 == 0;
   if (pm)
-    knn_prep_feat_pm_kernel<<<grid, 256, 0, st>>>(x, sb, sn, N, C, Cp, mean, stdv, out, norms, maxnorm, ext, out_tf32);
+    knn_prep_feat_pm_kernel<<<grid, 256, 0, st>>>(x, sb, sn, N, C, Cp, mean, stdv, out, norms, maxnorm, ext, out_hi, out_lo);
   else
-    knn_prep_feat_kernel<<<grid, 256, 0, st>>>(x, sb, sn, sc, N, C, Cp, mean, stdv, out, norms, maxnorm, ext, out_tf32);
+    knn_prep_feat_kernel<<<grid, 256, 0, st>>>(x, sb, sn, sc, N, C, Cp, mean, stdv, out, norms, maxnorm, ext, out_hi, out_lo);
 }
 
 template <class I>
@@ -710,8 +735,11 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   uint32_t* cand = w.take<uint32_t>((size_t)B * Nq * 128);
   int* cand_cnt = w.take<int>((size_t)B * Nq);
   float* bext = w.take<float>(knn_tc_ext_floats(B, Nr));
-  float* an_r = w.take<float>((size_t)B * Nq * Cp);          // tf32-rounded operand copies for the tensor-core passes
-  float* bn_r = self ? an_r : w.take<float>((size_t)B * Nr * Cp);
+  // bf16 hi/lo operand planes for the tensor-core passes (together the bytes of one fp32 copy)
+  __nv_bfloat16* a_hi = w.take<__nv_bfloat16>((size_t)B * Nq * Cp);
+  __nv_bfloat16* a_lo = w.take<__nv_bfloat16>((size_t)B * Nq * Cp);
+  __nv_bfloat16* b_hi = self ? a_hi : w.take<__nv_bfloat16>((size_t)B * Nr * Cp);
+  __nv_bfloat16* b_lo = self ? a_lo : w.take<__nv_bfloat16>((size_t)B * Nr * Cp);
   const bool use_tc = g_knn_mode != 1 && knn_tc_eligible(Nq, Nr, C, k);
   if (use_tc) {   // row_flags and bbmax are adjacent (256-byte granules): one memset node
     const size_t span = (size_t)((char*)(bbmax + B) - (char*)row_flags);
@@ -722,16 +750,16 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   // the candidate-side launch also covers the padding rows of the last 128-candidate tile (norm slice only)
   const bool a_is_cand = use_tc && self;
   launch_prep_feat(dim3(ceil_div(a_is_cand ? (int)align_up(Nq, 128) : Nq, 32), B), st, a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv,
-                   an, anorm, a_is_cand ? bbmax : nullptr, a_is_cand ? bext : nullptr, use_tc ? an_r : nullptr);
+                   an, anorm, a_is_cand ? bbmax : nullptr, a_is_cand ? bext : nullptr, use_tc ? a_hi : nullptr, use_tc ? a_lo : nullptr);
   SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   if (!self) {
     SAMBLE_PRE(st);
     launch_prep_feat(dim3(ceil_div(use_tc ? (int)align_up(Nr, 128) : Nr, 32), B), st, b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn,
-                     bnorm, use_tc ? bbmax : nullptr, use_tc ? bext : nullptr, use_tc ? bn_r : nullptr);
+                     bnorm, use_tc ? bbmax : nullptr, use_tc ? bext : nullptr, use_tc ? b_hi : nullptr, use_tc ? b_lo : nullptr);
     SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   }
   if (use_tc) {
-    if (int e = launch_knn_tc<I>(an, anorm, bn, bnorm, an_r, bn_r, bext, bbmax, B, Nq, Nr, Cp, k, thr, cand, cand_cnt, ordered, idx_out,
+    if (int e = launch_knn_tc<I>(an, anorm, bn, bnorm, a_hi, a_lo, b_hi, b_lo, bext, bbmax, B, Nq, Nr, Cp, k, thr, cand, cand_cnt, ordered, idx_out,
                                  dist_out, row_flags, st))
       return e;
     // rows whose candidate buffer overflowed are redone by the exact kernel (normally none: every tile exits at once)

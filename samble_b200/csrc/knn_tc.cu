@@ -1,14 +1,16 @@
 // K2 (tensor-core form): feature-space kNN with tcgen05.  reference utils/ops.py:35-43 (cdist + topk).
 //
-// Two passes over the SAME tf32 contraction with a thread-per-row TMEM epilogue that costs one or two
+// Two passes over the SAME tensor-core contraction with a thread-per-row TMEM epilogue that costs one or two
 // instructions per (query, candidate) pair, then an exact fp32 re-rank of a small candidate set:
 //
-//   The squared norm of the candidate rides in the GEMM: an extra K=8 MMA per tile multiplies the constant
-//   query-side row (1,1,0..) with (-|b|^2/2 split into tf32 hi+lo), so the accumulator holds
-//       s_ij = <a_i,b_j>_tf32 - |b_j|^2/2        and      d~_ij = |a_i|^2 - 2 s_ij.
+//   The squared norm of the candidate rides in the GEMM: an extra K=16 MMA per tile multiplies the constant
+//   query-side row (1,1,1,0..) with (-|b|^2/2 split into three bf16 terms), so the accumulator holds
+//       s_ij = <a_i,b_j>_bf16x2 - |b_j|^2/2      and      d~_ij = |a_i|^2 - 2 s_ij,
+//   operands split x = hi + lo into two bf16 planes (knn.cu prep), <a,b> ~= ah.bh + al.bh + ah.bl on kind::f16 MMAs
+//   (twice the tf32 issue rate, same operand bytes as one tf32 copy, error 2^-16 instead of 2^-10).
 //   pass A  per row keep the MAXIMUM of s over each of 64 interleaved column groups; the k-th largest of
 //           those 64 maxima bounds the k-th nearest approx distance (k distinct candidates reach it).
-//           -> T_i = that bound, loosened by the rigorous tf32 error e_i (knn_margin)
+//           -> T_i = that bound, loosened by the rigorous contraction error e_i (knn_margin)
 //   pass B  every candidate with s_ij >= T_i is appended to the row's list (ascending index)
 //   pass C  (knn_rerank_kernel) exact fp32 distance of the listed candidates -- the FFMA formula and
 //           accumulation order of the exact kernel in knn.cu -- and the k smallest by (distance, index).
@@ -16,11 +18,13 @@
 // The list is a provable superset of the exact kernel's answer, so idx/dist are IDENTICAL to
 // knn_feat_kernel's.  Rows whose list overflows are flagged and redone by the exact kernel.
 //
-// CTA = 128 query rows (UMMA M=128), candidate tiles of 128 (UMMA N=128), K-blocks of 32 channels
-// (128-byte rows, SWIZZLE_128B).  Warps 0-3: epilogue (thread = TMEM lane = query row); warp 4: MMA issuer;
+// CTA = 128 query rows (UMMA M=128), candidate tiles of 128 (UMMA N=128), K-tiles of 64 bf16 channels
+// (128-byte rows, SWIZZLE_128B), one per operand plane.  Warps 0-3: epilogue (thread = TMEM lane = query row); warp 4: MMA issuer;
 // warp 5: TMA producer (one thread: tensor-map box loads of the K-blocks, a bulk copy of the tile's norm slice).
 // smem ring of K-block stages (full/empty mbarriers, full[] counted in bytes by the TMA unit), two TMEM accumulators
 // (tmem_full/tmem_empty mbarriers) so the epilogue of tile t overlaps the MMAs of tile t+1.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -35,17 +39,19 @@ constexpr int kTcListLd = 128;    // list row pitch in global memory (32-bit ent
 constexpr int kTcListSm = 129;    // ... and in shared memory: odd, so the 32 rows of a warp hit 32 banks
 constexpr int kTcThreads = 192;   // 4 epilogue warps + MMA issuer + TMA producer
 
-static size_t tc_smem_bytes(int nkb, bool pass_b) {
-  return (size_t)nkb * 16384 + (size_t)kTcStages * 16384 /* A + B ring */ + 3 * kExt /* A_ext, B_ext x2 */
+static size_t tc_smem_bytes(int nkt, bool pass_b) {
+  return (size_t)2 * nkt * 16384 + (size_t)kTcStages * 16384 /* A hi+lo + B ring */ + 3 * kExt /* A_ext, B_ext x2 */
          + (pass_b ? (size_t)kTcRows * kTcListSm * 4 : 0) + 1024 + 256;
 }
 
-// |d~ - d_fp32| <= e:  the operands are ROUNDED to tf32 by the prep kernel (cvt.rna, |x - x_r| <= 2^-11 |x|; the MMA's own
-// truncation is then exact), so  2 * |<a_r,b_r> - <a,b>| <= 2 * (2^-11 + 2^-11 + 2^-22) |a||b| = (2^-9 + 2^-21) |a||b|,
-// + tensor-core fp32 accumulation slop + the tf32 split of |b|^2/2 + the fp32 rounding of the exact formula.
+// |d~ - d_fp32| <= e.  Operands: x = hi + lo + eps, |eps| <= 2^-18 |x| (two bf16 roundings), and the al.bl product is
+// dropped (<= 2^-18 |a||b|): |<a,b> - (ah.bh + al.bh + ah.bl)| <= 3 * 2^-18 |a||b|, i.e. 2^-15.4 |a||b| on d = ... - 2<a,b>.
+// The bf16 x bf16 products are exact in fp32; the tensor core's fp32 accumulation truncates: <= 2^-23 per update of an
+// accumulator bounded by |a||b| + |b|^2/2, ~25 updates per tile -> budgeted 2^-13 |a||b| (measured chains: DESIGN.md).
+// Plus the three-term bf16 split of |b|^2/2 (2^-25) and the fp32 rounding of the exact formula: 2^-15 (|a|^2 + |b|^2).
 __device__ __forceinline__ float knn_margin(float aa, float bbmax) {
   const float s = sqrtf(aa * bbmax);
-  return (0.001953125f + 0.00012207031f) * s + 3.0517578e-05f * (aa + bbmax);
+  return (3.0517578e-05f + 0.00012207031f) * s + 3.0517578e-05f * (aa + bbmax);
 }
 
 // A list entry is one 32-bit word: candidate index in the low half, and in the high half the upper 16 bits (sign,
@@ -78,15 +84,16 @@ __device__ __forceinline__ void sort64(float (&v)[64]) {
 
 template <bool PASS_B>
 __global__ void __launch_bounds__(kTcThreads, 1)
-    knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+    knn_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                   const float* __restrict__ anorm, const float* __restrict__ bext, const unsigned* __restrict__ bbmax_bits,
                   int Nq, int Nr, int Cp, int k, float* __restrict__ thr, uint32_t* __restrict__ cand_out,
                   int* __restrict__ cnt_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int nkb = Cp / 32;
-  uint8_t* sA = base;                                       // nkb K-blocks of the query tile
-  uint8_t* sB = sA + (size_t)nkb * 16384;                   // ring
+  const int nkt = (Cp + 63) / 64;                           // K-tiles of 64 bf16 (128-byte rows) per plane
+  uint8_t* sA = base;                                       // query tile: [hi: nkt tiles][lo: nkt tiles]
+  uint8_t* sB = sA + (size_t)2 * nkt * 16384;               // ring
   uint8_t* sAx = sB + (size_t)kTcStages * 16384;            // query-side norm slice: (1,1,0,...) per row
   uint8_t* sBx = sAx + kExt;                                // candidate-side norm slice, double buffered per tile
   uint8_t* tail = sBx + 2 * kExt;
@@ -107,7 +114,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   // ---- one-time setup: query-side norm slice, barriers, TMEM ----
   for (int p = tid; p < 256; p += kTcThreads) {
     const int row = p >> 1, ch = p & 1;
-    *reinterpret_cast<float4*>(sAx + tc::nosw_offset(row, ch, 128)) = ch == 0 ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // bf16 (1, 1, 1, 0, ...): picks up the three bf16 terms of -|b|^2/2
+    *reinterpret_cast<uint4*>(sAx + tc::nosw_offset(row, ch, 128)) = ch == 0 ? make_uint4(0x3f803f80u, 0x00003f80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
   }
   tc::fence_proxy_async();
   if (tid == 0) {
@@ -132,18 +140,23 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 5) {
     // ================= TMA producer =================
     if (tc::elect_one()) {
-      tc::tma_prefetch_desc(&map_a);
-      tc::tma_prefetch_desc(&map_b);
-      // resident query tile: nkb boxes of [128 rows x 32 channels]; rows past Nq read as zero
-      tc::mbar_arrive_expect_tx(afull, (uint32_t)nkb * 16384u);
-      for (int kb = 0; kb < nkb; ++kb) tc::tma_load_3d(sA + (size_t)kb * 16384, &map_a, afull, kb * 32, q0, b);
+      tc::tma_prefetch_desc(&map_a_hi);
+      tc::tma_prefetch_desc(&map_b_hi);
+      tc::tma_prefetch_desc(&map_b_lo);
+      // resident query tile, both planes: boxes of [128 rows x 64 bf16]; rows past Nq / channels past Cp read as zero
+      tc::mbar_arrive_expect_tx(afull, (uint32_t)(2 * nkt) * 16384u);
+      for (int kt = 0; kt < nkt; ++kt) {
+        tc::tma_load_3d(sA + (size_t)kt * 16384, &map_a_hi, afull, kt * 64, q0, b);
+        tc::tma_load_3d(sA + (size_t)(nkt + kt) * 16384, &map_a_lo, afull, kt * 64, q0, b);
+      }
       const float* ext_g = bext + (size_t)b * ntiles * (kExt / 4);
       int s = 0, ph = 0;
       for (int t = 0; t < ntiles; ++t) {
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int g = 0; g < 2 * nkt; ++g) {                 // stage order per tile: (kt 0: hi, lo), (kt 1: hi, lo), ...
+          const int kt = g >> 1;
           tc::mbar_wait(&empty[s], ph ^ 1);
-          if (kb == 0) {
-            // the tile's norm slice rides on the barrier of its first K-block; buffer t&1 is free once the norm
+          if (g == 0) {
+            // the tile's norm slice rides on the barrier of its first stage; buffer t&1 is free once the norm
             // MMA of tile t-2 retired
             tc::mbar_wait(&xempty[t & 1], ((t >> 1) & 1) ^ 1);
             tc::mbar_arrive_expect_tx(&full[s], 16384u + kExt);
@@ -151,7 +164,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           } else {
             tc::mbar_arrive_expect_tx(&full[s], 16384u);
           }
-          tc::tma_load_3d(sB + (size_t)s * 16384, &map_b, &full[s], kb * 32, t * kTcTile, b);   // rows past Nr: zero
+          tc::tma_load_3d(sB + (size_t)s * 16384, (g & 1) ? &map_b_lo : &map_b_hi, &full[s], kt * 64, t * kTcTile, b);
           if (++s == kTcStages) { s = 0; ph ^= 1; }
         }
       }
@@ -160,27 +173,37 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   } else if (warp == 4) {
     // ================= MMA issuer =================
     if (tc::elect_one()) {
-      const uint32_t idesc = tc::instr_desc(2, kTcRows, kTcTile);
+      const uint32_t idesc = tc::instr_desc(1, kTcRows, kTcTile);          // bf16 x bf16 -> fp32
       const uint64_t axd = tc::smem_desc_nosw(tc::smem_u32(sAx), 128);
       tc::mbar_wait(afull, 0);
+      int s = 0, ph = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int acc = t & 1;
         tc::mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);
         tc::tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int g = t * nkb + kb, s = g % kTcStages;
-          tc::mbar_wait(&full[s], (g / kTcStages) & 1);
+        for (int g = 0; g < 2 * nkt; ++g) {
+          const int kt = g >> 1;
+          tc::mbar_wait(&full[s], ph);
           tc::tc_fence_after();
-          const uint64_t ad = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)kb * 16384));
+          const uint64_t ah = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)kt * 16384));
+          const uint64_t al = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)(nkt + kt) * 16384));
           const uint64_t bd = tc::smem_desc_sw128(tc::smem_u32(sB + (size_t)s * 16384));
+          if ((g & 1) == 0) {                               // B_hi tile: ah.bh + al.bh
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) tc::mma_tf32(tmem + acc * kTcTile, ad + 2 * k8, bd + 2 * k8, idesc, (kb | k8) != 0);
-          if (kb == nkb - 1) {
-            // norm slice of tile t: landed with full[] of (t, kb=0), which this thread waited on
-            tc::mma_tf32(tmem + acc * kTcTile, axd, tc::smem_desc_nosw(tc::smem_u32(sBx + (size_t)(t & 1) * kExt), 128), idesc, 1);
+            for (int k16 = 0; k16 < 4; ++k16) tc::mma_bf16(tmem + acc * kTcTile, ah + 2 * k16, bd + 2 * k16, idesc, (g | k16) != 0);
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) tc::mma_bf16(tmem + acc * kTcTile, al + 2 * k16, bd + 2 * k16, idesc, 1);
+          } else {                                          // B_lo tile: ah.bl
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) tc::mma_bf16(tmem + acc * kTcTile, ah + 2 * k16, bd + 2 * k16, idesc, 1);
+          }
+          if (g == 2 * nkt - 1) {
+            // norm slice of tile t: landed with full[] of the tile's first stage, which this thread waited on
+            tc::mma_bf16(tmem + acc * kTcTile, axd, tc::smem_desc_nosw(tc::smem_u32(sBx + (size_t)(t & 1) * kExt), 128), idesc, 1);
             tc::mma_commit(&xempty[t & 1]);
           }
           tc::mma_commit(&empty[s]);                // smem stage reusable once these MMAs retire
+          if (++s == kTcStages) { s = 0; ph ^= 1; }
         }
         tc::mma_commit(&tfull[acc]);                // accumulator complete
       }
@@ -319,7 +342,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   }
 }
 
-// ---- pass C', indices only, any order: exact work only where the tf32 scores cannot decide. ----
+// ---- pass C', indices only, any order: exact work only where the approximate scores cannot decide. ----
 // With |d~ - d| <= e for every candidate (knn_margin) and d~(k), d~(k+1) the k-th / (k+1)-th smallest approx distances
 // of the row (both are in the list, which holds everything up to d~(k) + 2e):
 //   d~_j < d~(k+1) - 2e  and  d~(k+1) > e   =>  fewer than k candidates can beat j  -> j is in the exact answer
@@ -508,13 +531,16 @@ size_t knn_tc_workspace_bytes(int B, int Nq, int Nr) {
 size_t knn_tc_ext_floats(int B, int Nr) { return (size_t)B * ceil_div(Nr, kTcTile) * (kExt / 4); }
 
 template <class I>
-int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const float* an_tf32,
-                  const float* bn_tf32, const float* bext, const unsigned* bbmax, int B, int Nq, int Nr, int Cp, int k,
-                  float* thr, uint32_t* cand, int* cnt, bool ordered, I* idx, float* dist, int* row_flags, cudaStream_t st) {
-  const int nkb = Cp / 32;
-  alignas(64) CUtensorMap map_a, map_b;
-  if (int e = make_tile_map(&map_a, an_tf32, Cp, Cp, Nq, B, kTcRows)) return e;
-  if (int e = make_tile_map(&map_b, bn_tf32, Cp, Cp, Nr, B, kTcTile)) return e;
+int launch_knn_tc(const float* an, const float* anorm, const float* bn, const float* bnorm, const __nv_bfloat16* a_hi,
+                  const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi, const __nv_bfloat16* b_lo, const float* bext,
+                  const unsigned* bbmax, int B, int Nq, int Nr, int Cp, int k, float* thr, uint32_t* cand, int* cnt, bool ordered,
+                  I* idx, float* dist, int* row_flags, cudaStream_t st) {
+  const int nkb = (Cp + 63) / 64;                           // K-tiles of 64 bf16 per plane
+  alignas(64) CUtensorMap map_a, map_al, map_b, map_bl;
+  if (int e = make_tile_map(&map_a, a_hi, Cp, Cp, Nq, B, kTcRows, 2)) return e;
+  if (int e = make_tile_map(&map_al, a_lo, Cp, Cp, Nq, B, kTcRows, 2)) return e;
+  if (int e = make_tile_map(&map_b, b_hi, Cp, Cp, Nr, B, kTcTile, 2)) return e;
+  if (int e = make_tile_map(&map_bl, b_lo, Cp, Cp, Nr, B, kTcTile, 2)) return e;
   dim3 grid(ceil_div(Nq, kTcRows), B);
   {
     size_t smem = tc_smem_bytes(nkb, false);
@@ -522,7 +548,7 @@ int launch_knn_tc(const float* an, const float* anorm, const float* bn, const fl
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("knn_tc pass A smem attribute");
     SAMBLE_PRE(st);
-    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_b, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt);
+    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_al, map_b, map_bl, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt);
     SAMBLE_LAUNCHED("knn_tc_threshold_kernel");
   }
   {
@@ -531,7 +557,7 @@ int launch_knn_tc(const float* an, const float* anorm, const float* bn, const fl
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("knn_tc pass B smem attribute");
     SAMBLE_PRE(st);
-    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_b, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt);
+    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_al, map_b, map_bl, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt);
     SAMBLE_LAUNCHED("knn_tc_collect_kernel");
   }
   SAMBLE_PRE(st);
@@ -545,11 +571,12 @@ int launch_knn_tc(const float* an, const float* anorm, const float* bn, const fl
   return SAMBLE_OK;
 }
 
-template int launch_knn_tc<int>(const float*, const float*, const float*, const float*, const float*, const float*, const float*,
-                                const unsigned*, int, int, int, int, int, float*, uint32_t*, int*, bool, int*, float*, int*,
-                                cudaStream_t);
-template int launch_knn_tc<long long>(const float*, const float*, const float*, const float*, const float*, const float*,
-                                      const float*, const unsigned*, int, int, int, int, int, float*, uint32_t*, int*, bool,
-                                      long long*, float*, int*, cudaStream_t);
+template int launch_knn_tc<int>(const float*, const float*, const float*, const float*, const __nv_bfloat16*, const __nv_bfloat16*,
+                                const __nv_bfloat16*, const __nv_bfloat16*, const float*, const unsigned*, int, int, int, int, int,
+                                float*, uint32_t*, int*, bool, int*, float*, int*, cudaStream_t);
+template int launch_knn_tc<long long>(const float*, const float*, const float*, const float*, const __nv_bfloat16*,
+                                      const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, const float*, const unsigned*,
+                                      int, int, int, int, int, float*, uint32_t*, int*, bool, long long*, float*, int*,
+                                      cudaStream_t);
 
 }  // namespace samble

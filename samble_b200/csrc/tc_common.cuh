@@ -132,6 +132,13 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with bf16 operands (kind::f16, 128 x N x 16 per instruction: twice the tf32 rate)
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives when every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -168,6 +175,8 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 // batch pitch rows*ld, box = (1, box_rows, 32 floats = 128 B), 128-byte swizzle -- i.e. exactly the K-major SW128
 // operand tile smem_desc_sw128 describes; out-of-range rows and channels read as zero.
 // Returns SAMBLE_OK or sets the error text.
-int make_tile_map(CUtensorMap* map, const float* base, int inner, long long ld, int rows, int batch, int box_rows);
+// elem_bytes 4 = fp32 (box 32 wide), 2 = bf16 (box 64 wide): the box is always one 128-byte swizzled row segment.
+int make_tile_map(CUtensorMap* map, const void* base, int inner, long long ld, int rows, int batch, int box_rows,
+                  int elem_bytes = 4);
 
 }  // namespace samble

@@ -329,3 +329,20 @@ def test_transpose12():
     assert torch.equal(ops.transpose12(sl).cpu(), wide[..., 128:256].transpose(1, 2).contiguous())
     bcn = cu(torch.randn(2, 64, 300, generator=torch.Generator().manual_seed(3)))
     assert torch.equal(ops.transpose12(bcn), bcn.transpose(1, 2).contiguous())
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_tensor_core_knn_margin_stress(seed):
+    """The bf16x2 candidate passes keep a rigorous superset under heavy-tailed, badly scaled and low-rank features
+    (the error margin knn_margin is relative to |a||b|): ordered and any-order results equal the exact kernel's."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    B, N, C = 3, 2048, (128, 96, 64, 36)[seed]
+    base = torch.randn(B, N, C, generator=g)
+    heavy = base * torch.exp(1.5 * torch.randn(B, N, 1, generator=g))              # norms spread over ~3 decades
+    lowrank = (torch.randn(B, N, 5, generator=g) @ torch.randn(5, C, generator=g)) + 1e-3 * base
+    chan = base * torch.logspace(-3, 2, C).view(1, 1, C)                           # channel scales 1e-3 .. 1e2
+    for x in (heavy, lowrank, chan):
+        a = cu(x.contiguous())
+        (d0, i0), (d1, i1) = _knn_both(a, a, 32)
+        assert torch.equal(i0, i1) and torch.equal(d0, d1)
+        assert _same_sets_any_order(a, a, 32, i1)
