@@ -54,6 +54,14 @@ __device__ __forceinline__ float knn_margin(float aa, float bbmax) {
   return (3.0517578e-05f + 0.00012207031f) * s + 3.0517578e-05f * (aa + bbmax);
 }
 
+// Pass A only has to bound the k-th distance, so it runs the single product ah.bh (half the operand bytes, a third of
+// the MMAs): |<a,b> - ah.bh| <= (2^-9 + 2^-9 + 2^-18) |a||b|, i.e. 2^-7 |a||b| on d, plus the same accumulation / rounding
+// budget.  Its threshold is loosened by (e_A + e_B)/2 in score units (derivation at the pass-A epilogue).
+__device__ __forceinline__ float knn_margin_coarse(float aa, float bbmax) {
+  const float s = sqrtf(aa * bbmax);
+  return (0.0078125f + 3.0517578e-05f + 0.00012207031f) * s + 3.0517578e-05f * (aa + bbmax);
+}
+
 // A list entry is one 32-bit word: candidate index in the low half, and in the high half the upper 16 bits (sign,
 // exponent, 7 mantissa bits) of delta = s - T >= 0, the score's offset above the row's collection threshold T.
 // Words therefore order by score, and  delta_lo <= delta <= delta_lo * (1 + 2^-7)  with delta_lo = word & 0xffff0000.
@@ -92,6 +100,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nkt = (Cp + 63) / 64;                           // K-tiles of 64 bf16 (128-byte rows) per plane
+  constexpr int kPlanes = PASS_B ? 2 : 1;                   // candidate-side planes streamed per tile (pass A: hi only)
   uint8_t* sA = base;                                       // query tile: [hi: nkt tiles][lo: nkt tiles]
   uint8_t* sB = sA + (size_t)2 * nkt * 16384;               // ring
   uint8_t* sAx = sB + (size_t)kTcStages * 16384;            // query-side norm slice: (1,1,0,...) per row
@@ -152,8 +161,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const float* ext_g = bext + (size_t)b * ntiles * (kExt / 4);
       int s = 0, ph = 0;
       for (int t = 0; t < ntiles; ++t) {
-        for (int g = 0; g < 2 * nkt; ++g) {                 // stage order per tile: (kt 0: hi, lo), (kt 1: hi, lo), ...
-          const int kt = g >> 1;
+        for (int g = 0; g < kPlanes * nkt; ++g) {           // stage order per tile: (kt 0: hi[, lo]), (kt 1: hi[, lo]), ...
+          const int kt = PASS_B ? g >> 1 : g;
           tc::mbar_wait(&empty[s], ph ^ 1);
           if (g == 0) {
             // the tile's norm slice rides on the barrier of its first stage; buffer t&1 is free once the norm
@@ -164,7 +173,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           } else {
             tc::mbar_arrive_expect_tx(&full[s], 16384u);
           }
-          tc::tma_load_3d(sB + (size_t)s * 16384, (g & 1) ? &map_b_lo : &map_b_hi, &full[s], kt * 64, t * kTcTile, b);
+          tc::tma_load_3d(sB + (size_t)s * 16384, (PASS_B && (g & 1)) ? &map_b_lo : &map_b_hi, &full[s], kt * 64, t * kTcTile, b);
           if (++s == kTcStages) { s = 0; ph ^= 1; }
         }
       }
@@ -181,23 +190,25 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int acc = t & 1;
         tc::mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);
         tc::tc_fence_after();
-        for (int g = 0; g < 2 * nkt; ++g) {
-          const int kt = g >> 1;
+        for (int g = 0; g < kPlanes * nkt; ++g) {
+          const int kt = PASS_B ? g >> 1 : g;
           tc::mbar_wait(&full[s], ph);
           tc::tc_fence_after();
           const uint64_t ah = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)kt * 16384));
           const uint64_t al = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)(nkt + kt) * 16384));
           const uint64_t bd = tc::smem_desc_sw128(tc::smem_u32(sB + (size_t)s * 16384));
-          if ((g & 1) == 0) {                               // B_hi tile: ah.bh + al.bh
+          if (!PASS_B || (g & 1) == 0) {                    // B_hi tile: ah.bh (+ al.bh in pass B)
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) tc::mma_bf16(tmem + acc * kTcTile, ah + 2 * k16, bd + 2 * k16, idesc, (g | k16) != 0);
+            if (PASS_B) {
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) tc::mma_bf16(tmem + acc * kTcTile, al + 2 * k16, bd + 2 * k16, idesc, 1);
+              for (int k16 = 0; k16 < 4; ++k16) tc::mma_bf16(tmem + acc * kTcTile, al + 2 * k16, bd + 2 * k16, idesc, 1);
+            }
           } else {                                          // B_lo tile: ah.bl
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) tc::mma_bf16(tmem + acc * kTcTile, ah + 2 * k16, bd + 2 * k16, idesc, 1);
           }
-          if (g == 2 * nkt - 1) {
+          if (g == kPlanes * nkt - 1) {
             // norm slice of tile t: landed with full[] of the tile's first stage, which this thread waited on
             tc::mma_bf16(tmem + acc * kTcTile, axd, tc::smem_desc_nosw(tc::smem_u32(sBx + (size_t)(t & 1) * kExt), 128), idesc, 1);
             tc::mma_commit(&xempty[t & 1]);
@@ -261,10 +272,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
         for (int i = 32; i < 64; ++i) kth = fminf(kth, i >= 64 - k ? gmax[i] : INFINITY);
         const float aa = anorm[(size_t)b * Nq + q];
-        const float e = knn_margin(aa, __uint_as_float(bbmax_bits[b]));
-        // collect d~ <= d~_kth + 2e  <=>  s >= s_kth - e.  The min() covers k or more candidates sitting at (clamped)
-        // distance zero, e.g. duplicated points: then everything with d~ <= e, i.e. s >= (|a|^2 - e)/2, is needed.
-        thr[(size_t)b * Nq + q] = fminf(kth - e, 0.5f * (aa - e));
+        const float bbm = __uint_as_float(bbmax_bits[b]);
+        const float e = knn_margin(aa, bbm), ea = knn_margin_coarse(aa, bbm);
+        // k candidates have pass-A score >= kth, hence exact d <= |a|^2 - 2 kth + e_A, so the k-th exact distance is at
+        // most that; a member j of the exact answer then has pass-B score s_j >= (|a|^2 - d_j - e)/2 >= kth - (e_A + e)/2.
+        // The min() covers k or more candidates sitting at (clamped) distance zero, e.g. duplicated points: then
+        // everything with pass-B d~ <= e, i.e. s >= (|a|^2 - e)/2, is needed.
+        thr[(size_t)b * Nq + q] = fminf(kth - 0.5f * (ea + e), 0.5f * (aa - e));
       }
     } else if (q < Nq) {
       cnt_out[(size_t)b * Nq + q] = (int)(min(lptr, lbeg + 4u * kTcCap) - lbeg) >> 2;   // == kTcCap: saturated
