@@ -128,6 +128,93 @@ def sampled_index_parity(idx: Tensor, ref_idx: Tensor, score: Tensor, k_per_bin:
     return dict(exact_rate=float(exact.float().mean()), clouds=B, unexplained_bins=unexplained)
 
 
+def ds_scores_fp64(x: Tensor, wq: Tensor, wk: Tensor, tokens: Tensor, knn_idx: Tensor) -> Tuple[Tensor, Tensor]:
+    """fp64 statement of DownSampleToken's point score (models/downsample.py:124-153, 300-344) for the GIVEN
+    neighbour sets: x (B,C,N), wq/wk (D,C), tokens (C,nb), knn_idx (B,N,K) -> (score (B,N), amp (B,N)).
+    `amp[j]` = the largest sum_c |q_ic k_jc| / sqrt(D) over the edges i->j that enter score[j] and over the dominant
+    logit of those rows: the condition number that turns a relative fp32 dot-product error into a relative error of
+    score[j] (the softmax exponentiates the logit error)."""
+    B, C, N = x.shape
+    D = wq.shape[0]
+    wq, wk, tok = wq.double().cpu(), wk.double().cpu(), tokens.double().cpu()
+    scores, amps = [], []
+    for b in range(B):
+        xb = x[b].double().cpu()                                   # (C,N)
+        q = (wq @ xb).t()                                          # (N,D)
+        kk = (wk @ torch.cat([xb, tok], dim=1)).t()                # (N+nb,D)
+        logits = q @ kk.t() / (D ** 0.5)
+        amap = torch.softmax(logits, dim=-1)[:, :N]
+        idx = knn_idx[b].long().cpu()
+        mask = torch.zeros(N, N, dtype=torch.float64).scatter_(1, idx, 1.0)
+        indeg = mask.sum(0) + 1e-8
+        s = (amap * mask).sum(0) / indeg / indeg
+        s[torch.isnan(s)] = 0
+        scores.append(s)
+        mag = (q.abs() @ kk.abs().t()) / (D ** 0.5)                # sum_c |q_ic k_jc| / sqrt(D)
+        row_dom = mag.gather(1, logits.argmax(dim=1, keepdim=True))[:, 0]          # magnitude at each row's largest logit
+        edge = torch.maximum(mag[:, :N], row_dom[:, None]) * mask
+        amps.append(edge.max(dim=0)[0])
+    return torch.stack(scores), torch.stack(amps)
+
+
+def ds_parity(score64: Tensor, amp: Tensor, cuts: Tensor, idx: Tensor, bin_mask: Tensor, k_per_bin: Tensor,
+              ulps: float = 64.0) -> dict:
+    """fp64 adjudication of one DownSampleToken decision (the twin of knn_parity).
+
+    score64/amp from ds_scores_fp64; cuts (nb-1,) the frozen z-score thresholds (descending); idx (B,1,M), bin_mask
+    (B,1,N,nb) bool, k_per_bin (B,nb): the decision under test.  Any fp32 evaluation of the score carries a relative
+    error of about  eps_j = ulps * 2^-24 * amp_j  (dot-product rounding exponentiated by the softmax), so
+      * a point may sit in another bin than its fp64 z-score says only if that z is within eps_j*score_j/std of a cut;
+      * inside a bin, a chosen point may score below an unchosen one only if both are within eps of the bin's k-th score.
+    Everything else is counted as unexplained (must be 0)."""
+    score64, amp, idx = score64.double().cpu(), amp.double().cpu(), idx.cpu().long()
+    bin_mask, k_per_bin, cuts = bin_mask.cpu(), k_per_bin.cpu().long(), cuts.double().cpu().reshape(-1)
+    B, N = score64.shape
+    nb = bin_mask.shape[-1]
+    eps = ulps * 2.0 ** -24 * amp.clamp_min(1.0)                                     # (B,N) relative score tolerance
+    mu, sd = score64.mean(1, keepdim=True), score64.std(1, unbiased=False, keepdim=True)
+    z = (score64 - mu) / sd
+    upper = torch.cat([torch.tensor([float("inf")], dtype=torch.float64), cuts])
+    lower = torch.cat([cuts, torch.tensor([float("-inf")], dtype=torch.float64)])
+    bin64 = ((z.unsqueeze(-1) < upper) & (z.unsqueeze(-1) >= lower)).double().argmax(-1)     # (B,N)
+    mine = bin_mask[:, 0]
+    assert bool((mine.sum(-1) == 1).all()), "every point must sit in exactly one bin"
+    my_bin = mine.double().argmax(-1)
+    zband = eps * score64.abs() / sd + 1e-12
+    d_cut = (z.unsqueeze(-1) - cuts).abs().min(-1)[0] if cuts.numel() else torch.full_like(z, float("inf"))
+    flips = my_bin != bin64
+    bad_flips = flips & (d_cut > zband)
+    swaps = bad_swaps = wrong_bin = dup = 0
+    for b in range(B):
+        off = 0
+        for j in range(nb):
+            kj = int(k_per_bin[b, j])
+            seg = idx[b, 0, off:off + kj]
+            off += kj
+            members = (my_bin[b] == j).nonzero()[:, 0]
+            if kj == 0:
+                continue
+            if len(set(seg.tolist())) != kj:
+                dup += 1
+            if not bool(mine[b, seg, j].all()):
+                wrong_bin += int((~mine[b, seg, j]).sum())      # (k > bin size: the reference then takes non-members too)
+                continue
+            s = score64[b, members]
+            order = torch.sort(s, descending=True)[0]
+            kth = float(order[min(kj, len(order)) - 1])
+            chosen = torch.zeros(N, dtype=torch.bool)
+            chosen[seg] = True
+            ch = chosen[members]
+            e = eps[b, members]
+            low = ch & (s < kth)                     # chosen although below the fp64 k-th score
+            high = (~ch) & (s > kth)                 # passed over although above it
+            swaps += int(low.sum()) + int(high.sum())
+            bad_swaps += int((low & (s < kth * (1 - e) - 1e-300)).sum()) + int((high & (s > kth * (1 + e) + 1e-300)).sum())
+    return dict(points=B * N, bin_flips=int(flips.sum()), unexplained_bin_flips=int(bad_flips.sum()), topk_swaps=swaps,
+                unexplained_topk_swaps=bad_swaps, chosen_outside_bin=wrong_bin, duplicate_rows=dup,
+                max_eps=float(eps.max()), median_eps=float(eps.median()))
+
+
 def max_abs_rel(x: Tensor, ref: Tensor) -> Tuple[float, float]:
     x, ref = x.detach().double().cpu(), ref.detach().double().cpu()
     err = (x - ref).abs()
