@@ -214,6 +214,34 @@ int samble_ds_row_stats_fast(const float* q, long long ldq, const float* k, cons
                              const float* k_tok, int B, int N, int D, int nb, float* rowmax, float* rowsum,
                              float* token_logits, void* ws, size_t ws_bytes, samble_stream_t stream);
 
+/* ------------------------------------------- exact-product tensor-core GEMM -----
+ * The two contractions that decide DownSampleToken's sampled indices -- the q/k/v projection and q k^T
+ * (models/downsample.py:124-143) -- with an accumulation that is exact on the bf16 tensor cores (csrc/xgemm.cu):
+ * every operand is cut, per cloud, into three signed 8-bit digits stored as bf16 integers; the digit products are summed
+ * exactly by tcgen05.mma (integers < 2^23) and recombined with two fp32 roundings.  Result: fp32-class accuracy
+ * independent of summation order, bit-identical to an int32 restatement (reference != 0 runs that restatement).
+ *
+ * samble_digits: x (B, R, C) rows (row pitch ld, cloud pitch batch_stride, floats) -> planes: 3 x (B, R, Cp) bf16,
+ * Cp = C rounded up to 64, and scale[b].  The per-cloud magnitude comes from amax_in[b * amax_stride] (bits of max|x|,
+ * e.g. written by samble_xgemm's amax_out) or, when amax_in is NULL, from a reduction pass using amax_scratch[B]. */
+size_t samble_digits_bytes(int B, int R, int C);
+int samble_digits(const float* x, long long ld, long long batch_stride, int B, int R, int C, const unsigned* amax_in,
+                  int amax_stride, void* planes, float* scale, unsigned* amax_scratch, samble_stream_t stream);
+/* out[(b*Ra + i)*ldo + j] = <A[b,i,:], B[b or 0, j, :]>, A: Ba clouds of Ra rows, B: Bb (== Ba, or 1 = shared) sets of Rb
+ * rows, C <= 128 channels.  amax_out (or NULL): [Ba][ceil(Rb/amax_group)] bits of max|out| per cloud and column group
+ * (amax_group a multiple of 32), zeroed by the call. */
+int samble_xgemm(const void* a_planes, const float* a_scale, int Ba, int Ra, const void* b_planes, const float* b_scale,
+                 int Bb, int Rb, int C, float* out, long long ldo, unsigned* amax_out, int amax_group, int reference,
+                 samble_stream_t stream);
+/* DownSampleToken pass 1 (models/downsample.py:139-153) on that GEMM: row max / sum-of-exp of q k^T / sqrt(D) over the N
+ * point columns from the digit planes of q and k, merged with the nb token columns (exact fp32 dot products of the fp32
+ * q rows with k_tok, written to token_logits).  Any N. */
+size_t samble_ds_row_stats_exact_workspace_bytes(int B, int N);
+int samble_ds_row_stats_exact(const void* q_planes, const float* q_scale, const void* k_planes, const float* k_scale,
+                              const float* q, long long ldq, const float* k_tok, int B, int N, int D, int nb,
+                              float* rowmax, float* rowsum, float* token_logits, void* ws, size_t ws_bytes,
+                              samble_stream_t stream);
+
 /* models/downsample.py:300-344 (idx_mode sparse_col_sqr) without the dense mask:
  *   score[j] = sum_{i : j in kNN(i)} softmax_i[j] / indeg(j)^2,  NaN -> 0.
  * Only the N*K edges are evaluated; accumulation order is fixed (deterministic). */

@@ -50,7 +50,7 @@ class Forcing:
     point indices (DownSampleToken) -- whose fp32 near-ties no two implementations are obliged
     to break alike (SURVEY 7 hard part 1).  To compare everything downstream of such a decision
     within plain fp32 tolerance, the decision of the implementation under test is fed to the
-    oracle: `knn_log` is a list of ((Nq, Nr, C, k), idx (B,Nq,k)) in call order (entries are
+    oracle: `knn_log` is a list of ((Nq, Nr, C, k), idx (B,Nq,k)[, dist (B,Nq,k)]) in call order (entries are
     consumed by signature), `ds_idx` a list with one (B,1,M) index tensor per DownSample layer.
     What the oracle itself would have decided is still computed and kept in `knn_seen`
     (raw inputs + its own indices) / the `record` dict, so the decisions are compared stage by
@@ -63,10 +63,14 @@ class Forcing:
         self.knn_seen: List[dict] = []
 
     def take_knn(self, sig):
-        for n, (s, idx) in enumerate(self.knn_log):
-            if tuple(s) == tuple(sig):
+        """-> (idx, dist or None) of the first unconsumed entry with this signature, or None.  An entry may carry the
+        (positive) distances too: utils/ops.py:35's clamped GEMM-form distance of COINCIDENT points is pure fp32
+        cancellation noise (0 or ~1e-3), and upsample.py:206 turns it into a weight 1/(d + 1e-8) -- a quantity no two
+        fp32 implementations agree on, so it is forced like a decision and judged where it is computed."""
+        for n, entry in enumerate(self.knn_log):
+            if tuple(entry[0]) == tuple(sig):
                 del self.knn_log[n]
-                return idx
+                return entry[1], (entry[2] if len(entry) > 2 else None)
         return None
 
 
@@ -106,13 +110,14 @@ def knn(a: Tensor, b: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     # teacher-forced (tests only): same distance matrix, the neighbour choice of the implementation under test
     own = neg.topk(k=k, dim=-1)
     sig = (a.shape[1], b.shape[1], a.shape[2], k)
-    forced = _FORCE.take_knn(sig)
-    _FORCE.knn_seen.append(dict(sig=sig, idx=own[1], forced=forced, a=a if _FORCE.keep_inputs else None,
+    taken = _FORCE.take_knn(sig)
+    forced, fdist = taken if taken is not None else (None, None)
+    _FORCE.knn_seen.append(dict(sig=sig, idx=own[1], dist=own[0], forced=forced, a=a if _FORCE.keep_inputs else None,
                                 b=b if _FORCE.keep_inputs else None))
     if forced is None:
         return own
     forced = forced.to(torch.int64)
-    return neg.gather(2, forced), forced
+    return (neg.gather(2, forced) if fdist is None else -fdist), forced
 
 
 def index_points(points: Tensor, idx: Tensor) -> Tensor:

@@ -51,6 +51,11 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_n2p_attend": (_i, (_p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p, _p, _ll, _p)),
     "samble_set_ds_mode": (None, (_i,)),
     "samble_ds_row_stats": (_i, (_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p)),
+    "samble_digits_bytes": (_sz, (_i, _i, _i)),
+    "samble_digits": (_i, (_p, _ll, _ll, _i, _i, _i, _p, _i, _p, _p, _p, _p)),
+    "samble_xgemm": (_i, (_p, _p, _i, _i, _p, _p, _i, _i, _i, _p, _ll, _p, _i, _i, _p)),
+    "samble_ds_row_stats_exact_workspace_bytes": (_sz, (_i, _i)),
+    "samble_ds_row_stats_exact": (_i, (_p, _p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p)),
     "samble_ds_edge_score_workspace_bytes": (_sz, (_i, _i)),
     "samble_ds_edge_score": (_i, (_p, _ll, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p)),
     "samble_zscore": (_i, (_p, _i, _i, _p, _p)),
@@ -108,14 +113,19 @@ def need_cuda(*tensors: torch.Tensor) -> torch.device:
             dev = t.device
         elif t.device != dev:
             raise RuntimeError(f"samble_b200: tensors on different devices ({dev} vs {t.device})")
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        # kernels are launched on the calling thread's current device, on that device's current stream
+        raise RuntimeError(f"samble_b200: tensors live on {dev} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           "call torch.cuda.set_device(...) or wrap the call in `with torch.cuda.device(...)`")
     return dev
 
 
 def no_grad_check(*tensors: torch.Tensor) -> None:
-    """Forward-only (SURVEY 8b 'Autograd'): refuse rather than return silently wrong gradients."""
+    """The fused inference kernels have no backward: refuse rather than return silently wrong gradients.  (The
+    differentiable path is samble_b200.autograd; the blocks pick it whenever a gradient could be asked for.)"""
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        raise RuntimeError("samble_b200 native ops are forward-only: run under torch.no_grad() "
-                           "(backward is SURVEY 8f item f1)")
+        raise RuntimeError("samble_b200: this fused kernel is forward-only and a tensor (or module parameter) that requires "
+                           "grad reached it; run under torch.no_grad(), or use the differentiable path")
 
 
 def ptr(t) -> C.c_void_p:

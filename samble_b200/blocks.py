@@ -209,6 +209,11 @@ class Neighbor2PointAttention(nn.Module):
         return y.transpose(1, 2)          # the reference's (B,C,N) shape as a view of point-major storage (ops.rows_of)
 
 
+# DownSampleToken's score-deciding contractions on the exact-product GEMM (csrc/xgemm.cu).  False = the 3xTF32 kernels
+# of round 1 (kept for A/B measurements: tools/diag_parity.py).
+DS_EXACT = True
+
+
 class DownSampleToken(nn.Module):
     """models/downsample.py:15-378 for the shipped configuration: asm 'dot', one head, multi_token,
     idx_mode sparse_col_sqr, mean_relu, res off, sample_mode 'topk'.
@@ -282,15 +287,25 @@ class DownSampleToken(nn.Module):
         # projections of the points and of the nb bin tokens (shared by the whole batch, :116-118)
         w = self._wqkv.get([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], lambda: torch.cat(
             [self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C).contiguous())
-        qkv = ops.linear(x, w, x_layout="bcn")                                 # (B,N,3C) on the tensor cores (3xTF32)
+        # The two contractions that decide the sampled indices run on the exact-product tensor-core GEMM (csrc/xgemm.cu):
+        # fp32-class accuracy independent of accumulation order (the 3xTF32 kernels' logit error is exponentiated here).
+        exact = DS_EXACT and C <= 128 and C % 4 == 0 and D == C
+        if exact:
+            x_rows = ops.rows_of(x)                                            # (B,N,C)
+            qkv, amax = ops.xgemm(ops.digits(x_rows), ops.weight_digits(w), amax_group=C)     # (B,N,3C) + max|q|,|k|,|v| per cloud
+        else:
+            qkv = ops.linear(x, w, x_layout="bcn")                             # (B,N,3C), 3xTF32
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         tok = self.bin_tokens[0].t()                                           # (nb,C)
         k_tok = torch.matmul(tok, self.k_conv.weight.view(C, C).t()).contiguous()   # (nb,D)
         v_tok = torch.matmul(tok, self.v_conv.weight.view(C, C).t())
 
         idx = ops.knn_indices(x, self.K, ordered=False)                                       # neighbor_mask's kNN (:301)
-        k_split = ops.split_operand(k) if (N % 128 == 0 or self.M % 128 == 0) else None   # shared by pass 1 and the M rows
-        rowmax, rowsum, tok_logits = ops.ds_row_stats(q, k, k_tok, k_split=k_split)
+        k_split = ops.split_operand(k) if (self.M % 128 == 0 and N <= 4096) else None         # for the M selected rows
+        if exact:
+            rowmax, rowsum, tok_logits = ops.ds_row_stats_exact(ops.digits(q, amax, 0), ops.digits(k, amax, 1), q, k_tok)
+        else:
+            rowmax, rowsum, tok_logits = ops.ds_row_stats(q, k, k_tok, k_split=k_split)
         score = ops.ds_edge_score(q, k, rowmax, rowsum, idx)                   # (B,N)
         self.attention_point_score = score.view(B, 1, N)
 
@@ -313,7 +328,7 @@ class DownSampleToken(nn.Module):
         sel = s["idx"]
         scale = math.sqrt(D)
         q_sel, m_sel, s_sel, tok_mix = ops.ds_select_rows(q, rowmax, rowsum, tok_logits, v_tok, sel)
-        if self.M % 128 == 0:
+        if self.M % 128 == 0 and N <= 4096:        # (samble_cloud_matmul contracts at most 4096 keys)
             att = ops.cloud_matmul(q_sel, k, row_max=m_sel, row_sum=s_sel, logit_div=scale, w_split=k_split)     # (B,M,N)
             x_ds = ops.cloud_matmul(att, v.transpose(1, 2), residual=tok_mix)                     # (B,M,C)
         else:

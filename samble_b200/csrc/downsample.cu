@@ -4,9 +4,10 @@
 // five N x N fp32 temporaries per cloud.  Here:
 //   pass 1  ds_row_stats : q k^T tiles (shared FFMA tile engine) with an online max / sum-of-exp per
 //                          row; only (B,N) statistics and the nb pre-softmax token columns are written.
-//   pass 2  ds_edge_score: only the N*K kNN edges are re-evaluated (same FFMA order => the same logit
-//                          bit pattern as pass 1) and reduced per destination column in a FIXED order
-//                          (per-warp private partial columns, no float atomics) => deterministic.
+//   pass 2  ds_edge_score: only the N*K kNN edges are re-evaluated in fp32 FFMA and reduced per destination column
+//                          in a FIXED order (per-warp private partial columns, no float atomics) => deterministic.
+//                          (pass 1 normally runs on the tensor cores -- ds_rowstats_tc.cu / linear_tma.cu; the FFMA
+//                          kernel below is the cross-check, samble_set_ds_mode(1).)
 #include "common.cuh"
 #include "gemm_tile.cuh"
 
@@ -114,13 +115,14 @@ __global__ void __launch_bounds__(256) ds_edge_partial_kernel(const float* __res
       const int e = e0 + lane;
       const int j_mine = e < K ? (int)ld_idx(idx, row * K + e) : 0;
       float acc[32];
+      int jt[32];                                     // the 32 neighbour indices, broadcast while the warp is converged
 #pragma unroll
-      for (int t = 0; t < 32; ++t) acc[t] = 0.f;
-      for (int c = lane; c < nch; c += 32) {
+      for (int t = 0; t < 32; ++t) acc[t] = 0.f, jt[t] = __shfl_sync(kFull, j_mine, t);
+      for (int c = lane; c < nch; c += 32) {          // lanes beyond the chunk count (D < 128) skip: no shuffles inside
         const float4 qv = __ldg(reinterpret_cast<const float4*>(q + row * ldq) + c);
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
-          const int j = __shfl_sync(kFull, j_mine, t);
+          const int j = jt[t];
           const float4 kv = __ldg(reinterpret_cast<const float4*>(k + ((long long)b * N + j) * ldk) + c);
           acc[t] = fmaf(qv.x, kv.x, acc[t]);
           acc[t] = fmaf(qv.y, kv.y, acc[t]);

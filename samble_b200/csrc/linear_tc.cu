@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(256) ds_rowstats_finalize_kernel(const float2*
       for (int t = lane; t < ntiles; t += 32) {
         const float2 p = part[m * ntiles + t];
         const float mn = fmaxf(mx, p.x);
-        sum = sum * __expf(mx - mn) + p.y * __expf(p.x - mn);
+        sum = sum * expf(mx - mn) + p.y * expf(p.x - mn);
         mx = mn;
       }
     }
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256) ds_rowstats_finalize_kernel(const float2*
     for (int o = 16; o > 0; o >>= 1) {
       const float om = __shfl_xor_sync(kFull, mx, o), os = __shfl_xor_sync(kFull, sum, o);
       const float mn = fmaxf(mx, om);
-      sum = (mx == -INFINITY ? 0.f : sum * __expf(mx - mn)) + (om == -INFINITY ? 0.f : os * __expf(om - mn));
+      sum = (mx == -INFINITY ? 0.f : sum * expf(mx - mn)) + (om == -INFINITY ? 0.f : os * expf(om - mn));
       mx = mn;
     }
     mxr[r] = mx, sumr[r] = sum;
@@ -456,6 +456,21 @@ __global__ void __launch_bounds__(256) ds_rowstats_finalize_kernel(const float2*
   }
 }
 
+namespace samble {
+// shared with xgemm.cu (samble_ds_row_stats_exact)
+int launch_ds_rowstats_finalize(const float2* part, int ntiles, const float* q, long long ldq, const float* k_tok, int M, int D,
+                                int nb, float* rowmax, float* rowsum, float* token_logits, cudaStream_t st) {
+  SAMBLE_PRE(st);
+  const size_t fsmem = (size_t)(nb + 8 * kFinRows) * (D + kFinPad) * sizeof(float);
+  if (cudaFuncSetAttribute(ds_rowstats_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem) != cudaSuccess)
+    return check_launch("ds_rowstats_finalize smem attribute");
+  ds_rowstats_finalize_kernel<<<ceil_div(M, 8 * kFinRows), 256, fsmem, st>>>(part, ntiles, q, ldq, k_tok, M, D, nb, sqrtf((float)D),
+                                                                              rowmax, rowsum, token_logits);
+  SAMBLE_LAUNCHED("ds_rowstats_finalize_kernel");
+  return SAMBLE_OK;
+}
+}  // namespace samble
+
 extern "C" size_t samble_ds_row_stats_fast_workspace_bytes(int B, int N) {
   if (B <= 0 || N <= 0) return 0;
   return align_up((size_t)B * N * ceil_div(N, 128) * sizeof(float2), 256) + 256;
@@ -481,13 +496,6 @@ extern "C" int samble_ds_row_stats_fast(const float* q, long long ldq, const flo
             0, 0, 0, 0, 0, 0, nullptr, nullptr, 1, nullptr, nullptr, scale, 2 /* short chains: sharp logits, see ds_rowstats_tc.cu */,
             part};
   if (int e = launch_linear_tma<128>(a, st)) return e;
-  SAMBLE_PRE(st);
-  const size_t fsmem = (size_t)(nb + 8 * kFinRows) * (D + kFinPad) * sizeof(float);
-  if (cudaFuncSetAttribute(ds_rowstats_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem) != cudaSuccess)
-    return check_launch("ds_rowstats_finalize smem attribute");
-  ds_rowstats_finalize_kernel<<<ceil_div(B * N, 8 * kFinRows), 256, fsmem, st>>>(part, ntiles, q, ldq, k_tok, B * N, D, nb, scale,
-                                                                                  rowmax, rowsum, token_logits);
-  SAMBLE_LAUNCHED("ds_rowstats_finalize_kernel");
-  return SAMBLE_OK;
+  return launch_ds_rowstats_finalize(part, ntiles, q, ldq, k_tok, B * N, D, nb, rowmax, rowsum, token_logits, st);
 }
 

@@ -85,10 +85,17 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* key, int n) {
   __syncthreads();
 }
 
-__device__ __forceinline__ unsigned inv_score_bits(float s) {
-  // descending (score + 1e-8) == ascending inverted bit pattern (scores are >= 0; ops.py:478)
-  return 0xffffffffu - __float_as_uint(__fadd_rn(s, 1e-8f));
+// Sort key of v = score + 1e-8 (ops.py:478) such that ASCENDING key order == DESCENDING v, for any float: the IEEE
+// order-preserving map (negative values: all bits flipped, others: sign bit set), inverted.  -0 counts as +0 and NaN as
+// the largest value (torch.sort descending puts NaN first).
+__device__ __forceinline__ unsigned desc_key(float v) {
+  if (v != v) return 0u;
+  if (v == 0.f) v = 0.f;                                   // -0 -> +0
+  const unsigned b = __float_as_uint(v);
+  const unsigned asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ~asc;
 }
+__device__ __forceinline__ unsigned inv_score_bits(float s) { return desc_key(__fadd_rn(s, 1e-8f)); }
 
 static __host__ __device__ int next_pow2(int n) {
   int p = 1;
@@ -109,8 +116,9 @@ __global__ void __launch_bounds__(kSampThreads) index_topk_kernel(const float* _
     for (int i = threadIdx.x; i < npad; i += blockDim.x) {
       unsigned long long key = ~0ull;
       if (i < N) {
-        // non-members carry score*0 = +0 and therefore sort after every member, in index order
-        const unsigned hi = mask[((long long)b * N + i) * nb + j] ? inv_score_bits(score[(long long)b * N + i]) : 0xffffffffu;
+        // non-members carry (score + 1e-8) * 0 = 0: after every member with a positive value and before members with a
+        // negative one (ops.py:478-486), in index order among themselves
+        const unsigned hi = mask[((long long)b * N + i) * nb + j] ? inv_score_bits(score[(long long)b * N + i]) : desc_key(0.f);
         key = ((unsigned long long)hi << 24) | (unsigned)i;
       }
       keys[i] = key;
@@ -195,7 +203,6 @@ __global__ void __launch_bounds__(kSampThreads) ds_sample_kernel(const float* __
       k_out[b * nb + j] = kk[j];
     }
   }
-  for (int m = threadIdx.x; m < M; m += blockDim.x) idx_out[(long long)b * M + m] = 0;
   bitonic_sort(keys, npad);   // begins and ends with __syncthreads()
   for (int p = threadIdx.x; p < N; p += blockDim.x) {
     const unsigned long long key = keys[p];
@@ -203,6 +210,25 @@ __global__ void __launch_bounds__(kSampThreads) ds_sample_kernel(const float* __
     if (bin < nb) {
       const int r = p - start[bin];
       if (r < kk[bin] && koff[bin] + r < M) idx_out[(long long)b * M + koff[bin] + r] = (long long)(key & 0xffffffu);
+    }
+  }
+  // A bin that was asked for more points than it holds (the remainder rule of ops.py:427-430 can do that when nearly
+  // every bin is saturated): the reference's per-bin sort continues with the non-members, whose masked value is 0,
+  // i.e. in index order (ops.py:486-503).  One warp walks the cloud per such bin.
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    for (int j = 0; j < nb; ++j) {
+      int need = kk[j] - cnt[j];
+      if (need <= 0) continue;
+      int filled = 0;
+      for (int i0 = 0; i0 < N && filled < need; i0 += 32) {
+        const int i = i0 + lane;
+        const bool other = i < N && bin_id[(long long)b * N + i] != j;
+        const unsigned m = __ballot_sync(kFull, other);
+        const int r = filled + __popc(m & ((1u << lane) - 1u));
+        if (other && r < need && koff[j] + cnt[j] + r < M) idx_out[(long long)b * M + koff[j] + cnt[j] + r] = i;
+        filled += __popc(m);
+      }
     }
   }
 }

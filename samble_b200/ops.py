@@ -428,6 +428,91 @@ def split_operand(w: Tensor):
     return w, w_lo
 
 
+# ------------------------------------------------------------------ exact-product tensor-core GEMM (csrc/xgemm.cu)
+
+
+class Digits:
+    """Three signed-8-bit digit planes (bf16 integers) of a (B,R,C) fp32 array + the per-cloud power-of-two scale."""
+
+    __slots__ = ("planes", "scale", "B", "R", "C")
+
+    def __init__(self, planes, scale, B, R, C):
+        self.planes, self.scale, self.B, self.R, self.C = planes, scale, B, R, C
+
+
+def digits(x: Tensor, amax: Optional[Tensor] = None, group: int = 0) -> Digits:
+    """x (B,R,C) fp32 rows (unit inner stride, common row pitch; a column slice of a wider buffer is fine) -> Digits.
+    amax (B,G) int32 = bit patterns of max|x| per cloud and column group (xgemm(..., amax_group=C)); `group` picks the
+    column of amax that belongs to x.  Without amax a reduction pass finds the magnitudes."""
+    dev = L.need_cuda(x, amax)
+    x = _f32(x, "x")
+    if x.dim() != 3:
+        raise RuntimeError("digits: expected (B,R,C)")
+    B, R, Cc = x.shape
+    if x.stride(2) != 1 or x.stride(1) % 4 or x.stride(0) % 4 or x.data_ptr() % 16 or Cc % 4:
+        x = torch.nn.functional.pad(x, (0, (-Cc) % 4)).contiguous()
+    lib = L.lib()
+    planes = torch.empty(lib.samble_digits_bytes(B, R, x.shape[2]), dtype=torch.uint8, device=dev)
+    scale = torch.empty(B, dtype=torch.float32, device=dev)
+    if amax is None:
+        scratch = torch.empty(B, dtype=torch.int32, device=dev)
+        a_ptr, a_stride = None, 0
+    else:
+        scratch = None
+        a_ptr, a_stride = C.c_void_p(amax.data_ptr() + 4 * group), amax.shape[1]
+    L.check(lib.samble_digits(L.ptr(x), x.stride(1), x.stride(0), B, R, x.shape[2], a_ptr, a_stride, L.ptr(planes), L.ptr(scale),
+                              L.ptr(scratch), L.stream()), "samble_digits")
+    return Digits(planes, scale, B, R, x.shape[2])
+
+
+_W_DIGITS: dict = {}
+
+
+def weight_digits(weight: Tensor) -> Digits:
+    """digits() of a (Nout,K[,1[,1]]) weight as one 'cloud', cached per live tensor and in-place version."""
+    import weakref
+
+    key = id(weight)
+    ent = _W_DIGITS.get(key)
+    if ent is not None and ent[0]() is weight and ent[1] == weight._version:
+        return ent[2]
+    with torch.no_grad():
+        d = digits(weight.detach().flatten(1).unsqueeze(0))
+    _W_DIGITS[key] = (weakref.ref(weight, lambda _r, k=key: _W_DIGITS.pop(k, None)), weight._version, d)
+    return d
+
+
+def xgemm(a: Digits, b: Digits, amax_group: int = 0, reference: bool = False):
+    """out (Ba,Ra,Rb) = A[b] B[b or 0]^T, exact accumulation (samble_xgemm).  amax_group > 0 also returns the int32 bit
+    patterns of max|out| per cloud and group of `amax_group` output columns, which digits() of a column slice takes."""
+    if a.C != b.C or (b.B != a.B and b.B != 1):
+        raise RuntimeError(f"xgemm: A is ({a.B},{a.R},{a.C}), B is ({b.B},{b.R},{b.C})")
+    dev = a.planes.device
+    out = torch.empty(a.B, a.R, b.R, dtype=torch.float32, device=dev)
+    amax = torch.empty(a.B, (b.R + amax_group - 1) // amax_group, dtype=torch.int32, device=dev) if amax_group else None
+    L.check(L.lib().samble_xgemm(L.ptr(a.planes), L.ptr(a.scale), a.B, a.R, L.ptr(b.planes), L.ptr(b.scale), b.B, b.R, a.C,
+                                 L.ptr(out), b.R, L.ptr(amax), amax_group, 1 if reference else 0, L.stream()), "samble_xgemm")
+    return (out, amax) if amax_group else out
+
+
+def ds_row_stats_exact(qd: Digits, kd: Digits, q: Tensor, k_tok: Tensor):
+    """Row statistics of softmax(q [k | k_tok]^T / sqrt(D)) from the digit planes of q and k (point columns, exact
+    accumulation) and the fp32 q rows (token columns): -> rowmax (B,N), rowsum (B,N), token_logits (B,N,nb)."""
+    dev = L.need_cuda(q, k_tok)
+    B, N, D = q.shape
+    nb = k_tok.shape[0]
+    k_tok = _f32(k_tok, "k_tok").contiguous()
+    rowmax = torch.empty(B, N, dtype=torch.float32, device=dev)
+    rowsum = torch.empty(B, N, dtype=torch.float32, device=dev)
+    tok = torch.empty(B, N, nb, dtype=torch.float32, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.samble_ds_row_stats_exact_workspace_bytes(B, N), dev)
+    L.check(lib.samble_ds_row_stats_exact(L.ptr(qd.planes), L.ptr(qd.scale), L.ptr(kd.planes), L.ptr(kd.scale), L.ptr(q), q.stride(1),
+                                          L.ptr(k_tok), B, N, D, nb, L.ptr(rowmax), L.ptr(rowsum), L.ptr(tok), L.ptr(ws), ws.numel(),
+                                          L.stream()), "samble_ds_row_stats_exact")
+    return rowmax, rowsum, tok
+
+
 # Two tensor-core kernels compute the row statistics: the row-statistics epilogue of linear_tma.cu (default:
 # samble_ds_row_stats_fast; TMA-fed, shares k's tf32 split with cloud_matmul) and ds_rowstats_tc.cu (cp.async loaders).
 # Tests flip this to cross-check one against the other.

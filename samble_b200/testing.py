@@ -180,7 +180,8 @@ def ds_parity(score64: Tensor, amp: Tensor, cuts: Tensor, idx: Tensor, bin_mask:
     mine = bin_mask[:, 0]
     assert bool((mine.sum(-1) == 1).all()), "every point must sit in exactly one bin"
     my_bin = mine.double().argmax(-1)
-    zband = eps * score64.abs() / sd + 1e-12
+    # + the fp32 evaluation of z itself: (s - mean) / std with mean, std and the difference each rounded to fp32
+    zband = eps * score64.abs() / sd + 32 * 2.0 ** -24 * (mu.abs() / sd + z.abs() + 1.0)
     d_cut = (z.unsqueeze(-1) - cuts).abs().min(-1)[0] if cuts.numel() else torch.full_like(z, float("inf"))
     flips = my_bin != bin64
     bad_flips = flips & (d_cut > zband)
@@ -199,17 +200,20 @@ def ds_parity(score64: Tensor, amp: Tensor, cuts: Tensor, idx: Tensor, bin_mask:
             if not bool(mine[b, seg, j].all()):
                 wrong_bin += int((~mine[b, seg, j]).sum())      # (k > bin size: the reference then takes non-members too)
                 continue
+            # the sampler orders by key = fl32(score + 1e-8) (utils/ops.py:478): two keys closer than one fp32 rounding
+            # of the key are a tie (every score below ~6e-16 collapses onto 1e-8), on top of the score's own tolerance
             s = score64[b, members]
-            order = torch.sort(s, descending=True)[0]
+            key = s + 1e-8
+            order = torch.sort(key, descending=True)[0]
             kth = float(order[min(kj, len(order)) - 1])
             chosen = torch.zeros(N, dtype=torch.bool)
             chosen[seg] = True
             ch = chosen[members]
-            e = eps[b, members]
-            low = ch & (s < kth)                     # chosen although below the fp64 k-th score
-            high = (~ch) & (s > kth)                 # passed over although above it
+            tol = eps[b, members] * s.abs() + 2.0 ** -23 * key
+            low = ch & (key < kth)                   # chosen although below the fp64 k-th key
+            high = (~ch) & (key > kth)               # passed over although above it
             swaps += int(low.sum()) + int(high.sum())
-            bad_swaps += int((low & (s < kth * (1 - e) - 1e-300)).sum()) + int((high & (s > kth * (1 + e) + 1e-300)).sum())
+            bad_swaps += int((low & (key < kth - tol - 2.0 ** -23 * kth)).sum()) + int((high & (key > kth + tol + 2.0 ** -23 * kth)).sum())
     return dict(points=B * N, bin_flips=int(flips.sum()), unexplained_bin_flips=int(bad_flips.sum()), topk_swaps=swaps,
                 unexplained_topk_swaps=bad_swaps, chosen_outside_bin=wrong_bin, duplicate_rows=dup,
                 max_eps=float(eps.max()), median_eps=float(eps.median()))

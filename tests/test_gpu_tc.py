@@ -149,3 +149,88 @@ def test_cloud_matmul_matches_fp64(case):
     pref = torch.softmax(logits, dim=-1)
     assert (p.double().cpu() - pref).abs().max().item() < 2e-6
     assert (p.double().cpu().sum(-1) - 1).abs().max().item() < 1e-5
+
+
+# ---------------------------------------------------------------- exact-product GEMM (csrc/xgemm.cu)
+
+XG_SHAPES = [  # (Ba, Ra, Bb, Rb, C, scale of A, scale of B)
+    (2, 300, 2, 200, 128, 1.0, 1.0),
+    (3, 128, 1, 384, 128, 40.0, 0.09),        # shared B (a weight matrix), magnitudes far from 1
+    (1, 1000, 1, 70, 64, 1e-3, 1e3),
+    (2, 257, 2, 129, 20, 1.0, 1.0),           # channel count padded to 64, ragged tiles
+    (4, 2048, 4, 2048, 128, 3.0, 1.0),        # DownSampleToken q k^T at N=2048: a CTA walks several row tiles
+]
+
+
+@pytest.mark.parametrize("shape", XG_SHAPES, ids=lambda s: f"A{s[0]}x{s[1]}_B{s[2]}x{s[3]}_C{s[4]}")
+def test_xgemm_is_exact_and_order_independent(shape):
+    """The tensor-core accumulation of the digit products is EXACT: bit-identical to the int32 restatement, and
+    within the digit truncation bound of the fp64 product."""
+    from samble_b200 import ops
+
+    Ba, Ra, Bb, Rb, C, sa, sb = shape
+    g = torch.Generator().manual_seed(Ra + Rb)
+    A = (torch.randn(Ba, Ra, C, generator=g) * sa).cuda()
+    Bm = (torch.randn(Bb, Rb, C, generator=g) * sb).cuda()
+    A[0, 0] = 0                                                 # a zero row; one cloud much smaller than the others
+    if Ba > 1:
+        A[-1] *= 1e-2
+    ad, bd = ops.digits(A), ops.digits(Bm)
+    out = ops.xgemm(ad, bd)
+    ref = ops.xgemm(ad, bd, reference=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref), f"max |tc - int32| = {(out - ref).abs().max().item():.3e}"
+    exact = A.double() @ (Bm.double().transpose(1, 2) if Bb > 1 else Bm[0].double().t())
+    # digit pairs of weight < 2^-24 are dropped (<= ~K 2^-29 maxA maxB with the power-of-two ceilings), then three fused
+    # roundings of a partial sum no larger than the result: C is the fp64 product to within ~2 ulp
+    amax = A.abs().amax(dim=(1, 2)).double().clamp_min(1e-30)
+    bmax = Bm.abs().amax(dim=(1, 2)).double()
+    bound = (C * 2.0 ** -26 * amax * (bmax if Bb > 1 else bmax[0])).view(Ba, 1, 1) + 2.0 ** -22 * exact.abs()
+    err = (out.double() - exact).abs()
+    assert bool((err <= bound + 1e-30).all()), float((err / bound).max())
+    rel = err.max().item() / exact.abs().max().item()
+    print(f"xgemm {shape}: max err / max|C| = {rel:.2e}")
+
+
+def test_xgemm_amax_feeds_the_next_slicing():
+    from samble_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 640, 128, generator=g).cuda()
+    w = (torch.randn(384, 128, generator=g) / 11.3).cuda()
+    out, amax = ops.xgemm(ops.digits(x), ops.weight_digits(w), amax_group=128)
+    want = out.view(3, 640, 3, 128).abs().amax(dim=(1, 3))                     # (B, 3 groups)
+    assert torch.equal(amax.view(torch.float32), want)
+    q, k = out[..., :128], out[..., 128:256]
+    qd, kd = ops.digits(q, amax, 0), ops.digits(k, amax, 1)
+    qd2, kd2 = ops.digits(q.contiguous()), ops.digits(k.contiguous())          # own reduction pass
+    assert torch.equal(qd.planes, qd2.planes) and torch.equal(kd.planes, kd2.planes) and torch.equal(qd.scale, qd2.scale)
+    # the digits reconstruct the value to 2^-32 of the cloud's power-of-two ceiling (exactly, for all but tiny elements)
+    pl = qd.planes.view(torch.bfloat16).view(4, 3, 640, 128).double()
+    rec = (pl[0] + pl[1] / 2 ** 8 + pl[2] / 2 ** 16 + pl[3] / 2 ** 24) * qd.scale.double().view(3, 1, 1)
+    ceil2 = torch.exp2(torch.floor(torch.log2(want[:, 0].double())) + 1).view(3, 1, 1)
+    assert float(((rec - q.double()).abs() / ceil2).max()) <= 2.0 ** -32
+    assert float((rec == q.double()).double().mean()) > 0.95
+
+
+@pytest.mark.parametrize("B,N,nb,sharp", [(2, 2048, 4, 4.0), (1, 1000, 6, 8.0), (2, 512, 4, 1.0)])
+def test_ds_row_stats_exact_vs_fp64(B, N, nb, sharp):
+    """logsumexp of q [k | k_tok]^T / sqrt(D) from the exact GEMM: error of one fp32 rounding of the logit, not of a
+    tensor-core accumulation chain."""
+    import math
+
+    from samble_b200 import ops
+
+    D = 128
+    g = torch.Generator().manual_seed(N + nb)
+    q = (torch.randn(B, N, D, generator=g) * sharp).cuda()
+    k = torch.randn(B, N, D, generator=g).cuda()
+    k_tok = torch.randn(nb, D, generator=g).cuda()
+    rowmax, rowsum, tok = ops.ds_row_stats_exact(ops.digits(q), ops.digits(k), q, k_tok)
+    logits = torch.cat([q.double() @ k.double().transpose(1, 2), q.double() @ k_tok.double().t()], -1) / math.sqrt(D)
+    lse = rowmax.double() + torch.log(rowsum.double())
+    err = (lse - torch.logsumexp(logits, -1)).abs().max().item()
+    ulp = 2.0 ** -23 * float(logits.abs().max())
+    print(f"LSE error {err:.2e} (one ulp of the largest logit: {ulp:.2e})")
+    assert err <= 2 * ulp + 5e-7
+    torch.testing.assert_close(tok.double(), logits[..., N:], atol=1e-4, rtol=1e-5)

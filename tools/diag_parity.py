@@ -17,16 +17,18 @@ for which, B, N, M, wseed, xseed in cases:
     m.load_state_dict(sd)
     m = m.eval().cuda()
     x, cat = synthetic_clouds(B, N, xseed)
+    xc, catc = synthetic_clouds(B, N, xseed + 100)       # calibration batch != evaluation batch (no cut sits exactly on a z)
     with torch.no_grad():
-        m(x.cuda(), cat.cuda()) if which == "seg" else m(x.cuda())
+        m(xc.cuda(), catc.cuda()) if which == "seg" else m(xc.cuda())
     models.freeze_boundaries(m)
-    for mode_name, knn_mode, ds_mode in (("default", 0, 0), ("exact-kernels", 1, 1)):
+    from samble_b200 import blocks
+    for mode_name, knn_mode, ds_exact in (("default", 0, True), ("3xtf32-ds", 0, False)):
         L.lib().samble_set_knn_mode(knn_mode)
-        L.lib().samble_set_ds_mode(ds_mode)
+        blocks.DS_EXACT = ds_exact
         t = time.time()
         rep = harness.forward_parity(m, sd, cfg, x, cat, which=which)
         L.lib().samble_set_knn_mode(0)
-        L.lib().samble_set_ds_mode(0)
+        blocks.DS_EXACT = True
         key = f"{which}_B{B}_N{N}_{mode_name}"
         out[key] = rep
         print(key, f"({time.time() - t:.1f}s):", harness.brief(rep), flush=True)
