@@ -71,7 +71,7 @@ def fill_state_dict_(sd: Dict[str, Tensor], seed: int = 0, sharpen: float = 1.0)
 # --------------------------------------------------------------------------
 
 
-def knn_parity(idx: Tensor, ref_idx: Tensor, a: Tensor, b: Tensor, rel_band: float = 2e-5) -> dict:
+def knn_parity(idx: Tensor, ref_idx: Tensor, a: Tensor, b: Tensor, rel_band: float = 2e-5, cancel_ulps: float = 8.0) -> dict:
     """Tie-aware kNN comparison.  a (B,Nq,C), b (B,Nr,C) are the RAW inputs.
 
     Exact position-wise match rate is reported; every mismatching row must agree as
@@ -85,6 +85,8 @@ def knn_parity(idx: Tensor, ref_idx: Tensor, a: Tensor, b: Tensor, rel_band: flo
     exact = (idx == ref_idx)
     bad_rows = (~exact.all(dim=-1)).nonzero()
     a64, b64 = a.double().cpu(), b.double().cpu()
+    mu = a64.mean(dim=1, keepdim=True)                              # the reference centres both clouds on a's mean (ops.py:23-29)
+    na, nb_ = ((a64 - mu) ** 2).sum(-1), ((b64 - mu) ** 2).sum(-1)   # |a'|^2, |b'|^2 up to the common scale
     unexplained = 0
     for bi, qi in bad_rows.tolist():
         d = ((b64[bi] - a64[bi, qi]) ** 2).sum(-1)                  # (Nr,)
@@ -93,7 +95,9 @@ def knn_parity(idx: Tensor, ref_idx: Tensor, a: Tensor, b: Tensor, rel_band: flo
             unexplained += 1
             continue
         kth = torch.sort(d)[0][k - 1]
-        band = rel_band * max(float(kth), 1e-30)
+        # two sources of fp32 indecision: a relative near-tie, and the cancellation of the reference's own distance
+        # formula |a|^2 + |b|^2 - 2ab (ops.py:35, torch.cdist's GEMM form): a few roundings of |a'|^2 + |b'|^2
+        band = max(rel_band * max(float(kth), 1e-30), cancel_ulps * 2.0 ** -24 * float(na[bi, qi] + nb_[bi].max()))
         # every element either side must be no worse than the k-th distance + band,
         # and the sequence must be sorted up to the band
         ok = bool((d[mine] <= kth + band).all()) and bool((d[ref] <= kth + band).all())
@@ -185,6 +189,8 @@ def ds_parity(score64: Tensor, amp: Tensor, cuts: Tensor, idx: Tensor, bin_mask:
     d_cut = (z.unsqueeze(-1) - cuts).abs().min(-1)[0] if cuts.numel() else torch.full_like(z, float("inf"))
     flips = my_bin != bin64
     bad_flips = flips & (d_cut > zband)
+    # a whole group of EQUAL scores (e.g. every point no neighbourhood contains: score 0) sits at one z and flips together
+    flip_groups = max([len(set(score64[b][flips[b]].tolist())) for b in range(B)] + [0])
     swaps = bad_swaps = wrong_bin = dup = 0
     for b in range(B):
         off = 0
@@ -214,7 +220,8 @@ def ds_parity(score64: Tensor, amp: Tensor, cuts: Tensor, idx: Tensor, bin_mask:
             high = (~ch) & (key > kth)               # passed over although above it
             swaps += int(low.sum()) + int(high.sum())
             bad_swaps += int((low & (key < kth - tol - 2.0 ** -23 * kth)).sum()) + int((high & (key > kth + tol + 2.0 ** -23 * kth)).sum())
-    return dict(points=B * N, bin_flips=int(flips.sum()), unexplained_bin_flips=int(bad_flips.sum()), topk_swaps=swaps,
+    return dict(points=B * N, bin_flips=int(flips.sum()), distinct_flipped_scores_per_cloud=flip_groups,
+                unexplained_bin_flips=int(bad_flips.sum()), topk_swaps=swaps,
                 unexplained_topk_swaps=bad_swaps, chosen_outside_bin=wrong_bin, duplicate_rows=dup,
                 max_eps=float(eps.max()), median_eps=float(eps.median()))
 

@@ -17,7 +17,8 @@ import torch
 from oracle import samble_oracle as O
 from samble_b200 import blocks, models, ops
 from samble_b200.config import cls_config, seg_config
-from samble_b200.testing import (fill_state_dict_, knn_parity, sampled_index_parity, synthetic_clouds,
+from oracle import harness
+from samble_b200.testing import (ds_parity, ds_scores_fp64, fill_state_dict_, knn_parity, sampled_index_parity, synthetic_clouds,
                                  synthetic_features)
 from tests.golden import make_golden as G
 
@@ -92,7 +93,8 @@ def test_ds_row_stats_and_edge_score(B, N, nb, sharp):
     assert torch.equal(rm2, rowmax) and torch.equal(rs2, rowsum)
 
 
-@pytest.mark.parametrize("B,N,nb,M", [(4, 2048, 4, 1024), (4, 1024, 4, 512), (3, 1024, 6, 512), (2, 777, 6, 300), (1, 8192, 4, 4096)])
+@pytest.mark.parametrize("B,N,nb,M", [(4, 2048, 4, 1024), (4, 1024, 4, 512), (3, 1024, 6, 512), (2, 777, 6, 300), (1, 8192, 4, 4096),
+                                      (1, 16384, 4, 8192)])
 def test_ds_sample_vs_oracle(B, N, nb, M):
     g = torch.Generator().manual_seed(N * nb + M)
     score = torch.rand(B, N, generator=g) ** 3 * 1e-3
@@ -121,13 +123,57 @@ def test_ds_sample_vs_oracle(B, N, nb, M):
         assert int((k_mine - k_ref).abs().max()) <= 1 and int((k_mine - k_ref).abs().sum()) <= 2 * B, (k_mine, k_ref)
         idx_tf = O.generating_downsampled_index(M, score.unsqueeze(1), mask, "topk", None, k_mine)
         rep = sampled_index_parity(s["idx"].unsqueeze(1), idx_tf, score.unsqueeze(1), k_mine)
-        assert rep["unexplained_bins"] == 0 and rep["exact_rate"] == 1.0, rep
+        # (exact score ties -- a few at N = 16384 with 2^24 distinct random floats -- are ordered lower index first here,
+        # arbitrarily by torch.sort: sampled_index_parity counts only differences it cannot attribute to them)
+        assert rep["unexplained_bins"] == 0 and rep["exact_rate"] >= (1.0 if N < 8192 else 0.999), rep
     assert bool((s["k"].sum(1) == M).all())
     for b in range(B):
         assert len(set(s["idx"][b].tolist())) == M                              # a sample, not a multiset
 
 
 # ---------------------------------------------------------------- blocks
+
+
+def _amp_excusing_knn_ties(x, sd, pre, cheap=False):
+    """(fp64 scores, amplification) for ds_parity; columns whose in-edge set differs between the native kNN and the
+    oracle's (an fp32 near-tie of two distances, adjudicated by the kNN tests) get an unbounded tolerance: one neighbour
+    more or less changes such a score by ~3 % (score = colsum / indeg^2), which says nothing about the scoring kernels."""
+    C = x.shape[1]
+    mine = ops.knn_indices(cu(x), 32).cpu().long()
+    _, theirs = O.knn(x.transpose(1, 2), x.transpose(1, 2), 32)
+    if cheap:             # large clouds: skip the fp64 N x N pass, take a typical amplification for sharpened logits
+        s64, amp = None, torch.full((x.shape[0], x.shape[2]), 100.0, dtype=torch.float64)
+    else:
+        s64, amp = ds_scores_fp64(x, sd[pre + "q_conv.weight"].view(C, C), sd[pre + "k_conv.weight"].view(C, C), sd[pre + "bin_tokens"][0], mine)
+    B, N = amp.shape
+    a = torch.zeros(B, N, N, dtype=torch.bool).scatter_(2, mine, True)
+    b = torch.zeros(B, N, N, dtype=torch.bool).scatter_(2, theirs, True)
+    touched = (a != b).any(dim=1)                                   # (B,N) columns
+    return s64, torch.where(touched, torch.full_like(amp, 1e15), amp), touched
+
+
+def _judge_against_reference_scores(ds, idx, x_ds, ref_score, ref_idx, ref_k, ref_x_ds, amp):
+    """One DownSampleToken decision against the REFERENCE's own fp32 scores of the same input (golden file or oracle):
+    every bin membership and every per-bin choice must be the one those scores dictate, except where they cannot
+    decide: a z-score within fp32 rounding of a cut (a freshly calibrated cut IS some point's z), keys closer than one
+    rounding of score + 1e-8, or scores closer than the reference's OWN fp32 error (16 roundings x the softmax's
+    amplification `amp`, testing.ds_scores_fp64; measured 1e-5 for the reference, 3e-6 for the native kernels).
+    Rows of x_ds are compared wherever the same point was chosen, unconditionally."""
+    cuts = ds.bin_boundaries[0].reshape(-1)[1:].cpu()
+    rep = ds_parity(ref_score[:, 0].double(), amp, cuts, idx, ds.bin_points_mask, ds.k_point_to_choose, ulps=16.0)
+    print(rep)
+    assert rep["unexplained_bin_flips"] == 0 and rep["unexplained_topk_swaps"] == 0, rep
+    assert rep["chosen_outside_bin"] == 0 and rep["duplicate_rows"] == 0, rep
+    assert rep["distinct_flipped_scores_per_cloud"] <= 8, rep     # only points (nearly) tied with a cut flip -- as whole tie groups
+    k_mine = ds.k_point_to_choose.cpu().long()
+    assert int((k_mine - ref_k.long()).abs().max()) <= 1 and bool((k_mine.sum(1) == idx.shape[-1]).all())
+    same = idx.cpu() == ref_idx                              # (B,1,M)
+    key = ref_score + 1e-8                                   # the reference's fp32 sort key: equal keys are ordered arbitrarily
+    tie = key.gather(2, idx.cpu()) == key.gather(2, ref_idx)
+    assert float((same | tie).float().mean()) >= 0.98, float((same | tie).float().mean())
+    ok = ((x_ds.cpu().double() - ref_x_ds.double()).abs() <= 2e-4 + 2e-4 * ref_x_ds.double().abs())       # (B,C,M)
+    assert bool(ok[same.expand_as(ok)].all()), "x_ds rows of identically chosen points differ"
+
 
 
 def _sd(N, M=None, seed=5, sharpen=4.0):
@@ -151,15 +197,14 @@ def test_blocks_golden():
         ds = m.block.downsample_list[0]
         for tag in ("calib", "frozen"):
             (x_ds, idx), _ = ds(cu(x128))
-            torch.testing.assert_close(ds.bin_boundaries[0].cpu(), torch.from_numpy(gold[f"ds0.{tag}.upper"]), rtol=1e-4, atol=1e-5)
-            torch.testing.assert_close(ds.attention_point_score.cpu(), torch.from_numpy(gold[f"ds0.{tag}.score"]), rtol=1e-4, atol=1e-9)
-            assert int((ds.k_point_to_choose.cpu() - torch.from_numpy(gold[f"ds0.{tag}.k"])).abs().max()) <= 1
-            gidx = torch.from_numpy(gold[f"ds0.{tag}.idx"])
-            overlap = np.mean([len(set(idx[b, 0].tolist()) & set(gidx[b, 0].tolist())) / gidx.shape[-1] for b in range(2)])
-            assert overlap >= 0.98, overlap
-            if torch.equal(idx.cpu(), gidx):
-                assert close_frac(x_ds, torch.from_numpy(gold[f"ds0.{tag}.x_ds"])) == 1.0
+            torch.testing.assert_close(ds.bin_boundaries[0].cpu(), torch.from_numpy(gold[f"ds0.{tag}.upper"]), rtol=1e-5, atol=1e-6)
+            gscore = torch.from_numpy(gold[f"ds0.{tag}.score"])
             torch.testing.assert_close(ds.bin_weights_beforerelu.cpu(), torch.from_numpy(gold[f"ds0.{tag}.w"]), atol=1e-5, rtol=1e-4)
+            _, amp, touched = _amp_excusing_knn_ties(x128, sd, "block.downsample_list.0.")
+            ok = (ds.attention_point_score.cpu()[:, 0] - gscore[:, 0]).abs() <= 5e-5 * gscore[:, 0].abs() + 1e-30
+            assert bool((ok | touched).all()) and int(touched.sum()) <= 8, (int((~ok).sum()), int(touched.sum()))
+            _judge_against_reference_scores(ds, idx, x_ds, gscore, torch.from_numpy(gold[f"ds0.{tag}.idx"]),
+                                            torch.from_numpy(gold[f"ds0.{tag}.k"]), torch.from_numpy(gold[f"ds0.{tag}.x_ds"]), amp)
             ds.dynamic_boundaries_enable = False
         xyz_up, xyz_dn = synthetic_features(2, 3, N, 64), synthetic_features(2, 3, N // 2, 65)
         dn = synthetic_features(2, 128, N // 2, 66)
@@ -178,27 +223,48 @@ def test_blocks_vs_oracle(N):
         y = m.block.feature_learning_layer_list[0](cu(x128))
         assert close_frac(y, O.n2p_attention(sd, "block.feature_learning_layer_list.0.", x128, 32)) >= 0.9995
         ds, st = m.block.downsample_list[0], O.DSState(True)
+        pre = "block.downsample_list.0."
         for it in range(2):
             (x_ds, idx), _ = ds(cu(x128))
-            ref = O.downsample_token(sd, "block.downsample_list.0.", x128, N // 2, 32, 4, st)
-            torch.testing.assert_close(ds.bin_boundaries[0].cpu(), ref["boundaries"][0], rtol=1e-4, atol=1e-5)
-            # 3xTF32 projections / row statistics: the logit error (~1e-6 of sum|q_c k_c|) is amplified by exp() when the
-            # sharpened logits reach |l| ~ 100; measured median 1e-4, max 5e-4 (tools/probe_ds_precision.py), with
-            # no change of the sampled sets relative to the all-fp32 kernels.
-            assert close_frac(ds.attention_point_score, ref["score"], atol=1e-30, rtol=1e-3) >= 0.995
+            ref = O.downsample_token(sd, pre, x128, N // 2, 32, 4, st)
+            torch.testing.assert_close(ds.bin_boundaries[0].cpu(), ref["boundaries"][0], rtol=1e-5, atol=1e-6)
             assert tuple(ds.bin_points_mask.shape) == tuple(ref["mask"].shape) and ds.bin_points_mask.dtype == torch.bool
-            assert float((ds.bin_points_mask.cpu() != ref["mask"]).float().mean()) < 2e-3
-            assert int((ds.k_point_to_choose.cpu() - ref["k"]).abs().max()) <= 2
-            overlap = np.mean([len(set(idx[b, 0].tolist()) & set(ref["idx"][b, 0].tolist())) / (N // 2) for b in range(B)])
-            assert overlap >= 0.99, overlap
             assert close_frac(ds.attention_bins_beforesoftmax, ref["token_logits"]) == 1.0
-            if torch.equal(idx.cpu(), ref["idx"]):
-                assert close_frac(x_ds, ref["x_ds"]) == 1.0
+            # the exact-product GEMM (csrc/xgemm.cu) puts the native score within a few fp32 roundings of the fp64 value
+            s64, amp, touched = _amp_excusing_knn_ties(x128, sd, pre)
+            big = s64 > 1e-30                                 # (below that the fp32 probabilities underflow)
+            rel = (ds.attention_point_score.cpu().double()[:, 0] - s64).abs()[big] / s64[big]
+            assert float(rel.max()) <= 2e-5, float(rel.max())
+            _judge_against_reference_scores(ds, idx, x_ds, ref["score"], ref["idx"], ref["k"], ref["x_ds"], amp)
             ds.dynamic_boundaries_enable, st.dynamic = False, False
         M = N // 2
         xyz_up, xyz_dn, dn = synthetic_features(B, 3, N, 74), synthetic_features(B, 3, M, 75), synthetic_features(B, 128, M, 76)
         up = m.block.upsample_list[0](cu(x128), ((cu(dn), None, cu(xyz_dn)), (None, None)), cu(xyz_up))
         assert close_frac(up, O.upsample_interpolation(sd, "block.upsample_list.0.", x128, dn, xyz_up, xyz_dn, 3)) == 1.0
+
+
+@pytest.mark.parametrize("N", [8192, 16384])
+def test_downsample_block_large_clouds(N):
+    """BASELINE config 4 sizes: one DownSampleToken layer (N -> N/2) against the oracle, which needs ~6 GB of dense
+    N x N temporaries at 16384 where the native path needs O(N K)."""
+    cfg = seg_config(M=(N // 2, N // 4))
+    m = models.ShapeNetModel(cfg)
+    sd = fill_state_dict_(m.state_dict(), seed=9, sharpen=4.0)
+    m.load_state_dict(sd)
+    ds = m.block.downsample_list[0].eval().to(DEV)
+    x = synthetic_features(1, 128, N, 77)
+    pre = "block.downsample_list.0."
+    st = O.DSState(True)
+    with torch.no_grad():
+        for it in range(2):
+            (x_ds, idx), _ = ds(cu(x))
+            ref = O.downsample_token(sd, pre, x, N // 2, 32, 4, st)
+            torch.testing.assert_close(ds.bin_boundaries[0].cpu(), ref["boundaries"][0], rtol=1e-5, atol=1e-6)
+            _, amp, touched = _amp_excusing_knn_ties(x, sd, pre, cheap=True)
+            ok = (ds.attention_point_score.cpu()[:, 0] - ref["score"][:, 0]).abs() <= 2e-4 * ref["score"][:, 0].abs() + 1e-30
+            assert bool((ok | touched).all()), int((~(ok | touched)).sum())
+            _judge_against_reference_scores(ds, idx, x_ds, ref["score"], ref["idx"], ref["k"], ref["x_ds"], amp)
+            ds.dynamic_boundaries_enable, st.dynamic = False, False
 
 
 @pytest.mark.parametrize("B,N,K,Cin,C1,C2,gt", [(2, 300, 32, 3, 64, 64, "center_diff"), (1, 515, 16, 64, 64, 128, "center_diff"),
@@ -291,9 +357,37 @@ def test_models_golden(which):
                                    for b in range(c["B"])])
                 assert overlap >= (0.97 if i == 0 else 0.9), (tag, i, overlap)   # chained: reported as a rate
                 agree &= same
-            if agree:                                            # chained agreement: logits must match too
+            if agree:                                            # free-running chained agreement: logits match too
                 assert close_frac(y, torch.from_numpy(gold[f"{tag}.logits"]), atol=2e-3, rtol=2e-3) >= 0.999
             models.freeze_boundaries(m)
+    # ... and unconditionally: every decision adjudicated in fp64, every logit within tolerance once the decisions are
+    # forced into the oracle (oracle/harness.py)
+    sd = fill_state_dict_(m.cpu().state_dict(), seed=c["wseed"], sharpen=4.0)
+    m = m.to(DEV)
+    x2, cat2 = synthetic_clouds(c["B"], c["N"], c["xseed"] + 50)       # not the calibration batch: no cut sits on a z
+    rep = harness.forward_parity(m, sd, cfg, x2, cat2, which=which)
+    print(harness.brief(rep))
+    harness.assert_report(rep)
+
+
+@pytest.mark.parametrize("which,B,N,M", [("seg", 16, 2048, (1024, 512)), ("cls", 32, 1024, (512, 256))])
+def test_full_size_forward_vs_oracle(which, B, N, M):
+    """BASELINE configs 3 and 2 at full size against the CPU oracle (teacher-forced protocol, oracle/harness.py)."""
+    cfg = (seg_config if which == "seg" else cls_config)(M=M)
+    m = (models.ShapeNetModel if which == "seg" else models.ModelNetModel)(cfg)
+    sd = fill_state_dict_(m.state_dict(), seed=3, sharpen=4.0)
+    m.load_state_dict(sd)
+    m = m.eval().to(DEV)
+    xc, catc = synthetic_clouds(B, N, 105)
+    x, cat = synthetic_clouds(B, N, 5)
+    with torch.no_grad():
+        m(cu(xc), cu(catc)) if which == "seg" else m(cu(xc))
+    models.freeze_boundaries(m)
+    rep = harness.forward_parity(m, sd, cfg, x, cat, which=which)
+    print(harness.brief(rep))
+    harness.assert_report(rep)
+    for d in rep["ds"]:
+        assert d["score_rel_err_vs_fp64"]["native_max"] <= 2e-5, d["score_rel_err_vs_fp64"]
 
 
 def test_seg_forward_full_size_properties():
@@ -303,8 +397,9 @@ def test_seg_forward_full_size_properties():
     cfg, m, _ = _sd(2048, M=(1024, 512), seed=3, sharpen=4.0)
     x, cat = synthetic_clouds(16, 2048, 5)
     x, cat = cu(x), cu(cat)
+    xc, catc = synthetic_clouds(16, 2048, 105)
     with torch.no_grad():
-        m(x, cat)                                                # calibration batch
+        m(cu(xc), cu(catc))                                      # calibration batch (another one: no cut sits exactly on a z)
         models.freeze_boundaries(m)
         y1 = m(x, cat)
         idx1 = [ds.idx.clone() for ds in m.block.downsample_list]
@@ -316,11 +411,12 @@ def test_seg_forward_full_size_properties():
             assert all(len(set(ds.idx[b, 0].tolist())) == M for b in range(16))
             assert bool((ds.k_point_to_choose.sum(1) == M).all())
         ys = m(x[4:8], cat[4:8])                                 # a shard alone == the same clouds in the batch
-        # every native kernel is per-cloud; cuBLAS may pick another GEMM split for another batch size, so
-        # allow fp32 near-tie flips (the reference shows the same B-dependence, SURVEY 8e caveat 2)
+        # every native kernel is per-cloud; the few library GEMMs left (STN / category vectors) may pick another split for
+        # another batch size, so fp32 near-tie flips are possible (the reference shows the same B-dependence, SURVEY 8e
+        # caveat 2): measured identical here, asserted >= 0.99
         for a, ds in zip(idx1, m.block.downsample_list):
             ov = np.mean([len(set(a[4 + b, 0].tolist()) & set(ds.idx[b, 0].tolist())) / a.shape[-1] for b in range(4)])
-            assert ov >= 0.9, ov
+            assert ov >= 0.99, ov
 
 
 @pytest.mark.parametrize("mode", ["random", "uniform"])
