@@ -1,16 +1,20 @@
 #!/usr/bin/env python
 """Benchmark of the SAMBLE hot path on B200 (contract: README of the task / DESIGN.md section 6).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--points N]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload seg|cls|knn_ds] [--batch B | --global-batch G] [--points N]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference ...        # the reference's CPU algorithm (oracle port) on host cores
 
-A "step" is one SAMBLE ShapeNetPart segmentation forward (BASELINE config 3: per-GPU batch of B=16
-clouds, N=2048 points, k=32, downsample 2048->1024->512, eval mode, frozen bin boundaries, topk
-sampling) on synthetic clouds with seeded weights.  `value` = clouds/s with inputs resident in HBM;
-`e2e` = the same forward called with HOST (pinned) inputs and a host copy of the logits, copies timed.
-The batch is sharded by cloud across ranks with no collective on the path (weak scaling).
-One JSON line is printed by rank 0.
+Workloads (BASELINE.json configs):
+  seg     (default; configs 3 and 5) one SAMBLE ShapeNetPart segmentation forward: per-GPU batch of B=16 clouds
+          (or --global-batch G split over the ranks: config 5, strong scaling), N=2048, k=32, 2048->1024->512
+  cls     (config 2) one SAMBLE ModelNet40 classification forward, B=32/GPU, N=1024, 1024->512->256, nb=6
+  knn_ds  (config 4) micro-benchmark at N=8192 and N=16384: ops.knn (C=3 and C=128, k=32) and one DownSampleToken
+          layer (N -> N/2), us per batch with the roofline of each, the CPU oracle beside it at B=1
+All in eval mode with frozen bin boundaries and topk sampling, on synthetic clouds with seeded weights.
+`value` = clouds/s with inputs resident in HBM (whole step replayed as one CUDA graph); `e2e` = the same forward fed
+from HOST (pinned) buffers with a host copy of the result, every copy inside the timed region.  The batch is sharded
+by cloud across ranks with no collective on the path.  One JSON line is printed by rank 0.
 """
 from __future__ import annotations
 
@@ -26,74 +30,144 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC, UNIT = "clouds/sec SAMBLE seg fwd (N=2048)", "clouds/s"
+METRICS = {"seg": "clouds/sec SAMBLE seg fwd (N=2048)", "cls": "clouds/sec SAMBLE cls fwd (N=1024)",
+           "knn_ds": "kNN+sampling us/batch (N=8192, 16384)"}
+UNIT = "clouds/s"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=16, help="clouds per GPU per step")
-    ap.add_argument("--points", type=int, default=2048)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="seg", choices=["seg", "cls", "knn_ds"])
+    ap.add_argument("--batch", type=int, default=None, help="clouds per GPU per step (default 16 seg / 32 cls)")
+    ap.add_argument("--global-batch", type=int, default=None, help="total clouds per step, split over the ranks (strong scaling)")
+    ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--cpu-sample-batch", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.points = a.points or (1024 if a.workload == "cls" else 2048)
+    return a
 
 
-def workload_config(args, world):
-    return {"workload": f"SAMBLE ShapeNetPart seg forward, B={args.batch}/GPU N={args.points} k=32 "
-                        f"M=[{args.points // 2},{args.points // 4}] nb=4, eval, frozen boundaries, sample_mode=topk",
-            "global_batch": args.batch * world, "points": args.points, "parallelism": f"cloud-sharded x{world}",
+def per_rank_batch(args, world):
+    if args.global_batch is not None:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        return args.global_batch // world
+    return args.batch or (32 if args.workload == "cls" else 16)
+
+
+def workload_config(args, world, B):
+    N = args.points
+    if args.workload == "seg":
+        w = (f"SAMBLE ShapeNetPart seg forward, B={B}/GPU N={N} k=32 M=[{N // 2},{N // 4}] nb=4, eval, frozen boundaries, "
+             f"sample_mode=topk")
+    elif args.workload == "cls":
+        w = (f"SAMBLE ModelNet40 cls forward, B={B}/GPU N={N} k=32 M=[{N // 2},{N // 4}] nb=6, eval, frozen boundaries, "
+             f"sample_mode=topk")
+    else:
+        w = "kNN (C=3, C=128; k=32) + DownSampleToken (N -> N/2) micro-benchmark at N=8192 and N=16384"
+    return {"workload": w, "global_batch": B * world, "points": N, "parallelism": f"cloud-sharded x{world}",
             "l2": "256 MiB scratch write between timed steps (L2 flush)"}
+
+
+def build_model(workload, N):
+    from samble_b200 import models
+    from samble_b200.config import cls_config, seg_config
+    from samble_b200.testing import fill_state_dict_
+
+    cfg = (seg_config if workload == "seg" else cls_config)(M=(N // 2, N // 4))
+    model = (models.ShapeNetModel if workload == "seg" else models.ModelNetModel)(cfg)
+    sd = fill_state_dict_(model.state_dict(), seed=1, sharpen=4.0)
+    model.load_state_dict(sd)
+    return cfg, model, sd
 
 
 # ------------------------------------------------------------------------------- CPU arm
 
 
-def cpu_reference_rate(batch, points, steps, warmup):
+def cpu_reference_rate(workload, batch, points, steps, warmup):
     """The reference's algorithm (oracle port: dense cdist/topk/softmax on ATen CPU) on host cores."""
     from oracle import samble_oracle as O
-    from samble_b200 import models
-    from samble_b200.config import seg_config
-    from samble_b200.testing import fill_state_dict_, synthetic_clouds
+    from samble_b200.testing import synthetic_clouds
 
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core it can use
     torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    cfg = seg_config(M=(points // 2, points // 4))
-    sd = fill_state_dict_(models.ShapeNetModel(cfg).state_dict(), seed=1, sharpen=4.0)
+    cfg, _, sd = build_model(workload, points)
     x, cat = synthetic_clouds(batch, points, seed=2)
     states = [O.DSState(True), O.DSState(True)]
+    fwd = (lambda: O.seg_forward(sd, cfg, x, cat, states)) if workload == "seg" else (lambda: O.cls_forward(sd, cfg, x, states))
     times = []
     with torch.no_grad():
-        O.seg_forward(sd, cfg, x, cat, states)          # calibration
+        fwd()                                           # calibration
         for s in states:
             s.dynamic = False
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.seg_forward(sd, cfg, x, cat, states)
+            fwd()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
     return batch / dt, dt
 
 
+def cpu_knn_ds(N, reps=1):
+    """oracle ops.knn (C=3, C=128) and downsample_token at B=1 (the reference needs ~6 GB of N x N temporaries per cloud
+    at N=16384): seconds per call."""
+    from oracle import samble_oracle as O
+    from samble_b200.testing import synthetic_features
+
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    _, _, sd = build_model("seg", N)
+    out = {}
+    with torch.no_grad():
+        for C in (3, 128):
+            a = synthetic_features(1, N, C, 3)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                O.knn(a, a, 32)
+            out[f"knn_c{C}_s"] = (time.perf_counter() - t0) / reps
+        x = synthetic_features(1, 128, N, 4)
+        st = O.DSState(True)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.downsample_token(sd, "block.downsample_list.0.", x, N // 2, 32, 4, st)
+        out["downsample_token_s"] = (time.perf_counter() - t0) / reps
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = args.cpu_sample_batch
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    rate, dt = cpu_reference_rate(B, args.points, steps, warmup)
-    cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, max(1, args.gpus)),
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"seg forward of B={B} clouds N={args.points} per step, {steps} timed steps "
-                                       f"(reference is pure Python/ATen; its CPU path = oracle port, bit-exact to it)"},
+    world = max(1, args.gpus)
+    B = per_rank_batch(args, world)
+    cores = max(1, len(os.sched_getaffinity(0)))
+    if args.workload == "knn_ds":
+        res = {str(N): cpu_knn_ds(N) for N in (8192, 16384)}
+        line = {"impl": "reference", "metric": METRICS["knn_ds"], "value": res["8192"]["downsample_token_s"] * 1e6, "unit": "us/batch",
+                "n_gpus": args.gpus, "steps": 1, "warmup": 0, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, 1), "results_s_per_call_B1": res,
+                "cpu_baseline": {"value": res["8192"]["downsample_token_s"] * 1e6, "unit": "us/batch", "cores": cores, "kind": "port",
+                                 "sample": "oracle knn (C=3, C=128) and downsample_token at B=1, N=8192 and 16384, one call each"},
+                "e2e": {"value": res["8192"]["downsample_token_s"] * 1e6, "unit": "us/batch", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    # a bounded sample of the same workload: the SAME per-GPU batch as the native arm, few steps
+    steps, warmup = max(1, min(args.steps, 3)), 1
+    rate, dt = cpu_reference_rate(args.workload, B, args.points, steps, warmup)
+    line = {"impl": "reference", "metric": METRICS[args.workload], "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch is not None else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, B),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{args.workload} forward of B={B} clouds N={args.points} per step (one rank's share), {steps} timed "
+                                       f"steps after {warmup} warm-up (reference is pure Python/ATen; its CPU path = the oracle port, "
+                                       f"bit-exact to it)"},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -149,12 +223,7 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
-def knn_census(B, N):
-    """feature-space kNN calls of one seg forward: (Nq, Nr, C) x count."""
-    return [(N, N, 64, 1), (N, N, 128, 3), (N // 2, N // 2, 128, 3), (N // 4, N // 4, 128, 1)]
-
-
-def linear_census(model, x, cat):
+def linear_census(run_model):
     """Algorithmic bytes / FLOPs of the point-wise linear layers of one forward: every call of ops.linear /
     ops.linear_pool is intercepted once and its operands counted (activations in + weights + activations out
     (+ residual); 2*M*K*Nout FLOPs)."""
@@ -184,89 +253,128 @@ def linear_census(model, x, cat):
 
     ops.linear, ops.linear_pool = lin, pool
     try:
-        model(x, cat)
+        run_model()
         torch.cuda.synchronize()
     finally:
         ops.linear, ops.linear_pool = real_linear, real_pool
     return tot
 
 
-def downsample_block_ms(model, x, cat, reps=3):
-    """Device time of the DownSampleToken blocks of one forward (their kNN, scoring, sampler and selected-row
-    attention): BASELINE's secondary figure 'kNN+sampling us/batch' and the 'kNN+DownSample path' of SURVEY 8d."""
+def ds_flops(n, m, d=128, nb=4, k=32):
+    """feature kNN 2 N^2 C + q/k/v 6 N D^2 + QK^T 2 N (N+nb) D + edge pass 2 N K D + selected rows 2 M (N+nb) D."""
+    return 2.0 * n * n * d + 6.0 * n * d * d + 2.0 * n * (n + nb) * d + 2.0 * n * k * d + 2.0 * m * (n + nb) * d
+
+
+def graphed_us(fn, reps=20, flush=None):
+    """device time of fn() replayed as ONE CUDA graph (median of reps), us"""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.no_grad(), torch.cuda.graph(g):
+        fn()
+    for _ in range(3):
+        g.replay()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def knn_sampling_path(model, run_model, B, N, nb, pk, pk_src, flush):
+    """The north-star path (BASELINE.json's secondary metric, SURVEY 8d's 'kNN + DownSample path'): both DownSampleToken
+    blocks of the step -- feature kNN + q/k/v + QK^T row statistics + edge scores + bins / k / per-bin top-k + selected
+    rows x V -- replayed as one CUDA graph on the inputs they see inside the model."""
     ds_list = list(model.block.downsample_list)
-    spans = []
-    originals = [ds.forward for ds in ds_list]
-
-    def wrap(fn):
-        def timed(*a, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = fn(*a, **k)
-            e1.record()
-            spans.append((e0, e1))
-            return out
-        return timed
-
-    for ds, fn in zip(ds_list, originals):
-        ds.forward = wrap(fn)
+    seen = {}
+    hooks = [ds.register_forward_pre_hook(lambda mod, a, i=i: seen.__setitem__(i, tuple(t.detach().clone() if torch.is_tensor(t) else t for t in a)))
+             for i, ds in enumerate(ds_list)]
     try:
-        for _ in range(reps):
-            model(x, cat)
-        torch.cuda.synchronize()
+        run_model()
     finally:
-        for ds in ds_list:
-            del ds.forward                       # back to the class method
-    return sum(a.elapsed_time(b) for a, b in spans) / reps
+        for h in hooks:
+            h.remove()
+
+    def both():
+        for i, ds in enumerate(ds_list):
+            ds(*seen[i])
+
+    us = graphed_us(both, flush=flush)
+    flops = (ds_flops(N, N // 2, nb=nb) + ds_flops(N // 2, N // 4, nb=nb)) * B
+    ach = flops / (us * 1e-6) / 1e12
+    bf16 = pk["bf16_tflops_sustained"]
+    # what the tensor pipe actually executes per algorithmic product: the kNN runs 1 + 3 bf16 passes (threshold, collect),
+    # the exact-product GEMMs 10 digit products (q/k/v projection and QK^T), the selected-row attention 3 tf32 (= 6 bf16-rate) units
+    def executed(n, m, d=128):
+        return 4 * 2.0 * n * n * d + 10 * (6.0 * n * d * d + 2.0 * n * n * d) + 6 * 2.0 * m * n * d * 2
+    ex = (executed(N, N // 2) + executed(N // 2, N // 4)) * B / (us * 1e-6) / 1e12
+    return {"kernel": "kNN + DownSampleToken path (both blocks, CUDA-graph replay)", "bound": "tensor", "achieved": ach, "peak": bf16,
+            "unit": "TFLOP/s", "frac": ach / bf16, "traffic": None, "peak_source": pk_src + ", bf16 sustained (every MMA on this path is kind::f16)",
+            "us_per_batch": us, "clouds": B, "algorithmic_gflop_per_batch": flops / 1e9,
+            "executed_bf16_tflops": ex, "executed_frac_of_peak": ex / bf16,
+            "note": "achieved = ALGORITHMIC fp32 FLOPs (SURVEY 8d: 3.68 GFLOP per seg cloud) / graph-replayed device time. The path is "
+                    "fp32-exact by construction: the tensor pipe executes 4x (kNN: bf16 split passes) to 10x (exact-product digit GEMMs) "
+                    "the algorithmic products, so `executed_frac_of_peak` is the pipe utilisation and `frac` the price of exactness"}
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per step of `kernel`, from the committed ncu --set full capture
-    (profiles/r1_traffic.json, written by tools/summarize_ncu.py traffic); None if that kernel was not captured."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if not os.path.exists(p):
-        return None
-    with open(p) as f:
-        return json.load(f).get("dram_bytes_per_step", {}).get(kernel)
-
-
-def knn_sampling_block(ds_ms, B, N, pk):
-    """BASELINE.json's secondary metric and SURVEY 8d's 'kNN + DownSample path': both DownSampleToken blocks of the
-    step (feature kNN + q/k/v + QK^T row statistics + edge scores + bins / k / per-bin top-k + selected rows x V).
-    Algorithmic FLOPs per cloud from SURVEY 8d: kNN 2*N^2*C plus DS 6*N*D^2 + 2*N*(N+nb)*D + 2*N*K*D + 2*M*(N+nb)*D, for
-    N -> N/2 and N/2 -> N/4 (3.68 GFLOP at N=2048).  Peak = tf32 tensor rate (half the measured bf16 rate); the
-    kernels spend 3 tf32 MMAs per fp32-class product (linear layers, QK^T) or 2 passes (kNN), stated so the fraction
-    can be read either way."""
-    def ds_flops(n, m, d=128, nb=4, k=32):
-        return 2.0 * n * n * d + 6.0 * n * d * d + 2.0 * n * (n + nb) * d + 2.0 * n * k * d + 2.0 * m * (n + nb) * d
-
-    flops = (ds_flops(N, N // 2) + ds_flops(N // 2, N // 4)) * B
-    tf32_peak = pk["bf16_tflops_sustained"] / 2
-    ach = flops / (ds_ms * 1e-3) / 1e12
-    return {"us_per_batch": ds_ms * 1e3, "clouds": B, "algorithmic_gflop_per_batch": flops / 1e9, "achieved_tflops": ach,
-            "tf32_peak_tflops": tf32_peak, "frac_of_tf32_peak": ach / tf32_peak,
-            "note": "both DownSampleToken blocks (2048->1024, 1024->512) incl. their feature kNN, eager launches"}
-
-
-def roofline_of(dom, ms, census, B, N, pk):
-    """Roofline block for the dominant kernel family of the step (DESIGN.md section 5 states the per-unit figures)."""
+def linear_roofline(ms, census, pk):
+    """The point-wise linear layers (linear_tma_kernel): 3xTF32 => fp32-equivalent tensor peak = tf32 peak / 3."""
     sec = ms * 1e-3
-    if dom.startswith("linear"):
-        # fp32 point-wise layers, K <= 1024: 2*K*Nout/(4*(K+Nout)) ~ 50-100 FLOP/B, i.e. memory-side at fp32-class
-        # tensor throughput (3 tf32 MMAs per product); reported against HBM, with the tensor-pipe share beside it
-        ach = census["bytes"] / sec / 1e9
-        t = ncu_traffic(dom)
-        return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                "traffic": t, "algorithmic_bytes_per_step": census["bytes"], "calls_per_step": census["calls"],
-                "tensor_tflops_3xtf32": 3 * census["flops"] / sec / 1e12,
-                "note": "all linear_tma launches of the step; achieved = (X + W + Y [+ residual]) bytes / their summed duration"}
-    if dom.startswith("knn_tc") or dom.startswith("knn_select") or dom.startswith("knn_rerank"):
-        flops = sum(2.0 * nq * nr * (c + 8) * cnt for nq, nr, c, cnt in knn_census(B, N)) * B
-        ach = flops / sec / 1e12
-        return {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"] / 2, "unit": "TFLOP/s",
-                "frac": ach / (pk["bf16_tflops_sustained"] / 2), "traffic": ncu_traffic(dom),
-                "note": "tf32 distance GEMM of one pass; peak = half the measured bf16 rate (kind::tf32 issues at half the bf16 rate)"}
-    return {"bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": ncu_traffic(dom)}
+    tf32 = pk["bf16_tflops_sustained"] / 2
+    ach = census["flops"] / sec / 1e12
+    return {"kernel": "linear_tma_kernel (all point-wise linear layers of the step)", "bound": "tensor", "achieved": ach, "peak": tf32 / 3,
+            "unit": "TFLOP/s (fp32-equivalent)", "frac": ach / (tf32 / 3), "ms_per_step": ms, "calls_per_step": census["calls"],
+            "algorithmic_gb_per_step": census["bytes"] / 1e9, "hbm_gbs": census["bytes"] / sec / 1e9,
+            "flop_per_byte": census["flops"] / census["bytes"],
+            "note": "3 kind::tf32 MMAs per fp32-class product: peak = (bf16 sustained / 2) / 3; the layers sit above the 3xTF32 ridge "
+                    "(35 FLOP/B), so the tensor pipe is the binding roof"}
+
+
+def run_knn_ds(args, dev, pk, pk_src, flush):
+    """BASELINE config 4."""
+    from samble_b200 import blocks, ops
+    from samble_b200.config import seg_config
+    from samble_b200.testing import fill_state_dict_, synthetic_features
+    from samble_b200 import models
+
+    out = {}
+    bf16 = pk["bf16_tflops_sustained"]
+    for N in (8192, 16384):
+        B = 8 if N == 8192 else 4                       # >= 2 waves of 128-row tiles on 148 SMs
+        res = {"B": B}
+        for C in (3, 128):
+            a = synthetic_features(B, N, C, 3).to(dev)
+            us = graphed_us(lambda: ops.knn(a, a, 32), flush=flush)
+            flops = 2.0 * N * N * C * B
+            res[f"knn_c{C}"] = {"us_per_batch": us, "algorithmic_tflops": flops / (us * 1e-6) / 1e12,
+                                 "bound": "fp32 pipe" if C == 3 else "tensor",
+                                 "frac": (N * N * (C + 1) * B / (us * 1e-6)) / (148 * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6) if C == 3
+                                 else flops / (us * 1e-6) / 1e12 / bf16}
+        cfg = seg_config(M=(N // 2, N // 4))
+        m = models.ShapeNetModel(cfg)
+        m.load_state_dict(fill_state_dict_(m.state_dict(), seed=1, sharpen=4.0))
+        ds = m.block.downsample_list[0].eval().to(dev)
+        x = synthetic_features(B, 128, N, 4).to(dev)
+        with torch.no_grad():
+            ds(x)
+        ds.dynamic_boundaries_enable = False
+        us = graphed_us(lambda: ds(x), flush=flush)
+        fl = ds_flops(N, N // 2) * B
+        res["downsample_token"] = {"us_per_batch": us, "algorithmic_tflops": fl / (us * 1e-6) / 1e12, "bound": "tensor",
+                                   "frac": fl / (us * 1e-6) / 1e12 / bf16}
+        out[str(N)] = res
+    return out
 
 
 def run_native(args):
@@ -274,8 +382,7 @@ def run_native(args):
 
     from samble_b200 import _lib as L
     from samble_b200 import models
-    from samble_b200.config import seg_config
-    from samble_b200.testing import fill_state_dict_, synthetic_clouds
+    from samble_b200.testing import synthetic_clouds
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -287,18 +394,44 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = False          # stock GEMMs stay true fp32
     torch.backends.cudnn.allow_tf32 = False
-    B, N = args.batch, args.points
-    cfg = seg_config(M=(N // 2, N // 4))
-    model = models.ShapeNetModel(cfg)
-    model.load_state_dict(fill_state_dict_(model.state_dict(), seed=1, sharpen=4.0))
+    pk, pk_src = peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = L.lib()
+
+    if args.workload == "knn_ds":
+        if rank == 0:
+            sampler = ClockSampler(local)
+            sampler.start()
+            res = run_knn_ds(args, dev, pk, pk_src, flush)
+            sampler.stop_flag = True
+            sampler.join()
+            line = {"metric": METRICS["knn_ds"], "value": res["8192"]["downsample_token"]["us_per_batch"], "unit": "us/batch", "n_gpus": 1,
+                    "steps": 20, "warmup": 5, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                    "data": "synthetic", "config": workload_config(args, 1, res["8192"]["B"]), "clocks": sampler.result(),
+                    "results": res, "gpu_launches": int(lib.samble_launch_count())}
+            if not args.no_cpu_baseline:
+                cpu = {str(N): cpu_knn_ds(N) for N in (8192, 16384)}
+                line["cpu_baseline"] = {"value": cpu["8192"]["downsample_token_s"] * 1e6, "unit": "us/batch (B=1)",
+                                        "cores": torch.get_num_threads(), "kind": "port", "results_s_per_call_B1": cpu,
+                                        "sample": "oracle knn (C=3, C=128) and downsample_token at B=1, one call each"}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    B, N = per_rank_batch(args, world), args.points
+    seg = args.workload == "seg"
+    cfg, model, _ = build_model(args.workload, N)
     model = model.eval().to(dev)
+    nb = cfg.feature_learning_block.downsample.bin.num_bins[0]
     # every rank owns its own shard of the global batch: clouds [rank*B, (rank+1)*B)
     xh, cath = synthetic_clouds(B * world, N, seed=2)
     xh, cath = xh[rank * B:(rank + 1) * B].contiguous().pin_memory(), cath[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    xc, catc = synthetic_clouds(B, N, seed=1002)            # calibration batch
     x, cat = xh.to(dev), cath.to(dev)
-    out_h = torch.empty(B, 50, N, dtype=torch.float32).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    lib = L.lib()
+    ins = (x, cat) if seg else (x,)
+    ins_h = (xh, cath) if seg else (xh,)
 
     def barrier():
         if world > 1:
@@ -318,50 +451,51 @@ def run_native(args):
             e.record()
         barrier()
         ms = sum(s.elapsed_time(e) for s, e in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        mine = torch.tensor([ms], dtype=torch.float64, device=dev)
+        allms = [torch.zeros_like(mine) for _ in range(world)]
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), int(lib.samble_launch_count())
+            dist.all_gather(allms, mine)
+        else:
+            allms = [mine]
+        per_rank = [float(t.item()) for t in allms]
+        return max(per_rank), per_rank, int(lib.samble_launch_count())
 
     with torch.no_grad():
-        model(x, cat)                                       # calibration batch (dynamic boundaries)
+        model(xc.to(dev), catc.to(dev)) if seg else model(xc.to(dev))      # calibration batch (dynamic boundaries)
         models.freeze_boundaries(model)
         lib.samble_reset_launch_count()
-        model(x, cat)
+        y = model(*ins)
         launches_per_step = int(lib.samble_launch_count())
+        out_h = torch.empty(y.shape, dtype=torch.float32).pin_memory()
         run = model
-        if not args.no_graph:
-            from samble_b200.runtime import GraphedForward
-
-            run = GraphedForward(model, x, cat)             # whole step = one graph launch
-
-        def step_resident():
-            run(x, cat)
-
         pipe = None
         if not args.no_graph:
-            from samble_b200.runtime import HostPipeline
+            from samble_b200.runtime import GraphedForward, HostPipeline
 
+            run = GraphedForward(model, *ins)              # whole step = one graph launch
             pipe = HostPipeline(run)       # the serving loop a host-resident caller uses: D2H of step i overlaps step i+1
+
+        def step_resident():
+            run(*ins)
 
         def step_e2e():
             # every timed step contains: H2D of its inputs, the forward, and the wait for the PREVIOUS step's D2H (which
             # ran beside this step's compute); the last step also waits for its own (tail_fn) -- all copies are timed
             if pipe is None:
-                y = model(xh.to(dev, non_blocking=True), cath.to(dev, non_blocking=True))
-                out_h.copy_(y, non_blocking=True)
+                yy = model(*[t.to(dev, non_blocking=True) for t in ins_h])
+                out_h.copy_(yy, non_blocking=True)
             else:
-                pipe.submit(xh, cath)
+                pipe.submit(*ins_h)
                 pipe.wait_previous()
 
         for _ in range(max(3, args.warmup)):
             step_resident()
         sampler = ClockSampler(local)
         sampler.start()
-        ms, launches = timed(step_resident, args.steps)
+        ms, per_rank, launches = timed(step_resident, args.steps)
         for _ in range(2):
             step_e2e()
-        ms_e2e, _ = timed(step_e2e, args.steps, tail_fn=(pipe.wait_all if pipe is not None else None))
+        ms_e2e, per_rank_e2e, _ = timed(step_e2e, args.steps, tail_fn=(pipe.wait_all if pipe is not None else None))
         sampler.stop_flag = True
         sampler.join()
 
@@ -372,14 +506,13 @@ def run_native(args):
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(3):
-            model(x, cat)
+            model(*ins)
         t1.record()
         torch.cuda.synchronize()
         prof = L.profile_report()
         L.profile(False)
-        prof_total_ms = t0.elapsed_time(t1) / 3
-        census = linear_census(model, x, cat)
-        ds_ms = downsample_block_ms(model, x, cat)
+        census = linear_census(lambda: model(*ins))
+        north = knn_sampling_path(model, lambda: model(*ins), B, N, nb, pk, pk_src, flush) if rank == 0 else None
 
     value = B * world * args.steps / (ms / 1e3)
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
@@ -388,27 +521,27 @@ def run_native(args):
             dist.destroy_process_group()
         return
 
-    pk, pk_src = peaks()
     native_ms = {k: v[1] / 3 for k, v in prof.items()}
-    dom = max(native_ms, key=native_ms.get)
     step_ms = ms / args.steps                     # the graph-replayed step the kernels' event-timed durations are set against
-    roof = {"kernel": dom, "ms_per_step": native_ms[dom], "share_of_step": native_ms[dom] / step_ms,
-            "launches_per_step": prof[dom][0] // 3, "peak_source": pk_src}
-    roof.update(roofline_of(dom, native_ms[dom], census, B, N, pk))
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": sampler.result(),
+    north["share_of_step"] = north["us_per_batch"] * 1e-3 / step_ms
+    line = {"metric": METRICS[args.workload], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch is not None else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, B), "clocks": sampler.result(),
+            "per_rank_ms_per_step": [round(t / args.steps, 4) for t in per_rank],
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(xh.numel() * 4 + cath.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
+                    "per_rank_ms_per_step": [round(t / args.steps, 4) for t in per_rank_e2e],
+                    "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in ins_h)), "d2h_bytes_per_step": int(out_h.numel() * 4)},
             "gpu_launches": launches_per_step * args.steps, "launch_mode": "eager" if args.no_graph else "cuda_graph",
-            "roofline": roof,
-            "knn_plus_sampling": knn_sampling_block(ds_ms, B, N, pk),
+            "roofline": north,
+            "roofline_linear": linear_roofline(native_ms.get("linear_tma_kernel", 0.0) or 1e-9, census, pk),
             "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(native_ms.items(), key=lambda kv: -kv[1])},
             "native_share_of_step": min(1.0, sum(native_ms.values()) / step_ms)}
     if not args.no_cpu_baseline and world == 1:
-        rate, dt = cpu_reference_rate(args.cpu_sample_batch, N, 2, 1)
+        bs = min(B, 16)
+        rate, dt = cpu_reference_rate(args.workload, bs, N, args.cpu_steps, 1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"oracle seg forward, B={args.cpu_sample_batch} N={N}, 2 timed steps after 1 warm-up"}
+                                "sample": f"oracle {args.workload} forward, B={bs} N={N}, {args.cpu_steps} timed steps after 1 warm-up"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -242,6 +242,17 @@ int samble_ds_row_stats_exact(const void* q_planes, const float* q_scale, const 
                               float* rowmax, float* rowsum, float* token_logits, void* ws, size_t ws_bytes,
                               samble_stream_t stream);
 
+/* models/downsample.py:242-252 fused flash-style (csrc/ds_attend.cu): out[b, m, :] = softmax(q[idx[b,m]] [k | k_tok]^T / sqrt(D)) . [v ; v_tok]
+ * for the M selected points, from the digit planes of q and k (samble_digits), the fp32 v rows (B, N, C; row pitch ldv),
+ * the row statistics and token logits of samble_ds_row_stats_exact and v_tok (nb, C).  No (B, M, N) tensor is formed:
+ * S = Q_sel K^T tiles live in TMEM, P = exp(S/sqrt(D) - max)/sum goes through shared memory as the A operand of the
+ * second MMA.  out: (B, M, C) rows.  ws: V^T as bf16 hi/lo planes. */
+size_t samble_ds_attend_rows_workspace_bytes(int B, int N, int C);
+int samble_ds_attend_rows(const void* q_planes, const float* q_scale, const void* k_planes, const float* k_scale,
+                          const float* v, long long ldv, const long long* idx, const float* rowmax, const float* rowsum,
+                          const float* token_logits, const float* v_tok, int B, int N, int M, int D, int C, int nb,
+                          float* out, void* ws, size_t ws_bytes, samble_stream_t stream);
+
 /* models/downsample.py:300-344 (idx_mode sparse_col_sqr) without the dense mask:
  *   score[j] = sum_{i : j in kNN(i)} softmax_i[j] / indeg(j)^2,  NaN -> 0.
  * Only the N*K edges are evaluated; accumulation order is fixed (deterministic). */

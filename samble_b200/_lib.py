@@ -56,6 +56,8 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_xgemm": (_i, (_p, _p, _i, _i, _p, _p, _i, _i, _i, _p, _ll, _p, _i, _i, _p)),
     "samble_ds_row_stats_exact_workspace_bytes": (_sz, (_i, _i)),
     "samble_ds_row_stats_exact": (_i, (_p, _p, _p, _p, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p)),
+    "samble_ds_attend_rows_workspace_bytes": (_sz, (_i, _i, _i)),
+    "samble_ds_attend_rows": (_i, (_p, _p, _p, _p, _p, _ll, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p)),
     "samble_ds_edge_score_workspace_bytes": (_sz, (_i, _i)),
     "samble_ds_edge_score": (_i, (_p, _ll, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p)),
     "samble_zscore": (_i, (_p, _i, _i, _p, _p)),

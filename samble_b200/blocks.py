@@ -301,10 +301,12 @@ class DownSampleToken(nn.Module):
         v_tok = torch.matmul(tok, self.v_conv.weight.view(C, C).t())
 
         idx = ops.knn_indices(x, self.K, ordered=False)                                       # neighbor_mask's kNN (:301)
-        k_split = ops.split_operand(k) if (self.M % 128 == 0 and N <= 4096) else None         # for the M selected rows
+        k_split = None
         if exact:
-            rowmax, rowsum, tok_logits = ops.ds_row_stats_exact(ops.digits(q, amax, 0), ops.digits(k, amax, 1), q, k_tok)
+            qd, kd = ops.digits(q, amax, 0), ops.digits(k, amax, 1)
+            rowmax, rowsum, tok_logits = ops.ds_row_stats_exact(qd, kd, q, k_tok)
         else:
+            k_split = ops.split_operand(k) if (self.M % 128 == 0 and N <= 4096) else None     # for the M selected rows
             rowmax, rowsum, tok_logits = ops.ds_row_stats(q, k, k_tok, k_split=k_split)
         score = ops.ds_edge_score(q, k, rowmax, rowsum, idx)                   # (B,N)
         self.attention_point_score = score.view(B, 1, N)
@@ -323,17 +325,21 @@ class DownSampleToken(nn.Module):
         self.bin_weights_beforerelu = s["w_raw"]
 
         # attention rows of the selected points over all N+nb keys, times V (:242-252).  The softmax statistics of every
-        # row are already known (pass 1), so the rows are formed directly in the GEMM epilogue and applied to V by a
-        # second per-cloud GEMM (tcgen05, 3xTF32); the nb token columns are a (B,M,nb) side computation.
+        # row are already known (pass 1), so one flash-style kernel forms S = Q_sel K^T in TMEM, turns it into
+        # probabilities in registers and feeds them to the second MMA through shared memory (csrc/ds_attend.cu): no
+        # (B,M,N) tensor exists.
         sel = s["idx"]
         scale = math.sqrt(D)
-        q_sel, m_sel, s_sel, tok_mix = ops.ds_select_rows(q, rowmax, rowsum, tok_logits, v_tok, sel)
-        if self.M % 128 == 0 and N <= 4096:        # (samble_cloud_matmul contracts at most 4096 keys)
-            att = ops.cloud_matmul(q_sel, k, row_max=m_sel, row_sum=s_sel, logit_div=scale, w_split=k_split)     # (B,M,N)
-            x_ds = ops.cloud_matmul(att, v.transpose(1, 2), residual=tok_mix)                     # (B,M,C)
+        if exact:
+            x_ds = ops.ds_attend_rows(qd, kd, v, sel, rowmax, rowsum, tok_logits, v_tok)          # (B,M,C)
         else:
-            att = torch.exp(torch.matmul(q_sel, k.transpose(1, 2)) / scale - m_sel.unsqueeze(-1)) / s_sel.unsqueeze(-1)
-            x_ds = torch.matmul(att, v) + tok_mix
+            q_sel, m_sel, s_sel, tok_mix = ops.ds_select_rows(q, rowmax, rowsum, tok_logits, v_tok, sel)
+            if self.M % 128 == 0 and N <= 4096:        # (samble_cloud_matmul contracts at most 4096 keys)
+                att = ops.cloud_matmul(q_sel, k, row_max=m_sel, row_sum=s_sel, logit_div=scale, w_split=k_split)     # (B,M,N)
+                x_ds = ops.cloud_matmul(att, v.transpose(1, 2), residual=tok_mix)                     # (B,M,C)
+            else:
+                att = torch.exp(torch.matmul(q_sel, k.transpose(1, 2)) / scale - m_sel.unsqueeze(-1)) / s_sel.unsqueeze(-1)
+                x_ds = torch.matmul(att, v) + tok_mix
         x_ds = x_ds.transpose(1, 2)
 
         self.idx = index_down

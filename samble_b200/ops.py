@@ -513,6 +513,26 @@ def ds_row_stats_exact(qd: Digits, kd: Digits, q: Tensor, k_tok: Tensor):
     return rowmax, rowsum, tok
 
 
+def ds_attend_rows(qd: Digits, kd: Digits, v: Tensor, idx: Tensor, rowmax: Tensor, rowsum: Tensor, tok_logits: Tensor,
+                   v_tok: Tensor) -> Tensor:
+    """The attention rows of the selected points times V, flash-style (samble_ds_attend_rows; models/downsample.py:242-252):
+    qd/kd digit planes of q/k (B,N,D), v (B,N,C) fp32 rows (unit inner stride), idx (B,M) int64, row statistics (B,N),
+    tok_logits (B,N,nb), v_tok (nb,C) -> (B,M,C)."""
+    dev = L.need_cuda(v, idx, rowmax, rowsum, tok_logits, v_tok)
+    B, N, Cc = v.shape
+    M, nb, D = idx.shape[1], tok_logits.shape[-1], qd.C
+    if v.stride(2) != 1 or v.stride(0) != N * v.stride(1):
+        v = v.contiguous()
+    idx, v_tok = idx.contiguous(), _f32(v_tok, "v_tok").contiguous()
+    out = torch.empty(B, M, Cc, dtype=torch.float32, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.samble_ds_attend_rows_workspace_bytes(B, N, Cc), dev)
+    L.check(lib.samble_ds_attend_rows(L.ptr(qd.planes), L.ptr(qd.scale), L.ptr(kd.planes), L.ptr(kd.scale), L.ptr(v), v.stride(1),
+                                      L.ptr(idx), L.ptr(rowmax), L.ptr(rowsum), L.ptr(tok_logits), L.ptr(v_tok), B, N, M, D, Cc, nb,
+                                      L.ptr(out), L.ptr(ws), ws.numel(), L.stream()), "samble_ds_attend_rows")
+    return out
+
+
 # Two tensor-core kernels compute the row statistics: the row-statistics epilogue of linear_tma.cu (default:
 # samble_ds_row_stats_fast; TMA-fed, shares k's tf32 split with cloud_matmul) and ds_rowstats_tc.cu (cp.async loaders).
 # Tests flip this to cross-check one against the other.

@@ -189,8 +189,11 @@ def ds_parity(score64: Tensor, amp: Tensor, cuts: Tensor, idx: Tensor, bin_mask:
     d_cut = (z.unsqueeze(-1) - cuts).abs().min(-1)[0] if cuts.numel() else torch.full_like(z, float("inf"))
     flips = my_bin != bin64
     bad_flips = flips & (d_cut > zband)
-    # a whole group of EQUAL scores (e.g. every point no neighbourhood contains: score 0) sits at one z and flips together
-    flip_groups = max([len(set(score64[b][flips[b]].tolist())) for b in range(B)] + [0])
+    # points the reference's fp32 z-score cannot tell apart (equal scores -- e.g. 0 for every point no neighbourhood
+    # contains -- or scores far below mean/std's resolution) sit at ONE fp32 z and flip together
+    s32 = score64.float()
+    z32 = (s32 - s32.mean(1, keepdim=True)) / s32.std(1, unbiased=False, keepdim=True)
+    flip_groups = max([len(set(z32[b][flips[b]].tolist())) for b in range(B)] + [0])
     swaps = bad_swaps = wrong_bin = dup = 0
     for b in range(B):
         off = 0
@@ -220,7 +223,7 @@ def ds_parity(score64: Tensor, amp: Tensor, cuts: Tensor, idx: Tensor, bin_mask:
             high = (~ch) & (key > kth)               # passed over although above it
             swaps += int(low.sum()) + int(high.sum())
             bad_swaps += int((low & (key < kth - tol - 2.0 ** -23 * kth)).sum()) + int((high & (key > kth + tol + 2.0 ** -23 * kth)).sum())
-    return dict(points=B * N, bin_flips=int(flips.sum()), distinct_flipped_scores_per_cloud=flip_groups,
+    return dict(points=B * N, bin_flips=int(flips.sum()), distinct_flipped_z_per_cloud=flip_groups,
                 unexplained_bin_flips=int(bad_flips.sum()), topk_swaps=swaps,
                 unexplained_topk_swaps=bad_swaps, chosen_outside_bin=wrong_bin, duplicate_rows=dup,
                 max_eps=float(eps.max()), median_eps=float(eps.median()))
