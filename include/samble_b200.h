@@ -63,6 +63,11 @@ int samble_selftest_tc_gemm(const float* A, const float* B, int K, float* D, con
  * cycles_out[cta] = SM cycles from first issue to completion (measured tensor-pipe ceiling of the SS form). */
 int samble_selftest_mma_rate(int n_tile, int iters, int ctas, long long* cycles_out, samble_stream_t stream);
 
+/* extended probe: kind 1 = bf16 (kind::f16, K=16 per MMA), 2 = tf32 (K=8); the MMAs rotate over n_acc accumulators of n_tile columns
+ * (n_acc * n_tile <= 512) and n_a distinct A tiles -- the issue pattern of the exact-product GEMM. */
+int samble_selftest_mma_rate_ex(int kind, int n_tile, int n_acc, int n_a, int iters, int ctas, long long* cycles_out,
+                                samble_stream_t stream);
+
 /* ---------------------------------------------------------------- kNN ----------
  * utils/ops.py:17-44  knn(a, b, k) -> (distance, idx).
  * a: queries, b: candidates; element (bi, n, c) lives at base + bi*a_sb + n*a_sn + c*a_sc

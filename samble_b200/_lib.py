@@ -30,6 +30,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_profile_report": (_i, (C.c_char_p, _sz)),
     "samble_selftest_tc_gemm": (_i, (_p, _p, _i, _p, _p, _p, _p)),
     "samble_selftest_mma_rate": (_i, (_i, _i, _i, _p, _p)),
+    "samble_selftest_mma_rate_ex": (_i, (_i, _i, _i, _i, _i, _i, _p, _p)),
     "samble_set_knn_mode": (None, (_i,)),
     "samble_knn_workspace_bytes": (_sz, (_i, _i, _i, _i)),
     "samble_knn": (_i, (_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _sz, _p)),

@@ -149,10 +149,11 @@ __global__ void __launch_bounds__(kDaThreads, 1) ds_attend_rows_kernel(const __g
     __syncwarp();
   } else if (warp == 4) {
     // ================= MMA issuer: S(t0); then S(t+1), P V(t) =================
-    if (tc::elect_one()) {
+    // whole warp walks the loops (uniform control flow keeps descriptors in uniform registers), one elected lane issues
+    {
       const uint32_t idesc_s = tc::instr_desc(1, 128, kDaTileN);
       const uint32_t idesc_o = tc::instr_desc(1, 128, 128);
-      const uint32_t q_base = tc::smem_u32(sQ);
+      const uint32_t q_base = tc::smem_u32(sQ), k_base = tc::smem_u32(sK);
       int s = 0, ph = 0;
       auto issue_s = [&](int u) {                               // u = tile ordinal within this CTA
         const int set = u & 1, use = u >> 1;
@@ -160,25 +161,26 @@ __global__ void __launch_bounds__(kDaThreads, 1) ds_attend_rows_kernel(const __g
         tc::tc_fence_after();
         const uint32_t g0 = tmem + set * kDaDigits * kDaTileN;
         for (int kt = 0; kt < nkt; ++kt) {
-          uint64_t qd[kDaDigits];
-#pragma unroll
-          for (int d = 0; d < kDaDigits; ++d) qd[d] = tc::smem_desc_sw128(q_base + (d * nkt + kt) * 16384);
 #pragma unroll
           for (int p = 0; p < kDaDigits; ++p) {
             tc::mbar_wait(&kfull[s], ph);
             tc::tc_fence_after();
-            const uint64_t kd = tc::smem_desc_sw128(tc::smem_u32(sK + (size_t)s * 8192));
+            if (tc::elect_one()) {
+              const uint64_t kd = tc::smem_desc_sw128(k_base + s * 8192);
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) {
+              for (int k16 = 0; k16 < 4; ++k16) {
 #pragma unroll
-              for (int d = 0; d + p < kDaDigits; ++d)
-                tc::mma_bf16(g0 + (d + p) * kDaTileN, qd[d] + 2 * k16, kd + 2 * k16, idesc_s, p == 0 ? (uint32_t)((kt | k16) != 0) : 1u);
+                for (int d = 0; d + p < kDaDigits; ++d)
+                  tc::mma_bf16(g0 + (d + p) * kDaTileN, tc::smem_desc_sw128(q_base + (d * nkt + kt) * 16384) + 2 * k16, kd + 2 * k16, idesc_s,
+                               p == 0 ? (uint32_t)((kt | k16) != 0) : 1u);
+              }
+              tc::mma_commit(&kempty[s]);
+              if (p == kDaDigits - 1 && kt == nkt - 1) tc::mma_commit(&sfull[set]);
             }
-            tc::mma_commit(&kempty[s]);
+            __syncwarp();
             if (++s == kDaKSlots) { s = 0; ph ^= 1; }
           }
         }
-        tc::mma_commit(&sfull[set]);
       };
       tc::mbar_wait(qfull, 0);
       tc::tc_fence_after();
@@ -191,18 +193,20 @@ __global__ void __launch_bounds__(kDaThreads, 1) ds_attend_rows_kernel(const __g
         tc::mbar_wait(pfull, u & 1);
         tc::mbar_wait(vfull, u & 1);
         tc::tc_fence_after();
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) {
-          tc::mma_bf16(tmem_o, ph_d + 2 * k16, vh_d + 2 * k16, idesc_o, (uint32_t)((u | k16) != 0));
-          tc::mma_bf16(tmem_o, pl_d + 2 * k16, vh_d + 2 * k16, idesc_o, 1u);
-          tc::mma_bf16(tmem_o, ph_d + 2 * k16, vl_d + 2 * k16, idesc_o, 1u);
+          for (int k16 = 0; k16 < 4; ++k16) {
+            tc::mma_bf16(tmem_o, ph_d + 2 * k16, vh_d + 2 * k16, idesc_o, (uint32_t)((u | k16) != 0));
+            tc::mma_bf16(tmem_o, pl_d + 2 * k16, vh_d + 2 * k16, idesc_o, 1u);
+            tc::mma_bf16(tmem_o, ph_d + 2 * k16, vl_d + 2 * k16, idesc_o, 1u);
+          }
+          tc::mma_commit(pempty);
+          tc::mma_commit(vempty);
+          if (u == nt - 1) tc::mma_commit(ofull);
         }
-        tc::mma_commit(pempty);
-        tc::mma_commit(vempty);
+        __syncwarp();
       }
-      tc::mma_commit(ofull);
     }
-    __syncwarp();
   } else {
     // ================= warps 0-3: thread = selected row =================
     const int row = warp * 32 + lane;

@@ -139,6 +139,27 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Lean issue path.  Measured (tools/probe_mma_rate.py, tools/probe_xgemm.py): a 128 x 64 x 16 MMA takes 48 cycles
+// (shared-memory operand reads bound it), but an issuing warp that rebuilds 64-bit descriptors with ~15 uniform-ALU
+// instructions per MMA, or moves them through R2UR, issues one MMA per ~75 cycles and paces the kernel.  The high
+// word of a SW128 K-major descriptor is a constant and the low word is (address >> 4) | LBO, so an operand tile at a
+// compile-time offset from a base is ONE 32-bit add away: lo = lo_base + (byte offset >> 4).
+constexpr uint32_t kDescSw128Hi = 0x40004040u;     // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t smem_desc_sw128_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void mma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .b64 da, db;\n setp.ne.b32 p, %4, 0;\n mov.b64 da, {%1, %5};\n mov.b64 db, {%2, %5};\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescSw128Hi)
+      : "memory");
+}
+__device__ __forceinline__ void mma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .b64 da, db;\n setp.ne.b32 p, %4, 0;\n mov.b64 da, {%1, %5};\n mov.b64 db, {%2, %5};\n"
+      " tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescSw128Hi)
+      : "memory");
+}
 // mbarrier arrives when every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

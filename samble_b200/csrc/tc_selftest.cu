@@ -144,3 +144,74 @@ extern "C" int samble_selftest_mma_rate(int n_tile, int iters, int ctas, long lo
   SAMBLE_LAUNCHED("tc_mma_rate_kernel");
   return SAMBLE_OK;
 }
+
+// ---- extended rate probe: bf16 MMAs of 128 x NT x 16, rotating over NACC accumulators and NA distinct A tiles (the
+// exact-product GEMM pattern: one B box against several A digit planes into several accumulators).  Everything is a
+// compile-time pattern so that the descriptors stay in uniform registers and the loop is not issue-bound. ----
+namespace samble {
+template <int NT, int NACC, int NA>
+__global__ void __launch_bounds__(128) tc_mma_rate_ex_kernel(int iters, long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int p = tid; p < (4 * 16384 + NT * 128) / 16; p += 128) reinterpret_cast<uint4*>(base)[p] = make_uint4(0x3f803f80u, 0x3f003f00u, 0x3e803e80u, 0x40004000u);
+  tc::fence_proxy_async();
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = tc::instr_desc(1, 128, NT);
+    const uint64_t ad = tc::smem_desc_sw128(tc::smem_u32(base)), bd = tc::smem_desc_sw128(tc::smem_u32(base + 4 * 16384));
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        tc::mma_bf16(tmem + (k % NACC) * NT, ad + (k % NA) * (16384 >> 4) + 2 * k, bd + 2 * k, idesc, 1);
+    tc::mma_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    cycles_out[blockIdx.x] = clock64() - t0;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+template <int NT, int NACC, int NA>
+static void launch_rate_ex(int iters, int ctas, long long* out, cudaStream_t st) {
+  const size_t smem = 4 * 16384 + (size_t)NT * 128 + 2048;
+  cudaFuncSetAttribute(tc_mma_rate_ex_kernel<NT, NACC, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_mma_rate_ex_kernel<NT, NACC, NA><<<ctas, 128, smem, st>>>(iters, out);
+}
+}  // namespace samble
+
+extern "C" int samble_selftest_mma_rate_ex(int kind, int n_tile, int n_acc, int n_a, int iters, int ctas, long long* cycles_out,
+                                           samble_stream_t stream) {
+  SAMBLE_REQUIRE(cycles_out && iters > 0 && ctas > 0 && kind == 1, "samble_selftest_mma_rate_ex: bad arguments (kind 1 = bf16 only)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int key = n_tile * 100 + n_acc * 10 + n_a;
+  SAMBLE_PRE(st);
+  switch (key) {
+    case 6411: launch_rate_ex<64, 1, 1>(iters, ctas, cycles_out, st); break;
+    case 6441: launch_rate_ex<64, 4, 1>(iters, ctas, cycles_out, st); break;
+    case 6444: launch_rate_ex<64, 4, 4>(iters, ctas, cycles_out, st); break;
+    case 6414: launch_rate_ex<64, 1, 4>(iters, ctas, cycles_out, st); break;
+    case 12811: launch_rate_ex<128, 1, 1>(iters, ctas, cycles_out, st); break;
+    case 12841: launch_rate_ex<128, 4, 1>(iters, ctas, cycles_out, st); break;
+    case 12844: launch_rate_ex<128, 4, 4>(iters, ctas, cycles_out, st); break;
+    case 12814: launch_rate_ex<128, 1, 4>(iters, ctas, cycles_out, st); break;
+    case 25611: launch_rate_ex<256, 1, 1>(iters, ctas, cycles_out, st); break;
+    case 25621: launch_rate_ex<256, 2, 1>(iters, ctas, cycles_out, st); break;
+    case 25614: launch_rate_ex<256, 1, 4>(iters, ctas, cycles_out, st); break;
+    default: set_error("samble_selftest_mma_rate_ex: unsupported (n_tile, n_acc, n_a) = (%d, %d, %d)", n_tile, n_acc, n_a); return SAMBLE_E_INVALID;
+  }
+  SAMBLE_LAUNCHED("tc_mma_rate_ex_kernel");
+  return SAMBLE_OK;
+}

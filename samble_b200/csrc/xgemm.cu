@@ -39,7 +39,11 @@
 namespace samble {
 
 constexpr int kXgThreads = 192;
-constexpr int kXgStages = 8;          // B ring: 8 KB boxes [64 rows x 64 bf16]
+constexpr int kXgStageBytes = 4 * 8192;   // one B stage = the four digit boxes [64 rows x 64 bf16] of one K tile
+// ring depth: every stage costs the issuing threads a ~360-cycle mbarrier round trip (measured, tools/probe_xgemm.py:
+// "handshakes only" = 93 us for 65k stages), so a stage must carry far more MMA time than that: 40 MMAs = 1920 cycles.
+// (The first version used one 8 KB box per stage -- 4 to 16 MMAs -- and ran at 47 % tensor-pipe activity.)
+template <int EPI> constexpr int xg_stages() { return EPI == 1 ? 3 : 2; }
 constexpr int kXgTileN = 64;
 constexpr int kXgDigits = 4;
 constexpr int kXgSlabLd = 36;         // floats per staged row (pad 4: conflict-free 128-bit access)
@@ -138,19 +142,20 @@ struct XgMaps {
   CUtensorMap a[kXgDigits], b[kXgDigits];       // digit planes of A (boxes of 128 rows) and of B (boxes of 64 rows)
 };
 
-template <int EPI>
+template <int EPI, int NKT>
 __global__ void __launch_bounds__(kXgThreads, 1)
     xgemm_kernel(const __grid_constant__ XgMaps maps, XgArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int nkt = a.Cp >> 6;                                  // K tiles of 64 bf16 (128-byte rows)
+  constexpr int nkt = NKT;                                    // K tiles of 64 bf16 (128-byte rows): Cp = 64 * NKT
   uint8_t* sA = base;                                         // [plane][kt] tiles of 128 rows x 128 B
   uint8_t* sB = sA + (size_t)kXgDigits * nkt * 16384;         // ring
-  float* slab = reinterpret_cast<float*>(sB + (size_t)kXgStages * 8192);
+  constexpr int kStages = xg_stages<EPI>();
+  float* slab = reinterpret_cast<float*>(sB + (size_t)kStages * kXgStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(slab) + (EPI == 0 ? kXgSlabBytes : 0));
-  uint64_t* full = bars;                        // [kXgStages]
-  uint64_t* empty = bars + kXgStages;           // [kXgStages]
-  uint64_t* tfull = bars + 2 * kXgStages;       // [2]
+  uint64_t* full = bars;                        // [kStages]
+  uint64_t* empty = bars + kStages;             // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;         // [2]
   uint64_t* tempty = tfull + 2;                 // [2]
   uint64_t* afull = tempty + 2;                 // A row tile landed
   uint64_t* aempty = afull + 1;                 // ... no longer read by any MMA
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(kXgThreads, 1)
   const long long t0 = (long long)blockIdx.x * total / gridDim.x, t1 = (long long)(blockIdx.x + 1) * total / gridDim.x;
 
   if (tid == 0) {
-    for (int s = 0; s < kXgStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       tc::mbar_init(&full[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
@@ -182,10 +187,12 @@ __global__ void __launch_bounds__(kXgThreads, 1)
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 5) {
-    // ================= TMA producer =================
-    if (tc::elect_one()) {
-      tc::tma_prefetch_desc(&maps.a[0]);
-      tc::tma_prefetch_desc(&maps.b[0]);
+    // ================= TMA producer (whole warp loops, one elected lane issues) =================
+    {
+      if (tc::elect_one()) {
+        tc::tma_prefetch_desc(&maps.a[0]);
+        tc::tma_prefetch_desc(&maps.b[0]);
+      }
       int s = 0, ph = 0, aruns = 0;
       long long cur_rt = -1;
       for (long long item = t0; item < t1; ++item) {
@@ -194,34 +201,42 @@ __global__ void __launch_bounds__(kXgThreads, 1)
         const int b = (int)(rt / tpc), r0 = (int)(rt % tpc) * 128;
         if (rt != cur_rt) {
           tc::mbar_wait(aempty, (aruns & 1) ^ 1);             // MMAs of the previous row tile retired
-          tc::mbar_arrive_expect_tx(afull, (uint32_t)(kXgDigits * nkt) * 16384u);
-          for (int kt = 0; kt < nkt; ++kt) {
+          if (tc::elect_one()) {
+            tc::mbar_arrive_expect_tx(afull, (uint32_t)(kXgDigits * nkt) * 16384u);
+            for (int kt = 0; kt < nkt; ++kt) {
 #pragma unroll
-            for (int d = 0; d < kXgDigits; ++d) tc::tma_load_3d(sA + (size_t)(d * nkt + kt) * 16384, &maps.a[d], afull, kt * 64, r0, b);
+              for (int d = 0; d < kXgDigits; ++d) tc::tma_load_3d(sA + (size_t)(d * nkt + kt) * 16384, &maps.a[d], afull, kt * 64, r0, b);
+            }
           }
+          __syncwarp();
           cur_rt = rt;
           ++aruns;
         }
         const int bb = a.Bb > 1 ? b : 0;
         for (int kt = 0; kt < nkt; ++kt) {
+          tc::mbar_wait(&empty[s], ph ^ 1);
+          if (tc::elect_one()) {
+            tc::mbar_arrive_expect_tx(&full[s], (uint32_t)kXgStageBytes);
 #pragma unroll
-          for (int p = 0; p < kXgDigits; ++p) {
-            tc::mbar_wait(&empty[s], ph ^ 1);
-            tc::mbar_arrive_expect_tx(&full[s], 8192u);
-            tc::tma_load_3d(sB + (size_t)s * 8192, &maps.b[p], &full[s], kt * 64, ct * kXgTileN, bb);
-            if (++s == kXgStages) { s = 0; ph ^= 1; }
+            for (int p = 0; p < kXgDigits; ++p)
+              tc::tma_load_3d(sB + (size_t)s * kXgStageBytes + p * 8192, &maps.b[p], &full[s], kt * 64, ct * kXgTileN, bb);
           }
+          __syncwarp();
+          if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 4) {
     // ================= MMA issuer =================
-    if (tc::elect_one()) {
+    // The WHOLE warp walks the loop (uniform control flow: stage indices, phases and descriptors stay in uniform
+    // registers) and one elected lane issues each batch of MMAs + its commit.  With the loop inside `if (elect_one())`
+    // every descriptor went through R2UR moves in front of each UTCHMMA and the single issuing thread paced the
+    // kernel (ncu round 2: tensor pipe 47 % active, the epilogue warps idle 39 % of their samples on tfull).
+    {
       const uint32_t idesc = tc::instr_desc(1, 128, kXgTileN);              // bf16 x bf16 -> fp32
       int s = 0, ph = 0, aruns = 0, it = 0;
       long long cur_rt = -1;
-      const uint32_t a_base = tc::smem_u32(sA);
+      const uint32_t a_lo0 = tc::smem_desc_sw128_lo(tc::smem_u32(sA)), b_lo0 = tc::smem_desc_sw128_lo(tc::smem_u32(sB));
       for (long long item = t0; item < t1; ++item, ++it) {
         const long long rt = item / nct;
         const int set = it & 1, use = it >> 1;
@@ -233,31 +248,35 @@ __global__ void __launch_bounds__(kXgThreads, 1)
         tc::mbar_wait(&tempty[set], (use & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t g0 = tmem + set * kXgDigits * kXgTileN;            // accumulator G_g at g0 + g*64
+#pragma unroll
         for (int kt = 0; kt < nkt; ++kt) {
-          uint64_t ad[kXgDigits];
+          tc::mbar_wait(&full[s], ph);
+          tc::tc_fence_after();
+          if (tc::elect_one()) {
+            const uint32_t b_lo = b_lo0 + (uint32_t)s * (kXgStageBytes >> 4);
 #pragma unroll
-          for (int d = 0; d < kXgDigits; ++d) ad[d] = tc::smem_desc_sw128(a_base + (d * nkt + kt) * 16384);
+            for (int p = 0; p < kXgDigits; ++p) {                         // B digit p pairs with A digits 0 .. D-1-p
 #pragma unroll
-          for (int p = 0; p < kXgDigits; ++p) {                           // B digit p pairs with A digits 0 .. D-1-p
-            tc::mbar_wait(&full[s], ph);
-            tc::tc_fence_after();
-            const uint64_t bd = tc::smem_desc_sw128(tc::smem_u32(sB + (size_t)s * 8192));
+              for (int k16 = 0; k16 < 4; ++k16) {
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) {
-#pragma unroll
-              for (int d = 0; d + p < kXgDigits; ++d)
-                // the first write of every G_g happens with B digit 0 at the first K step
-                tc::mma_bf16(g0 + (d + p) * kXgTileN, ad[d] + 2 * k16, bd + 2 * k16, idesc, p == 0 ? (uint32_t)((kt | k16) != 0) : 1u);
+                for (int d = 0; d + p < kXgDigits; ++d)
+                  // (the first write of every G_g happens with B digit 0 at the first K step; every operand tile is a
+                  // compile-time offset from its base descriptor word: one 32-bit add per operand)
+                  tc::mma_bf16_lo(g0 + (d + p) * kXgTileN, a_lo0 + (d * nkt + kt) * 1024 + 2 * k16, b_lo + p * 512 + 2 * k16, idesc,
+                                  p == 0 ? (uint32_t)((kt | k16) != 0) : 1u);
+              }
             }
             tc::mma_commit(&empty[s]);
-            if (++s == kXgStages) { s = 0; ph ^= 1; }
+            if (kt == nkt - 1) {
+              tc::mma_commit(&tfull[set]);
+              if (item + 1 >= t1 || (item + 1) / nct != rt) tc::mma_commit(aempty);   // last item of this row tile
+            }
           }
+          __syncwarp();
+          if (++s == kStages) { s = 0; ph ^= 1; }
         }
-        tc::mma_commit(&tfull[set]);
-        if (item + 1 >= t1 || (item + 1) / nct != rt) tc::mma_commit(aempty);   // last item of this row tile
       }
     }
-    __syncwarp();
   } else {
     // ================= epilogue: thread = row =================
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
@@ -375,7 +394,7 @@ __global__ void __launch_bounds__(256) xgemm_ref_kernel(const __nv_bfloat16* __r
 }
 
 static size_t xg_smem_bytes(int nkt, int epi) {
-  return (size_t)kXgDigits * nkt * 16384 + (size_t)kXgStages * 8192 + (epi == 0 ? kXgSlabBytes : 0) + 512 + 1024;
+  return (size_t)kXgDigits * nkt * 16384 + (size_t)(epi ? xg_stages<1>() : xg_stages<0>()) * kXgStageBytes + (epi == 0 ? kXgSlabBytes : 0) + 512 + 1024;
 }
 
 static int launch_xgemm(const __nv_bfloat16* ap, const __nv_bfloat16* bp, const XgArgs& a, cudaStream_t st) {
@@ -387,7 +406,7 @@ static int launch_xgemm(const __nv_bfloat16* ap, const __nv_bfloat16* bp, const 
   }
   const int epi = a.stat_out ? 1 : 0;
   const size_t smem = xg_smem_bytes(a.Cp >> 6, epi);
-  auto kern = epi ? xgemm_kernel<1> : xgemm_kernel<0>;
+  auto kern = epi ? (a.Cp == 64 ? xgemm_kernel<1, 1> : xgemm_kernel<1, 2>) : (a.Cp == 64 ? xgemm_kernel<0, 1> : xgemm_kernel<0, 2>);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("xgemm smem attribute");
   const long long total = (long long)a.Ba * ceil_div(a.Ra, 128) * ceil_div(a.Rb, kXgTileN);
