@@ -122,6 +122,13 @@ int samble_gather_by_idx(const float* pcd, const void* idx, int idx_bits, int B,
 int samble_transpose(const float* in, long long in_batch_stride, long long in_row_stride, int B, int R, int C, float* out,
                      samble_stream_t stream);
 
+/* ---- backward of the gathers (the reference relies on ATen autograd of torch.gather, utils/ops.py:13,144).
+ * grad_points (B,N,C) / grad_pcd (B,C,N) must be zero-initialised (or hold a gradient to accumulate into); fp32 atomics. */
+int samble_index_points_backward(const float* grad_out, const void* idx, int idx_bits, int B, int N, int C, int R,
+                                 float* grad_points, samble_stream_t stream);
+int samble_gather_by_idx_backward(const float* grad_out, const void* idx, int idx_bits, int B, int C, int N, int M,
+                                  float* grad_pcd, samble_stream_t stream);
+
 /* utils/ops.py:125-133  neighbor_mask: dense 0/1 (B,N,N) from idx (B,N,K) (zeros + scatter_). */
 int samble_neighbor_mask(const void* idx, int idx_bits, int B, int N, int K, float* out, samble_stream_t stream);
 
@@ -197,6 +204,13 @@ int samble_n2p_attend(const float* q, const float* k, const float* v, long long 
                       const void* idx, int idx_bits, int B, int N, int C, int K, int heads,
                       const float* residual, long long ld_res, const float* scale, const float* shift,
                       float* out, long long ld_out, samble_stream_t stream);
+
+/* backward of samble_n2p_attend without the fused tail (models/attention.py:207-250 under autograd): grad_out (B,N,C) with leading
+ * dimension ld_go -> grad_q (written), grad_k / grad_v (ACCUMULATED with fp32 atomics: zero them first), all with leading
+ * dimension ld_g.  Recomputes the probabilities from q, k (no (B,N,K) tensor is saved by the forward pass). */
+int samble_n2p_attend_backward(const float* q, const float* k, const float* v, long long ld, const void* idx, int idx_bits,
+                               int B, int N, int C, int K, int heads, const float* grad_out, long long ld_go,
+                               float* grad_q, float* grad_k, float* grad_v, long long ld_g, samble_stream_t stream);
 
 /* --------------------------------------------------- DownSampleToken scoring ----
  * models/downsample.py:124-153: energy = q @ [k | k_tok] / sqrt(D), row softmax over

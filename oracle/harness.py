@@ -29,18 +29,23 @@ from samble_b200.testing import ds_parity, ds_scores_fp64, knn_parity
 
 @contextlib.contextmanager
 def record_decisions(log: List):
-    """Record (signature, idx) of every neighbour search the native blocks issue, in call order."""
-    real_knn, real_i3r = ops.knn_indices, ops.interpolate3_rows
+    """Record (signature, idx[, dist]) of every neighbour search the native path issues, in call order.  Every search
+    goes through ops._knn_strided (knn, knn_indices, group, select_neighbors, select_neighbors_interpolate) except the
+    fused 3-NN interpolation, which is asked separately for its neighbours."""
+    real_knn, real_i3r = ops._knn_strided, ops.interpolate3_rows
 
     inputs = getattr(log, "inputs", None)
 
-    def knn_indices(pcd, K, idx_dtype=torch.int32, ordered=True):
-        idx = real_knn(pcd, K, idx_dtype, ordered)
-        log.append(((pcd.shape[2], pcd.shape[2], pcd.shape[1], K), idx.detach().cpu().long()))
+    def _knn_strided(a, b, k, layout, want_dist, idx_dtype=torch.int64, ordered=True):
+        dist, idx = real_knn(a, b, k, layout, want_dist, idx_dtype, ordered)
+        pa, pb = (a.detach(), b.detach()) if layout == "bnc" else (a.detach().transpose(1, 2), b.detach().transpose(1, 2))
+        entry = ((pa.shape[1], pb.shape[1], pa.shape[2], k), idx.detach().cpu().long())
+        if want_dist:
+            entry = entry + ((-dist).detach().cpu(),)
+        log.append(entry)
         if inputs is not None:
-            pts = pcd.detach().transpose(1, 2).cpu()
-            inputs.append((pts, pts))
-        return idx
+            inputs.append((pa.cpu(), pb.cpu()))
+        return dist, idx
 
     def interpolate3_rows(xyz_up, xyz_sel, feat_rows, out):
         # the fused 3-NN interpolation does not return its neighbours: ask the same search for them
@@ -51,11 +56,11 @@ def record_decisions(log: List):
             inputs.append((xyz_up.detach().transpose(1, 2).cpu(), xyz_sel.detach().transpose(1, 2).cpu()))
         return real_i3r(xyz_up, xyz_sel, feat_rows, out)
 
-    ops.knn_indices, ops.interpolate3_rows = knn_indices, interpolate3_rows
+    ops._knn_strided, ops.interpolate3_rows = _knn_strided, interpolate3_rows
     try:
         yield log
     finally:
-        ops.knn_indices, ops.interpolate3_rows = real_knn, real_i3r
+        ops._knn_strided, ops.interpolate3_rows = real_knn, real_i3r
 
 
 class _Log(list):
@@ -170,6 +175,104 @@ def forward_parity(model, sd: Dict[str, torch.Tensor], cfg, x: torch.Tensor, cat
     report["logits_scale"] = float(y_ref.abs().max())
     report["finite"] = bool(torch.isfinite(y).all())
     return report
+
+
+def gradient_parity(model, sd: Dict[str, torch.Tensor], cfg, x: torch.Tensor, cat=None, *, which: str = "seg",
+                    device: str = "cuda:0", seed: int = 0) -> dict:
+    """one backward pass of the native differentiable path against the oracle's ATen autograd.
+
+    The native model runs with gradients enabled (its own mode: eval -> running-statistics BatchNorm, train -> batch
+    statistics, mirrored in the oracle via O.bn_training); its neighbour sets, 3-NN distances and sampled indices are
+    forced into the oracle (decisions carry no gradient on either side); the scalar loss is sum(logits * probe) with a
+    fixed random probe.  Returns per-tensor errors relative to the largest reference gradient entry of that tensor."""
+    ds_list = list(model.block.downsample_list)
+    for ds in ds_list:
+        if ds.dynamic_boundaries_enable or ds.bin_boundaries is None:
+            raise RuntimeError("gradient_parity: calibrate one batch and freeze the boundaries first")
+    from samble_b200._precision import strict_fp32
+
+    import torch.nn.functional as F
+
+    log = _Log()
+    masks: List[torch.Tensor] = []
+    real_lrelu = F.leaky_relu
+
+    def recording_lrelu(inp, negative_slope=0.01, inplace=False):
+        masks.append((inp.detach() > 0).cpu())
+        return real_lrelu(inp, negative_slope, inplace)
+
+    model.zero_grad(set_to_none=True)
+    xg = x.to(device).requires_grad_(True)
+    F.leaky_relu = recording_lrelu
+    try:
+        with record_decisions(log):
+            y = model(xg, cat.to(device)) if which == "seg" else model(xg)
+    finally:
+        F.leaky_relu = real_lrelu
+    y = y[0] if isinstance(y, tuple) else y
+    probe = torch.randn(y.shape, generator=torch.Generator().manual_seed(seed))
+    with strict_fp32():          # cuDNN's default lets convolution BACKWARD passes use TF32; the comparison is fp32 vs fp32
+        (y * probe.to(device)).sum().backward()
+    torch.cuda.synchronize()
+    mine = {n: p.grad.detach().cpu() for n, p in model.named_parameters() if p.grad is not None}
+    no_grad_params = [n for n, p in model.named_parameters() if p.requires_grad and p.grad is None]
+    mine_x = xg.grad.detach().cpu()
+    ds_idx = [ds.idx.cpu() for ds in ds_list]
+
+    def oracle_grads(dtype):
+        """the oracle's autograd in fp32 (the reference's arithmetic) or fp64 (the referee), same forced decisions"""
+        states = [O.DSState(False, [t.detach().cpu().to(dtype).clone() for t in ds.bin_boundaries]) for ds in ds_list]
+        sdg = {k: (v.detach().to(dtype).requires_grad_(True) if (v.is_floating_point() and "running_" not in k)
+                   else (v.detach().to(dtype) if v.is_floating_point() else v.detach().clone())) for k, v in sd.items()}
+        xr = x.detach().to(dtype).requires_grad_(True)
+        klog = [(e[0], e[1]) + ((e[2].to(dtype),) if len(e) > 2 else ()) for e in log]
+        with O.forcing(O.Forcing(knn_log=klog, ds_idx=ds_idx, keep_inputs=False, lrelu_masks=masks)) as f, O.bn_training(model.training):
+            y_ref = (O.seg_forward(sdg, cfg, xr, cat.to(dtype), states) if which == "seg" else O.cls_forward(sdg, cfg, xr, states))
+        (y_ref * probe.to(dtype)).sum().backward()
+        grads = {n: r.grad for n, r in sdg.items() if isinstance(r, torch.Tensor) and r.requires_grad and r.grad is not None}
+        return y_ref.detach(), grads, xr.grad, len(f.knn_log), len(f.lrelu_masks), f.lrelu_flips
+
+    y32, g32, x32, unforced, masks_left, flips32 = oracle_grads(torch.float32)
+    y64, g64, x64, _, _, flips64 = oracle_grads(torch.float64)
+    rep = dict(unforced_knn_calls=unforced, logits_close_frac=close_frac(y, y32), logits_close_frac_fp64=close_frac(y, y64),
+               params={}, missing=no_grad_params, lrelu_calls=len(masks), lrelu_masks_unconsumed=masks_left,
+               lrelu_elements=int(sum(m.numel() for m in masks)), lrelu_flips_vs_fp32=flips32, lrelu_flips_vs_fp64=flips64)
+    # per tensor: error against the fp64 referee, in units of the largest gradient entry of the WHOLE model for that kind
+    # of tensor would hide small tensors, and a tensor's own largest entry is meaningless where the true gradient is zero
+    # (a bias in front of a batch-statistics BatchNorm) -- so both are reported: `rel` (own scale) and `abs`.
+    scale_all = max(float(v.abs().max()) for v in g64.values())
+
+    def errs(g, r64, r32):
+        e_native = float((g.double() - r64).abs().max())
+        e_oracle = float((r32.double() - r64).abs().max())
+        own = float(r64.abs().max())
+        return dict(native=e_native, oracle32=e_oracle, own_scale=own, rel=e_native / max(own, 1e-30),
+                    rel_oracle32=e_oracle / max(own, 1e-30))
+
+    for n, r in g64.items():
+        if n not in mine:
+            rep["missing"].append(n)
+            continue
+        rep["params"][n] = errs(mine[n], r, g32[n])
+    rep["input"] = errs(mine_x, x64, x32)
+    rep["model_grad_scale"] = scale_all
+    rep["n_params"] = len(rep["params"])
+    return rep
+
+
+def assert_gradient_report(rep: dict, tol: float = 1e-4, noise: float = 8.0, floor: float = 1e-6) -> None:
+    """Every gradient tensor agrees with the fp64 referee within `tol` of its own largest entry, OR within `noise` times the
+    error the reference's own fp32 autograd makes on that tensor, OR -- tensors whose true gradient vanishes (a bias feeding a
+    batch-statistics BatchNorm) -- within `floor` of the model's largest gradient entry."""
+    assert rep["unforced_knn_calls"] == 0 and rep["lrelu_masks_unconsumed"] == 0
+    assert rep["lrelu_flips_vs_fp64"] <= 1e-5 * rep["lrelu_elements"] + 4, "forced LeakyReLU sides must be near-zero pre-activations only"
+    assert not rep["missing"], rep["missing"]
+    bad = {}
+    for n, e in list(rep["params"].items()) + [("<input>", rep["input"])]:
+        ok = e["native"] <= tol * e["own_scale"] or e["native"] <= noise * e["oracle32"] or e["native"] <= floor * rep["model_grad_scale"]
+        if not ok:
+            bad[n] = e
+    assert not bad, bad
 
 
 def assert_report(rep: dict, *, logits_frac: float = 1.0, knn_exact: float = 0.995) -> None:

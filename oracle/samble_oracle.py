@@ -56,11 +56,19 @@ class Forcing:
     (raw inputs + its own indices) / the `record` dict, so the decisions are compared stage by
     stage on IDENTICAL inputs with the tie-aware comparators of samble_b200.testing."""
 
-    def __init__(self, knn_log=None, ds_idx=None, keep_inputs: bool = True):
+    def __init__(self, knn_log=None, ds_idx=None, keep_inputs: bool = True, lrelu_masks=None):
         self.knn_log = list(knn_log or [])
         self.ds_idx = list(ds_idx or [])
         self.keep_inputs = keep_inputs
         self.knn_seen: List[dict] = []
+        self.lrelu_masks = None if lrelu_masks is None else list(lrelu_masks)     # (x > 0) per LeakyReLU call, call order
+        self.lrelu_flips = 0                                                        # forced sides that differ from the oracle's own
+
+    def take_lrelu(self, shape):
+        for n, m in enumerate(self.lrelu_masks):
+            if tuple(m.shape) == tuple(shape):
+                return self.lrelu_masks.pop(n)
+        return None
 
     def take_knn(self, sig):
         """-> (idx, dist or None) of the first unconsumed entry with this signature, or None.  An entry may carry the
@@ -117,7 +125,12 @@ def knn(a: Tensor, b: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     if forced is None:
         return own
     forced = forced.to(torch.int64)
-    return (neg.gather(2, forced) if fdist is None else -fdist), forced
+    mine = neg.gather(2, forced)
+    if fdist is None:
+        return mine, forced
+    # forced VALUES, own gradient (straight-through): under autograd (the f1 gradient tests) the distance keeps the
+    # reference's graph through cdist and the normalisation; without autograd this is exactly -fdist
+    return (mine + (-fdist - mine).detach() if mine.requires_grad else -fdist), forced
 
 
 def index_points(points: Tensor, idx: Tensor) -> Tensor:
@@ -298,15 +311,48 @@ def _conv(sd: SD, name: str, x: Tensor) -> Tensor:
     return F.conv2d(x, w) if w.dim() == 4 else F.conv1d(x, w)
 
 
+_BN_TRAINING = False
+
+
+class bn_training:
+    """with bn_training(True): BatchNorm normalises with the batch statistics (nn.BatchNorm in train mode, as under
+    train_shapenet.py:398; running statistics are not updated here).  Default: eval mode."""
+
+    def __init__(self, on: bool):
+        self.on = bool(on)
+
+    def __enter__(self):
+        global _BN_TRAINING
+        self.prev, _BN_TRAINING = _BN_TRAINING, self.on
+
+    def __exit__(self, *exc):
+        global _BN_TRAINING
+        _BN_TRAINING = self.prev
+
+
 def _bn(sd: SD, name: str, x: Tensor) -> Tensor:
-    """eval-mode BatchNorm (running statistics)."""
+    """BatchNorm: eval mode (running statistics) unless inside `bn_training(True)`."""
+    if _BN_TRAINING:
+        return F.batch_norm(x, None, None, sd[name + ".weight"], sd[name + ".bias"], True, 0.0, 1e-5)
     return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"],
                         sd[name + ".weight"], sd[name + ".bias"], False, 0.0, 1e-5)
 
 
+def _lrelu(x: Tensor) -> Tensor:
+    """LeakyReLU(0.2).  Under teacher forcing with recorded activation masks (gradient tests only) the side of the kink
+    is the one the implementation under test took: a pre-activation within fp32 rounding of zero changes the output by
+    ~1e-7 but the derivative by 0.8, i.e. it is one more discrete decision."""
+    if _FORCE is not None and _FORCE.lrelu_masks is not None:
+        m = _FORCE.take_lrelu(tuple(x.shape))
+        if m is not None:
+            _FORCE.lrelu_flips += int((m != (x > 0)).sum())
+            return torch.where(m, x, x * 0.2)
+    return F.leaky_relu(x, 0.2)
+
+
 def _cbl(sd: SD, name: str, x: Tensor) -> Tensor:
     """nn.Sequential(conv, bn, LeakyReLU(0.2)) as used all over the reference."""
-    return F.leaky_relu(_bn(sd, name + ".1", _conv(sd, name + ".0", x)), 0.2)
+    return _lrelu(_bn(sd, name + ".1", _conv(sd, name + ".0", x)))
 
 
 def edgeconv(sd: SD, pre: str, x: Tensor, K: int, group_type: str = "center_diff") -> Tensor:
@@ -330,7 +376,7 @@ def n2p_attention(sd: SD, pre: str, x: Tensor, K: int, heads: int = 4) -> Tensor
     att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(D), dim=-1)   # (B,H,N,1,K)
     y = (att @ v)[:, :, :, 0, :].permute(0, 2, 1, 3).reshape(B, N, C).permute(0, 2, 1)
     x = _bn(sd, pre + "bn1", x + y)
-    ff = _conv(sd, pre + "ff.2", F.leaky_relu(_conv(sd, pre + "ff.0", x), 0.2))
+    ff = _conv(sd, pre + "ff.2", _lrelu(_conv(sd, pre + "ff.0", x)))
     return _bn(sd, pre + "bn2", x + ff)
 
 
@@ -396,7 +442,7 @@ def stn(sd: SD, pre: str, x0: Tensor) -> Tensor:
     x = _cbl(sd, pre + "conv2", _cbl(sd, pre + "conv1", x0)).max(dim=-1)[0]
     x = _cbl(sd, pre + "conv3", x).max(dim=-1)[0]
     for name in ("linear1", "linear2"):
-        x = F.leaky_relu(_bn(sd, f"{pre}{name}.1", F.linear(x, sd[f"{pre}{name}.0.weight"])), 0.2)
+        x = _lrelu(_bn(sd, f"{pre}{name}.1", F.linear(x, sd[f"{pre}{name}.0.weight"])))
     return F.linear(x, sd[pre + "transform.weight"], sd[pre + "transform.bias"]).view(B, 3, 3)
 
 
@@ -469,5 +515,5 @@ def cls_forward(sd: SD, config, x: Tensor, states: Sequence[DSState],
     y = torch.cat(pooled, dim=1)
     for name in ("linear1", "linear2"):
         y = F.linear(y, sd[f"{name}.0.weight"], sd[f"{name}.0.bias"])
-        y = F.leaky_relu(_bn(sd, f"{name}.1", y), 0.2)
+        y = _lrelu(_bn(sd, f"{name}.1", y))
     return F.linear(y, sd["linear3.weight"], sd["linear3.bias"])

@@ -37,6 +37,9 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_index_points": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
     "samble_group": (_i, (_p, _p, _i, _i, _i, _i, _i, _i, _p, _p)),
     "samble_gather_by_idx": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
+    "samble_index_points_backward": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
+    "samble_gather_by_idx_backward": (_i, (_p, _p, _i, _i, _i, _i, _i, _p, _p)),
+    "samble_n2p_attend_backward": (_i, (_p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p, _p, _ll, _p)),
     "samble_transpose": (_i, (_p, _ll, _ll, _i, _i, _i, _p, _p)),
     "samble_neighbor_mask": (_i, (_p, _i, _i, _i, _i, _p, _p)),
     "samble_split_tf32": (_i, (_p, _p, _ll, _p)),

@@ -26,6 +26,17 @@ from ._precision import fp32_forward
 Tensor = torch.Tensor
 
 
+def differentiable(mod: nn.Module, *tensors) -> bool:
+    """True when a forward must take the differentiable path (samble_b200.autograd + ATen dense layers): BatchNorm needs
+    batch statistics (train mode), or a gradient could be asked for (grad mode on and an input or a parameter of `mod`
+    requires grad).  Otherwise the fused inference kernels run; they refuse tensors that require grad (_lib.no_grad_check)."""
+    if mod.training:
+        return True
+    if not torch.is_grad_enabled():
+        return False
+    return any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in mod.parameters())
+
+
 def fold_bn(bn: nn.modules.batchnorm._BatchNorm):
     """eval-mode BatchNorm as y = a*x + b."""
     a = bn.weight / torch.sqrt(bn.running_var + bn.eps)
@@ -141,7 +152,7 @@ class EdgeConv(nn.Module):
             raise ValueError(
                 f"group_type should be neighbor, diff, center_neighbor or center_diff, but got {self.group_type}")
         c2 = self.conv2[0].out_channels
-        if self.training or self.K > 32 or c2 not in (32, 64, 128) or self.conv1[0].out_channels % 4:
+        if differentiable(self, x) or self.K > 32 or c2 not in (32, 64, 128) or self.conv1[0].out_channels % 4:
             x, _ = ops.group(x, self.K, self.group_type, self.normal_channel)
             return self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0]
         key = x[:, :3, :] if (self.normal_channel and x.shape[1] == 6) else x
@@ -191,13 +202,16 @@ class Neighbor2PointAttention(nn.Module):
                                       "attention_mode='scalar_dot', asm='dot' (the shipped configs)")
         B, C, N = x.shape
         idx = ops.knn_indices(x, self.K, ordered=False)                                        # (B,N,K) int32
-        w = self._wqkv.get([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], lambda: torch.cat(
-            [self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C).contiguous())
-        if self.training:                                                       # BatchNorm batch statistics: library ops
+        if differentiable(self, x):
+            # train mode / gradients: the same hoisted form, projections and BatchNorm (batch statistics) in ATen, the
+            # attention core and its backward native (autograd.N2PAttend) -- still no (B,C,N,K) tensor in either direction
+            w = torch.cat([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C)
             qkv = torch.matmul(x.transpose(1, 2), w.t())                        # (B,N,3C) point-major
             y = ops.n2p_attend(qkv, idx, self.num_heads)                        # (B,N,C)
             x = self.bn1(x + y.transpose(1, 2))
             return self.bn2(x + self.ff(x))
+        w = self._wqkv.get([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], lambda: torch.cat(
+            [self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C).contiguous())
         # eval: everything point-major, projections / feed-forward on the tensor cores, BatchNorms folded into epilogues
         x_pm = ops.rows_of(x)                                                   # (B,N,C)
         qkv = ops.linear(x_pm, w)                                               # (B,N,3C)
@@ -282,6 +296,32 @@ class DownSampleToken(nn.Module):
                                       "relu_mean_order='mean_relu', one head (the shipped configs)")
         if self.bin_sample_mode not in ("topk", "uniform", "random"):
             raise ValueError("Please check the setting of bin sample mode. It must be topk, multinomial or random!")
+        if differentiable(self, x):
+            # train mode / gradients.  The sampled indices are a discrete decision (no gradient in the reference either):
+            # they come from the same native scoring + sampling kernels.  Gradients flow through the selected attention
+            # rows times V (:242-252) and through the token logits (token-orthogonality loss, train_shapenet.py:401-413),
+            # which are formed here in ATen on an (B,M,N+nb) slab -- not the reference's (B,N,N+nb).
+            with torch.no_grad():
+                _, index_down = self._forward_native(x.detach(), want_rows=False)
+            x_ds, tok = self._selected_rows_autograd(x, index_down)
+            self.attention_bins_beforesoftmax = tok
+            return (x_ds, index_down), (None, None)
+        x_ds, index_down = self._forward_native(x, want_rows=True)
+        return (x_ds, index_down), (None, None)
+
+    def _selected_rows_autograd(self, x: Tensor, index_down: Tensor):
+        """x_ds (B,C,M) and the pre-softmax token logits (B,1,N,nb) as differentiable functions of x and the parameters."""
+        B, C, N = x.shape
+        nb, scale = self.num_bins, math.sqrt(self.q_depth)
+        xt = torch.cat([x, self.bin_tokens.expand(B, -1, -1)], dim=2)          # (B,C,N+nb)  (:116-118)
+        q, k, v = self.q_conv(x), self.k_conv(xt), self.v_conv(xt)             # (B,D,N), (B,D,N+nb) x2
+        tok = torch.matmul(q.transpose(1, 2), k[:, :, N:]) / scale             # (B,N,nb)
+        q_sel = ops.gather_by_idx(q, index_down)                               # (B,D,M), native gather + scatter-add backward
+        att = torch.softmax(torch.matmul(q_sel.transpose(1, 2), k) / scale, dim=-1)          # (B,M,N+nb)
+        x_ds = torch.matmul(att, v.transpose(1, 2)).transpose(1, 2)            # (B,C,M)
+        return x_ds, tok.view(B, 1, N, nb)
+
+    def _forward_native(self, x: Tensor, want_rows: bool):
         B, C, N = x.shape
         D, nb = self.q_depth, self.num_bins
         # projections of the points and of the nb bin tokens (shared by the whole batch, :116-118)
@@ -330,6 +370,10 @@ class DownSampleToken(nn.Module):
         # (B,M,N) tensor exists.
         sel = s["idx"]
         scale = math.sqrt(D)
+        self.idx = index_down
+        self.attention_bins_beforesoftmax = tok_logits.view(B, 1, N, nb)
+        if not want_rows:
+            return None, index_down
         if exact:
             x_ds = ops.ds_attend_rows(qd, kd, v, sel, rowmax, rowsum, tok_logits, v_tok)          # (B,M,C)
         else:
@@ -340,11 +384,7 @@ class DownSampleToken(nn.Module):
             else:
                 att = torch.exp(torch.matmul(q_sel, k.transpose(1, 2)) / scale - m_sel.unsqueeze(-1)) / s_sel.unsqueeze(-1)
                 x_ds = torch.matmul(att, v) + tok_mix
-        x_ds = x_ds.transpose(1, 2)
-
-        self.idx = index_down
-        self.attention_bins_beforesoftmax = tok_logits.view(B, 1, N, nb)
-        return (x_ds, index_down), (None, None)
+        return x_ds.transpose(1, 2), index_down
 
     # reference API kept for callers (downsample.py:346-378)
     def output_variable_calculatio(self):
@@ -378,7 +418,8 @@ class UpSampleInterpolation(nn.Module):
     @fp32_forward
     def forward(self, pcd_up, pcd_down, pcd_up_xyz):
         (points_select, idx_select, points_select_xyz), (points_drop, idx_drop) = pcd_down
-        if not self.training and self.distance_type == "xyz" and self.K == 3 and points_select.shape[1] % 4 == 0:
+        slow = differentiable(self, pcd_up, points_select, pcd_up_xyz, points_select_xyz)
+        if not slow and self.distance_type == "xyz" and self.K == 3 and points_select.shape[1] % 4 == 0:
             # point-major throughout: [pcd_up | interpolated] is assembled as rows (the interpolation writes its half in
             # place), res_conv reads it as a GEMM operand, the result is handed on as a (B,C,N) view of rows
             B, C, N = pcd_up.shape
@@ -390,11 +431,12 @@ class UpSampleInterpolation(nn.Module):
         interpolated = self.interpolate(pcd_up, points_select, pcd_up_xyz, points_select_xyz,
                                         distance_type=self.distance_type, K=self.K)
         x = torch.cat([pcd_up, interpolated], dim=1)
-        return self.res_conv(x) if self.training else cbl(self.res_conv, x)
+        return self.res_conv(x) if slow else cbl(self.res_conv, x)
 
     def interpolate(self, pcd_up, points_select, pcd_up_xyz, points_select_xyz, distance_type="feature", K=3):
-        feat = self.conv(points_select) if self.training else cbl(self.conv, points_select)
-        if distance_type == "xyz" and K == 3:
+        slow = differentiable(self, pcd_up, points_select, pcd_up_xyz, points_select_xyz)
+        feat = self.conv(points_select) if slow else cbl(self.conv, points_select)
+        if distance_type == "xyz" and K == 3 and not slow:
             return ops.interpolate3(pcd_up_xyz, points_select_xyz, feat)
         if distance_type == "feature":
             nbr, _, d = ops.select_neighbors_interpolate(pcd_up, points_select, feat, K=K)

@@ -47,7 +47,7 @@ class STN(nn.Module):
 
     def _tail(self, x: Tensor) -> Tensor:
         B = x.size(0)
-        x = self.conv3(x).max(dim=-1, keepdim=False)[0] if self.training else blocks.cbl_pool(self.conv3, x, want_mean=False)[0]
+        x = self.conv3(x).max(dim=-1, keepdim=False)[0] if blocks.differentiable(self, x) else blocks.cbl_pool(self.conv3, x, want_mean=False)[0]
         x = self.dp2(self.linear2(self.dp1(self.linear1(x))))
         return self.transform(x).view(B, 3, 3)
 
@@ -60,7 +60,7 @@ class STN(nn.Module):
     def forward_cloud(self, x: Tensor, K: int = 32) -> Tensor:
         """same result from the raw (B,3,N) cloud: conv1 -> conv2 -> max over K is the EdgeConv pattern
         (seg_model.py:182-184 + embedding.py:81-85), so eval mode reuses the fused edge-MLP kernel."""
-        if self.training:
+        if blocks.differentiable(self, x):
             return self.forward(ops.group(x, K, "center_diff")[0])
         idx = ops.knn_indices(x, K, ordered=False)
         params = [self.conv1[0].weight, self.conv2[0].weight, *self.conv1[1].parameters(), *self.conv1[1].buffers(),
@@ -148,7 +148,7 @@ class ShapeNetModel(nn.Module):
             trans = self.STN.forward_cloud(x, 32)
             x = torch.bmm(x.transpose(2, 1), trans).transpose(2, 1).contiguous()
         f = self.block(x)                                                     # (B,C,N)
-        if self.training:
+        if blocks.differentiable(self, x, f):
             g = self.conv(f)
             g = torch.cat([g.max(dim=-1, keepdim=True)[0], g.mean(dim=-1, keepdim=True), self.conv1(category_id)], dim=1)
             w2 = self.conv2[0].weight
@@ -194,7 +194,7 @@ class ClsFeatureLearningBlock(_BlockBase):
 
     def _pooled(self, conv: nn.Conv1d, x: Tensor) -> Tensor:
         """conv(x).max(dim=-1)[0] (cls_model.py:104,133); eval mode pools inside the GEMM epilogue."""
-        if self.training or x.shape[-1] % 32:
+        if blocks.differentiable(self, x) or x.shape[-1] % 32:
             return conv(x).max(dim=-1)[0]
         return ops.linear_pool(ops.rows_of(x), conv.weight, want_mean=False)[0]
 

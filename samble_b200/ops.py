@@ -17,6 +17,7 @@ from typing import List, Optional, Tuple
 import torch
 
 from . import _lib as L
+from . import autograd as AG
 
 Tensor = torch.Tensor
 
@@ -43,7 +44,7 @@ def _idx_bits(idx: Tensor) -> int:
 def _knn_strided(a: Tensor, b: Tensor, k: int, layout: str, want_dist: bool, idx_dtype=torch.int64, ordered=True):
     """a, b: 3-D fp32 CUDA tensors in 'bnc' (B,N,C) or 'bcn' (B,C,N) layout, any strides."""
     dev = L.need_cuda(a, b)
-    L.no_grad_check(a, b)
+    a, b = a.detach(), b.detach()            # discrete output + forward values; callers attach the distance gradient (autograd.py)
     _f32(a, "a"), _f32(b, "b")
     if layout == "bnc":
         (B, Nq, Cc), (Bb, Nr, Cb) = a.shape, b.shape
@@ -67,8 +68,12 @@ def _knn_strided(a: Tensor, b: Tensor, k: int, layout: str, want_dist: bool, idx
 
 
 def knn(a: Tensor, b: Tensor, k: int) -> Tuple[Tensor, Tensor]:
-    """utils/ops.py:17-44.  a (B,N,C), b (B,M,C) -> (negative distance (B,N,k), idx (B,N,k) int64)."""
-    return _knn_strided(a, b, k, "bnc", True)
+    """utils/ops.py:17-44.  a (B,N,C), b (B,M,C) -> (negative distance (B,N,k), idx (B,N,k) int64).
+    When a or b requires grad the distances carry the reference's gradient (autograd.knn_distance)."""
+    neg, idx = _knn_strided(a, b, k, "bnc", True)
+    if AG.wants_grad(a, b):
+        neg = -AG.knn_distance(a, b, idx, -neg)
+    return neg, idx
 
 
 def knn_indices(pcd: Tensor, K: int, idx_dtype=torch.int32, ordered: bool = True) -> Tensor:
@@ -84,7 +89,8 @@ def knn_indices(pcd: Tensor, K: int, idx_dtype=torch.int32, ordered: bool = True
 def index_points(points: Tensor, idx: Tensor) -> Tensor:
     """utils/ops.py:5-14.  points (B,N,C), idx (B,M,K) -> (B,M,K,C)."""
     dev = L.need_cuda(points, idx)
-    L.no_grad_check(points)
+    if AG.wants_grad(points):
+        return AG.IndexPoints.apply(_f32(points, "points"), idx)
     points = _f32(points, "points").contiguous()
     idx = idx.contiguous()
     B, N, Cc = points.shape
@@ -99,6 +105,8 @@ def _group_from_idx(pcd: Tensor, idx: Tensor, group_type: str) -> Tensor:
     B, Cc, N = pcd.shape
     K = idx.shape[-1]
     t = _GROUP_TYPES[group_type]
+    if AG.wants_grad(pcd):
+        return AG.Group.apply(pcd, idx, t)
     if t < 2:
         buf = torch.empty(B, N, K, Cc, dtype=torch.float32, device=pcd.device)
     else:
@@ -114,7 +122,6 @@ def select_neighbors(pcd: Tensor, K: int, neighbor_type: str, normal_channel: bo
     if neighbor_type not in ("neighbor", "diff"):
         raise ValueError(f'neighbor_type should be "neighbor" or "diff", but got {neighbor_type}')
     L.need_cuda(pcd)
-    L.no_grad_check(pcd)
     pcd = _f32(pcd, "pcd").contiguous()
     key = pcd[:, :3, :] if (normal_channel and pcd.shape[1] == 6) else pcd
     _, idx = _knn_strided(key, key, K, "bcn", False)
@@ -127,7 +134,6 @@ def group(pcd: Tensor, K: int, group_type: str, normal_channel: bool = False):
         raise ValueError(
             f"group_type should be neighbor, diff, center_neighbor or center_diff, but got {group_type}")
     L.need_cuda(pcd)
-    L.no_grad_check(pcd)
     pcd = _f32(pcd, "pcd").contiguous()
     key = pcd[:, :3, :] if (normal_channel and pcd.shape[1] == 6) else pcd
     _, idx = _knn_strided(key, key, K, "bcn", False)
@@ -138,14 +144,16 @@ def select_neighbors_interpolate(unknown: Tensor, known: Tensor, known_feature: 
     """utils/ops.py:68-80.  -> (neighbors (B,C,N,K) view, idx (B,N,K), distance (B,N,K) >= 0)."""
     L.need_cuda(unknown, known, known_feature)
     neg, idx = _knn_strided(unknown, known, K, "bcn", True)
+    d = -1 * neg
+    if AG.wants_grad(unknown, known):        # the distances feed the interpolation weights (models/upsample.py:206-209)
+        d = AG.knn_distance(unknown.permute(0, 2, 1), known.permute(0, 2, 1), idx, d)
     nbr = index_points(known_feature.permute(0, 2, 1), idx)
-    return nbr.permute(0, 3, 1, 2), idx, -1 * neg
+    return nbr.permute(0, 3, 1, 2), idx, d
 
 
 def neighbor_mask(pcd: Tensor, K: int) -> Tensor:
     """utils/ops.py:125-133.  dense 0/1 (B,N,N) float32."""
     dev = L.need_cuda(pcd)
-    L.no_grad_check(pcd)
     pcd = _f32(pcd, "pcd")
     idx = knn_indices(pcd, K)
     B, N, _ = idx.shape
@@ -157,11 +165,12 @@ def neighbor_mask(pcd: Tensor, K: int) -> Tensor:
 def gather_by_idx(pcd: Tensor, idx: Tensor) -> Tensor:
     """utils/ops.py:136-145.  pcd (B,C,N), idx (B,1,M) -> (B,C,M)."""
     dev = L.need_cuda(pcd, idx)
-    L.no_grad_check(pcd)
-    pcd = _f32(pcd, "pcd").contiguous()
-    B, Cc, N = pcd.shape
     if idx.dim() != 3 or idx.shape[1] != 1:
         raise RuntimeError(f"gather_by_idx expects idx of shape (B,1,M), got {tuple(idx.shape)}")
+    if AG.wants_grad(pcd):
+        return AG.GatherByIdx.apply(_f32(pcd, "pcd"), idx)
+    pcd = _f32(pcd, "pcd").contiguous()
+    B, Cc, N = pcd.shape
     idx = idx.contiguous()
     M = idx.shape[2]
     out = torch.empty(B, Cc, M, dtype=torch.float32, device=dev)
@@ -399,6 +408,11 @@ def n2p_attend(qkv: Tensor, idx: Tensor, heads: int, residual: Optional[Tensor] 
     Core of models/attention.py:165-185,207-250 with the k/v convolutions hoisted (attention.cu).
     With residual (B,N,C) / scale,shift (C,): returns (residual + attention) * scale + shift (folded bn1, :187)."""
     dev = L.need_cuda(qkv, idx, residual, scale, shift)
+    if AG.wants_grad(qkv, residual, scale, shift):
+        y = AG.N2PAttend.apply(qkv, idx, heads)
+        if residual is not None:
+            y = y + residual
+        return y * scale + shift if scale is not None else y
     B, N, C3 = qkv.shape
     Cc = C3 // 3
     K = idx.shape[-1]
@@ -681,7 +695,7 @@ def bin_partition(attention_point_score: Tensor, bin_boundaries, dynamic_boundar
                   momentum_update_factor: float, num_bins: int):
     """utils/ops.py:435-464.  score (B,H,N) -> ([upper, lower], mask (B,H,N,num_bins) bool)."""
     dev = L.need_cuda(attention_point_score)
-    L.no_grad_check(attention_point_score)
+    attention_point_score = attention_point_score.detach()      # a partition: no gradient in the reference either
     B, H, N = attention_point_score.shape
     if bin_boundaries is not None:
         bin_boundaries = [t.to(dev) for t in bin_boundaries]

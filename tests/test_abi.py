@@ -100,3 +100,41 @@ def test_state_dict_layout_is_the_documented_one():
     assert len(sd) == 188
     sdc = ModelNetModel(cls_config()).state_dict()
     assert tuple(sdc["block.downsample_list.0.bin_tokens"].shape) == (1, 128, 6) and len(sdc) == 96
+
+
+def test_checkpoint_wire_format_roundtrip(tmp_path):
+    """train_shapenet.py:663-675 / test_shapenet.py:173-187: DDP-prefixed state_dict, alone or with the per-layer
+    [upper, lower] boundary pairs; loading installs the boundaries and freezes the EMA.  (CPU: construction and
+    load_state_dict need no kernel.)"""
+    import torch
+    from samble_b200 import checkpoint, models
+    from samble_b200.config import seg_config
+    from samble_b200.testing import fill_state_dict_
+
+    cfg = seg_config(M=(128, 64))
+    src = models.ShapeNetModel(cfg)
+    fill_state_dict_(src.state_dict(), seed=5)
+    nb = src.block.downsample_list[0].num_bins
+    for l, ds in enumerate(src.block.downsample_list):
+        cuts = [1.5 - 0.5 * j - 0.1 * l for j in range(nb - 1)]
+        ds.bin_boundaries = [torch.tensor([float("inf")] + cuts).reshape(1, 1, 1, nb), torch.tensor(cuts + [float("-inf")]).reshape(1, 1, 1, nb)]
+    for dyn in (True, False):
+        path = tmp_path / f"checkpoint_{dyn}.pt"
+        checkpoint.save(src, str(path), dynamic_boundaries=dyn)
+        raw = torch.load(str(path), weights_only=False)
+        sd = raw["model_state_dict"] if dyn else raw
+        assert all(k.startswith("module.") for k in sd) and (("bin_boundaries" in raw) == dyn)
+        dst = models.ShapeNetModel(cfg)
+        checkpoint.load(dst, str(path))
+        for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+            assert torch.equal(a, b), k
+        for a, b in zip(src.block.downsample_list, dst.block.downsample_list):
+            if dyn:
+                assert b.dynamic_boundaries_enable is False
+                assert torch.equal(a.bin_boundaries[0], b.bin_boundaries[0]) and torch.equal(a.bin_boundaries[1], b.bin_boundaries[1])
+            else:
+                assert b.bin_boundaries is None or b.dynamic_boundaries_enable == a.dynamic_boundaries_enable
+    with __import__("pytest").raises(RuntimeError):
+        bad = checkpoint.state(src)
+        bad["bin_boundaries"] = bad["bin_boundaries"][:1]
+        checkpoint.load(models.ShapeNetModel(cfg), bad)

@@ -326,11 +326,17 @@ def test_cuda_graph_replay_matches_eager():
         assert all(torch.equal(a, ds.idx) for a, ds in zip(idx2, m.block.downsample_list))
 
 
-def test_grad_is_refused_not_wrong():
+def test_grad_is_never_silently_dropped():
+    """An input (or parameter) that requires grad sends a block down the differentiable path (tests/test_gpu_backward.py);
+    the fused inference kernels themselves refuse such tensors instead of returning a detached result."""
     cfg, m, sd = _sd(128)
     x = cu(synthetic_features(1, 128, 128, 1)).requires_grad_(True)
+    y = m.block.feature_learning_layer_list[0](x)
+    assert y.requires_grad
+    y.sum().backward()
+    assert x.grad is not None and float(x.grad.abs().max()) > 0
     with pytest.raises(RuntimeError, match="forward-only"):
-        m.block.feature_learning_layer_list[0](x)
+        ops.linear(x, m.block.feature_learning_layer_list[0].ff[0].weight, x_layout="bcn")
 
 
 # ---------------------------------------------------------------- whole models
@@ -499,3 +505,36 @@ def test_ds_attend_rows_vs_fp64(B, N, M, nb, sharp):
     err = (out.cpu().double() - ref).abs()
     print(f"ds_attend_rows B={B} N={N} M={M}: max abs err {err.max():.2e} on values of magnitude {ref.abs().max():.1f}")
     assert bool((err <= 5e-5 + 1e-4 * ref.abs()).all()), float(err.max())
+
+
+def test_checkpoint_and_eval_harness(tmp_path):
+    """a reference-format checkpoint ({"model_state_dict" with DDP prefix, "bin_boundaries"}) restores a
+    model that reproduces the source model's predictions and sampled indices bit for bit through the evaluation loop."""
+    from torch.utils.data import DataLoader
+
+    from samble_b200 import checkpoint, evaluate
+
+    cfg = seg_config(M=(128, 64))
+    src = models.ShapeNetModel(cfg)
+    src.load_state_dict(fill_state_dict_(src.state_dict(), seed=12, sharpen=2.0))
+    src = src.eval().to(DEV)
+    xc, catc = synthetic_clouds(4, 256, 31)
+    with torch.no_grad():
+        src(cu(xc), cu(catc))                                     # calibrates the dynamic boundaries (EMA state outside the state_dict)
+    path = str(tmp_path / "checkpoint.pt")
+    checkpoint.save(src, path)
+    dst = checkpoint.load(models.ShapeNetModel(cfg).to(DEV), path, map_location=DEV)
+    models.freeze_boundaries(src)
+    data = evaluate.SyntheticShapeNetPart(8, N=256, seed=3)
+    a = evaluate.evaluate_seg(src, DataLoader(data, batch_size=4), device=DEV)
+    b = evaluate.evaluate_seg(dst, DataLoader(data, batch_size=4), device=DEV)
+    assert a["pred"].shape == (8, 256) and a["seg_label"].shape == (8, 256) and len(a["ds_idx"]) == 2
+    assert a["ds_idx"][0].shape == (8, 1, 128) and a["ds_idx"][1].shape == (8, 1, 64)
+    assert np.array_equal(a["pred"], b["pred"]) and all(np.array_equal(x, y) for x, y in zip(a["ds_idx"], b["ds_idx"]))
+    assert 0.0 <= a["point_accuracy"] <= 1.0
+    ccfg = cls_config(M=(128, 64))
+    cm = models.ModelNetModel(ccfg)
+    cm.load_state_dict(fill_state_dict_(cm.state_dict(), seed=13))
+    cm = cm.eval().to(DEV)
+    r = evaluate.evaluate_cls(cm, DataLoader(evaluate.SyntheticModelNet(6, N=256), batch_size=3), device=DEV)
+    assert r["pred"].shape == (6,) and 0.0 <= r["accuracy"] <= 1.0
