@@ -205,6 +205,9 @@ int samble_n2p_attend(const float* q, const float* k, const float* v, long long 
                       const float* residual, long long ld_res, const float* scale, const float* shift,
                       float* out, long long ld_out, samble_stream_t stream);
 
+/* 0 (default): eight-lanes-per-point kernel when the shape allows; 1: the warp-per-point kernel only (cross-check). */
+void samble_set_n2p_mode(int mode);
+
 /* backward of samble_n2p_attend without the fused tail (models/attention.py:207-250 under autograd): grad_out (B,N,C) with leading
  * dimension ld_go -> grad_q (written), grad_k / grad_v (ACCUMULATED with fp32 atomics: zero them first), all with leading
  * dimension ld_g.  Recomputes the probabilities from q, k (no (B,N,K) tensor is saved by the forward pass). */

@@ -538,3 +538,66 @@ def test_checkpoint_and_eval_harness(tmp_path):
     cm = cm.eval().to(DEV)
     r = evaluate.evaluate_cls(cm, DataLoader(evaluate.SyntheticModelNet(6, N=256), batch_size=3), device=DEV)
     assert r["pred"].shape == (6,) and 0.0 <= r["accuracy"] <= 1.0
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("which", ["seg", "cls"])
+def test_unmodified_reference_wiring_with_the_patch_installed(which):
+    """The drop-in claim end to end: the reference's OWN models/seg_model.py / cls_model.py (unmodified, imported from
+    SAMBLE_REFERENCE or /root/reference) with samble_b200.patch installed, against the wiring mirror the other tests use.
+    Needs the reference checkout next to a GPU, which the build container (no GPU) and the GPU box (no reference) never
+    offer together: it runs wherever a maintainer has both, and is skipped otherwise."""
+    from samble_b200 import patch
+    from tests.golden import ref_loader as R
+
+    B, N, M = 2, 512, (256, 128)
+    with patch.installed():
+        over = {"downsample.M": list(M), "downsample.bin.sample_mode": ["topk", "topk"]}
+        ref = R.build_model(which, R.reference_config(which, **over))
+    cfg = (seg_config if which == "seg" else cls_config)(M=M)
+    mine = (models.ShapeNetModel if which == "seg" else models.ModelNetModel)(cfg)
+    sd = fill_state_dict_(mine.state_dict(), seed=21, sharpen=2.0)
+    mine.load_state_dict(sd)
+    ref.load_state_dict(sd)
+    mine, ref = mine.eval().to(DEV), ref.eval().to(DEV)
+    x, cat = synthetic_clouds(B, N, 41)
+    args = (cu(x), cu(cat)) if which == "seg" else (cu(x),)
+    with torch.no_grad(), patch.installed():
+        for net in (mine, ref):
+            net(*args)                                               # calibrate the boundaries
+            for ds in net.block.downsample_list:
+                ds.dynamic_boundaries_enable = False
+        y_ref, y = ref(*args), mine(*args)
+    assert all(isinstance(ds, blocks.DownSampleToken) for ds in ref.block.downsample_list)
+    for a, b in zip(ref.block.downsample_list, mine.block.downsample_list):
+        assert torch.equal(a.idx, b.idx)
+    assert close_frac(y, y_ref) == 1.0
+
+
+@pytest.mark.parametrize("B,N,C,K,H", [(2, 2048, 128, 32, 4), (1, 1000, 128, 32, 4), (3, 77, 64, 20, 4), (1, 300, 128, 17, 1), (2, 130, 64, 32, 8)])
+def test_n2p_attend_eight_lane_kernel_vs_warp_per_point_and_fp64(B, N, C, K, H):
+    """The two gather-attend kernels (csrc/attention.cu) against each other and against the literal fp64 statement of
+    models/attention.py:207-250 on the hoisted projections, incl. the fused residual + folded-BN tail."""
+    from samble_b200 import _lib as L
+    g = torch.Generator().manual_seed(N + C + K)
+    qkv = torch.randn(B, N, 3 * C, generator=g)
+    idx = torch.stack([torch.stack([torch.randperm(N, generator=g)[:K] for _ in range(N)]) for _ in range(B)])
+    res, sc, sh = torch.randn(B, N, C, generator=g), torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    D = C // H
+    q, k, v = (qkv.double()[..., i * C:(i + 1) * C] for i in range(3))
+    gat = lambda t: torch.gather(t, 1, idx.reshape(B, -1, 1).expand(-1, -1, C)).view(B, N, K, C)
+    att = torch.softmax(torch.einsum("bnhd,bnkhd->bnhk", q.reshape(B, N, H, D), gat(k).view(B, N, K, H, D)) / math.sqrt(D), dim=-1)
+    ref = torch.einsum("bnhk,bnkhd->bnhd", att, (gat(v) - v[:, :, None, :]).view(B, N, K, H, D)).reshape(B, N, C)
+    ref_tail = (ref + res.double()) * sc.double() + sh.double()
+    outs = {}
+    for mode in (0, 1):
+        L.lib().samble_set_n2p_mode(mode)
+        try:
+            for dt in (torch.int32, torch.int64):
+                y = ops.n2p_attend(cu(qkv), cu(idx).to(dt), H)
+                yt = ops.n2p_attend(cu(qkv), cu(idx).to(dt), H, residual=cu(res), scale=cu(sc), shift=cu(sh))
+                assert close_frac(y, ref, 2e-5, 2e-5) == 1.0 and close_frac(yt, ref_tail, 2e-5, 2e-5) == 1.0, (mode, dt)
+            outs[mode] = (y, yt)
+        finally:
+            L.lib().samble_set_n2p_mode(0)
+    assert close_frac(outs[0][0], outs[1][0].cpu(), 1e-5, 1e-5) == 1.0
