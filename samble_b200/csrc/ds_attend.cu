@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) ds_vt_split_kernel(const float* __restric
 
 __global__ void __launch_bounds__(kDaThreads, 1) ds_attend_rows_kernel(const __grid_constant__ DaMaps maps, DaArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc::smem_align1024(smem_raw);
   const int nkt = a.Cp >> 6;
   uint8_t* sQ = base;                                           // [digit][kt] tiles of 128 rows x 128 B (gathered)
   uint8_t* sK = sQ + (size_t)kDaDigits * nkt * 16384;           // ring of 8 KB boxes

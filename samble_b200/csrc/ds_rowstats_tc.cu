@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
                            const float* __restrict__ k_tok, int N, int D, int nb, float scale, float* __restrict__ rowmax,
                            float* __restrict__ rowsum, float* __restrict__ token_logits) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc::smem_align1024(smem_raw);
   const int nkb = D / 32;
   uint8_t* sQh = base;                                   // [nkb][16 KB]
   uint8_t* sQl = sQh + (size_t)nkb * 16384;

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(kEtThreads, 1)
     edge_mlp_tc_kernel(const float* __restrict__ pr, long long ld_pr, const I* __restrict__ idx, const float* __restrict__ w2,
                        const float* __restrict__ b2, int B, int N, int K, int C1, float* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc::smem_align1024(smem_raw);
   const int nkb = C1 / 32;
   constexpr int kWBlock = C2 * 128;                          // one K-block of W2': C2 rows x 128 B
   uint8_t* sWh = base;                                       // [nkb][C2 x 128 B]
@@ -73,26 +73,29 @@ __global__ void __launch_bounds__(kEtThreads, 1)
   const uint32_t tmem = *tmem_slot;
 
   if (warp >= 5) {
-    // ================= loaders: thread = edge row (point lw of the tile, edge `lane`) =================
+    // ================= loaders: warp = point lw of the tile, its 32 edge rows built cooperatively =================
     // Two groups of four warps take alternate stages, so one group's gathers (an L2 round trip that registers cannot
     // prefetch more than one stage deep) are in flight while the other group builds its stage.
+    // Eight lanes share one gathered row: a load instruction covers 4 rows x 128 contiguous bytes = 16 whole sectors.
+    // (Round 1 had thread = edge row, i.e. 32 half-used sectors per instruction and the centre row P' re-read by every
+    // lane: L1/TEX throughput 85 %, profiles/r2_step_full.md.)
     const int grp = (warp - 5) >> 2, lw = (warp - 5) & 3;
-    const int row = lw * 32 + lane;
+    const int sub = lane & 7, rsel = lane >> 3;
     const int ntl = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
     const int G = ntl * nkb;
-    float4 pv[8], rv[8];
+    float4 pv, rv[8];
     auto fetch = [&](int g) {                       // loads for stage g into registers
       const int tile = blockIdx.x + (g / nkb) * gridDim.x, kb = g % nkb;
       const int b = tile / tiles_per_cloud, n = (tile % tiles_per_cloud) * 4 + lw;
       const bool ok = n < N;
       const long long prow = (long long)b * N + (ok ? n : 0);
       const int j = ok ? ld_idx(idx, prow * K + min(lane, K - 1)) : 0;     // lanes >= K repeat the last edge
-      const float4* pp = reinterpret_cast<const float4*>(pr + prow * ld_pr + kb * 32);
-      const float4* rp = reinterpret_cast<const float4*>(pr + ((long long)b * N + j) * ld_pr + C1 + kb * 32);
+      pv = ok ? __ldg(reinterpret_cast<const float4*>(pr + prow * ld_pr + kb * 32) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* rbase = pr + (long long)b * N * ld_pr + C1 + kb * 32;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        pv[c] = ok ? __ldg(pp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        rv[c] = ok ? __ldg(rp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = 0; t < 8; ++t) {
+        const int jr = __shfl_sync(kFull, j, t * 4 + rsel);                // edge row t*4 + rsel of this point
+        rv[t] = ok ? __ldg(reinterpret_cast<const float4*>(rbase + (long long)jr * ld_pr) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     if (grp < G) fetch(grp);
@@ -102,9 +105,9 @@ __global__ void __launch_bounds__(kEtThreads, 1)
       uint8_t* hh = sH + (size_t)s * 32768;
       uint8_t* hl = hh + 16384;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int t = 0; t < 8; ++t) {
         float4 h;
-        h.x = pv[c].x + rv[c].x, h.y = pv[c].y + rv[c].y, h.z = pv[c].z + rv[c].z, h.w = pv[c].w + rv[c].w;
+        h.x = pv.x + rv[t].x, h.y = pv.y + rv[t].y, h.z = pv.z + rv[t].z, h.w = pv.w + rv[t].w;
         h.x = h.x > 0.f ? h.x : 0.2f * h.x;
         h.y = h.y > 0.f ? h.y : 0.2f * h.y;
         h.z = h.z > 0.f ? h.z : 0.2f * h.z;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(kEtThreads, 1)
         lo.y = h.y - __uint_as_float(__float_as_uint(h.y) & 0xffffe000u);
         lo.z = h.z - __uint_as_float(__float_as_uint(h.z) & 0xffffe000u);
         lo.w = h.w - __uint_as_float(__float_as_uint(h.w) & 0xffffe000u);
-        const uint32_t off = tc::sw128_offset(row, c);
+        const uint32_t off = tc::sw128_offset(lw * 32 + t * 4 + rsel, sub);
         *reinterpret_cast<float4*>(hh + off) = h;
         *reinterpret_cast<float4*>(hl + off) = lo;
       }

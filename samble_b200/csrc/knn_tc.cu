@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                   int Nq, int Nr, int Cp, int k, float* __restrict__ thr, uint32_t* __restrict__ cand_out,
                   int* __restrict__ cnt_out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc::smem_align1024(smem_raw);
   const int nkt = (Cp + 63) / 64;                           // K-tiles of 64 bf16 (128-byte rows) per plane
   constexpr int kPlanes = PASS_B ? 2 : 1;                   // candidate-side planes streamed per tile (pass A: hi only)
   uint8_t* sA = base;                                       // query tile: [hi: nkt tiles][lo: nkt tiles]

@@ -40,6 +40,7 @@ struct LinArgs {
   // row-statistics mode (linear_tma.cu): nothing is stored but, per row and 128-column tile, the maximum of
   // acc / logit_div and the sum of exp(. - max):  stat_out[m * ntiles + n_tile] = (max, sum)
   float2* stat_out;
+  int dbg;                            // measurement switches (samble_set_linear_debug): 8 = no residual loads, 16 = no stores
 };
 
 
@@ -71,13 +72,19 @@ __device__ __forceinline__ void linear_epilogue_tile(const LinArgs& a, uint32_t 
     if (!live || n0 + c0 >= a.Nout) continue;
     const bool full32 = n0 + c0 + 32 <= a.Nout;
     float r[32];
-    if (a.residual) {
+    if (a.dbg & 8) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = 0.f;
+    } else if (a.residual) {
       if (a.res_cm) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) r[i] = (n0 + c0 + i < a.Nout) ? __ldg(a.residual + (ob * a.Nout + n0 + c0 + i) * a.npc + on) : 0.f;
       } else {
         const float* rrow = a.residual + (long long)m * a.ldr + n0 + c0;
-        if (full32 && a.ldr % 4 == 0 && reinterpret_cast<uintptr_t>(a.residual) % 16 == 0) {
+        if (full32 && a.ldr % 8 == 0 && (n0 + c0) % 8 == 0 && reinterpret_cast<uintptr_t>(a.residual) % 32 == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) tc::ldg256(rrow + i, r + i);          // one whole sector per lane and instruction
+        } else if (full32 && a.ldr % 4 == 0 && reinterpret_cast<uintptr_t>(a.residual) % 16 == 0) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 t = __ldg(reinterpret_cast<const float4*>(rrow + i));
@@ -124,13 +131,18 @@ __device__ __forceinline__ void linear_epilogue_tile(const LinArgs& a, uint32_t 
       if (a.residual && !a.res_first) y += r[i];
       v[i] = y;
     }
-    if (a.out_cm) {
+    if (a.dbg & 16) {
+      if (v[0] == 1234.5f) a.out[0] = v[1];                    // (keeps the math alive)
+    } else if (a.out_cm) {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (n0 + c0 + i < a.Nout) a.out[(ob * a.Nout + n0 + c0 + i) * a.npc + on] = v[i];
     } else {
       float* orow = a.out + (long long)m * a.ldo + n0 + c0;
-      if (full32 && a.ldo % 4 == 0 && reinterpret_cast<uintptr_t>(a.out) % 16 == 0) {
+      if (full32 && a.ldo % 8 == 0 && (n0 + c0) % 8 == 0 && reinterpret_cast<uintptr_t>(a.out) % 32 == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) tc::stg256(orow + i, v + i);            // 32 whole sectors per warp instruction
+      } else if (full32 && a.ldo % 4 == 0 && reinterpret_cast<uintptr_t>(a.out) % 16 == 0) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(orow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       } else {
@@ -142,24 +154,39 @@ __device__ __forceinline__ void linear_epilogue_tile(const LinArgs& a, uint32_t 
   }
 }
 
-// Row-major outputs: the same epilogue, staged through a per-warp shared-memory slab so that global traffic is
-// coalesced and the per-column constants sit in registers.  Phase 1 (thread = row) dumps a 32x32 block of raw
-// accumulators into the slab; phase 2 re-reads it with 8 lanes per row (one float4 = 4 fixed columns per lane), so a
-// warp instruction moves four full 128-byte row segments, scale/shift are loaded once per block, and a row-major
-// residual is read coalesced.  The slab is private to the warp (warp w owns rows 32w..32w+31): __syncwarp only.
-constexpr int kLinSlabLd = 36;                                   // floats per slab row (pad 4: conflict-free 128-bit access)
-constexpr int kLinSlabBytes = 4 * 32 * kLinSlabLd * 4;           // four epilogue warps
+// Row-major outputs through TMA stores (round 2).  Phase ablation of linear_tma_kernel (tools/probe_linear.py,
+// profiles/r2_linear_tma.md) showed the thread-per-row global stores ADDING their whole duration to the kernel instead
+// of overlapping with the main loop: 32 scattered sectors per instruction queue up in the LSU, which the operand
+// splitters share.  Here a warp parks its 32 x 32 block in shared memory (128-byte-swizzled rows: conflict-free for
+// thread = row) and one lane hands it to the TMA engine: whole 128-byte lines, no LSU involvement, rows / columns past
+// the end clipped by the tensor map.  Two 4 KB buffers per warp: the store of block c drains while block c+1 is computed.
+constexpr int kLinStoreBytes = 4 * 2 * 4096;                     // four epilogue warps, double buffered
 
 template <int NT>
-__device__ __forceinline__ void linear_epilogue_tile_staged(const LinArgs& a, uint32_t tmem, int set, int nacc, int m0, int n0,
-                                                            int warp, int lane, float* slab_all) {
-  float* slab = slab_all + warp * 32 * kLinSlabLd;
+__device__ __forceinline__ void linear_epilogue_tile_tma(const LinArgs& a, const CUtensorMap* map_out, uint32_t tmem, int set,
+                                                         int nacc, int m0, int n0, int warp, int lane, uint8_t* stage_all,
+                                                         int& parity) {
+  const int m = m0 + warp * 32 + lane;
   const uint32_t lane_base = ((uint32_t)(warp * 32) << 16) + set * nacc * NT;
-  const int rq = lane >> 3, cq = (lane & 7) * 4;                 // phase 2: row within a group of 4, first of 4 columns
-  const bool vec_ok = a.ldo % 4 == 0 && reinterpret_cast<uintptr_t>(a.out) % 16 == 0 &&
-                      (!a.residual || (a.ldr % 4 == 0 && reinterpret_cast<uintptr_t>(a.residual) % 16 == 0));
+  const bool live = m < a.M;
+  const int mm = live ? m : 0;
+  const float* shift = a.shift ? a.shift + (a.shift_ldb ? (long long)(mm / a.npc) * a.shift_ldb : 0) : nullptr;
+  const bool res_vec = a.residual && a.ldr % 8 == 0 && reinterpret_cast<uintptr_t>(a.residual) % 32 == 0;
 #pragma unroll 1
   for (int c0 = 0; c0 < NT; c0 += 32) {
+    if (n0 + c0 >= a.Nout) break;                                // warp-uniform (tail tile of the n range)
+    const bool full32 = n0 + c0 + 32 <= a.Nout;
+    float r[32];
+    if (a.residual) {                                            // issued first: in flight during the TMEM load
+      const float* rrow = a.residual + (long long)mm * a.ldr + n0 + c0;
+      if (full32 && res_vec && (n0 + c0) % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) tc::ldg256(rrow + i, r + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = (n0 + c0 + i < a.Nout) ? __ldg(rrow + i) : 0.f;
+      }
+    }
     float v[32];
     tc::tmem_ld32(tmem + lane_base + c0, v);
     for (int ac = 1; ac < nacc; ++ac) {
@@ -168,77 +195,48 @@ __device__ __forceinline__ void linear_epilogue_tile_staged(const LinArgs& a, ui
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] += w[i];
     }
-    if (n0 + c0 >= a.Nout) continue;                             // warp-uniform
+    if (a.row_max) {                                             // softmax row with known max / sum (downsample.py:242-250)
+      const float mu = __ldg(a.row_max + mm), inv_s = 1.f / __ldg(a.row_sum + mm), inv_div = 1.f / a.logit_div;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(slab + lane * kLinSlabLd + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      for (int i = 0; i < 32; ++i) v[i] = __expf(fmaf(v[i], inv_div, -mu)) * inv_s;
+    }
+    const bool cvec = full32 && (n0 + c0) % 4 == 0 && (!a.scale || reinterpret_cast<uintptr_t>(a.scale) % 16 == 0) &&
+                      (!shift || (reinterpret_cast<uintptr_t>(shift) % 16 == 0));
+    uint8_t* buf = stage_all + warp * 8192 + (parity & 1) * 4096;
+    if (lane == 0) tc::bulk_wait_read<1>();                      // the store issued from this buffer two blocks ago has read it
     __syncwarp();
-    const int c = n0 + c0 + cq;                                  // this lane's 4 columns: c .. c+3
-    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int cc = min(c + j, a.Nout - 1);
-      if (a.scale) sc[j] = __ldg(a.scale + cc);
-      if (a.shift && a.shift_ldb == 0) sh[j] = __ldg(a.shift + cc);
-    }
-    const bool full4 = c + 4 <= a.Nout;
-    // residual rows of the 8 row groups: all eight loads are issued before any is used (one latency, not eight)
-    float4 res4[8];
-    if (a.residual) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int m = m0 + warp * 32 + it * 4 + rq;
-        res4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < a.M && c < a.Nout) {
-          const float* rp = a.residual + (long long)m * a.ldr + c;
-          if (full4 && vec_ok) {
-            res4[it] = __ldg(reinterpret_cast<const float4*>(rp));
-          } else {
-            res4[it].x = __ldg(rp);
-            if (c + 1 < a.Nout) res4[it].y = __ldg(rp + 1);
-            if (c + 2 < a.Nout) res4[it].z = __ldg(rp + 2);
-            if (c + 3 < a.Nout) res4[it].w = __ldg(rp + 3);
-          }
-        }
+    for (int i = 0; i < 32; i += 4) {
+      float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cvec) {
+        if (a.scale) s4 = __ldg(reinterpret_cast<const float4*>(a.scale + n0 + c0 + i));
+        if (shift) h4 = __ldg(reinterpret_cast<const float4*>(shift + n0 + c0 + i));
+      } else {
+        const int c = n0 + c0 + i, last = a.Nout - 1;
+        if (a.scale) s4 = make_float4(__ldg(a.scale + min(c, last)), __ldg(a.scale + min(c + 1, last)), __ldg(a.scale + min(c + 2, last)), __ldg(a.scale + min(c + 3, last)));
+        if (shift) h4 = make_float4(__ldg(shift + min(c, last)), __ldg(shift + min(c + 1, last)), __ldg(shift + min(c + 2, last)), __ldg(shift + min(c + 3, last)));
       }
-    }
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + rq;
-      const int m = m0 + warp * 32 + r;
-      if (m >= a.M || c >= a.Nout) continue;
-      const float4 t = *reinterpret_cast<const float4*>(slab + r * kLinSlabLd + cq);
-      float y[4] = {t.x, t.y, t.z, t.w};
-      if (a.shift && a.shift_ldb != 0) {
-        const float* shp = a.shift + (long long)(m / a.npc) * a.shift_ldb;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sh[j] = __ldg(shp + min(c + j, a.Nout - 1));
-      }
-      const float res[4] = {res4[it].x, res4[it].y, res4[it].z, res4[it].w};
-      if (a.row_max) {                                           // softmax row with known max / sum (downsample.py:242-250)
-        const float mu = __ldg(a.row_max + m), inv_s = 1.f / __ldg(a.row_sum + m), inv_div = 1.f / a.logit_div;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) y[j] = __expf(fmaf(y[j], inv_div, -mu)) * inv_s;
-      }
+      const float sc[4] = {s4.x, s4.y, s4.z, s4.w}, sh[4] = {h4.x, h4.y, h4.z, h4.w};
+      float y[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float z = y[j];
-        if (a.residual && a.res_first) z += res[j];
+        float z = v[i + j];
+        if (a.residual && a.res_first) z += r[i + j];
         if (a.scale) z *= sc[j];
-        if (a.shift) z += sh[j];
+        if (shift) z += sh[j];
         if (a.lrelu) z = z > 0.f ? z : 0.2f * z;
-        if (a.residual && !a.res_first) z += res[j];
+        if (a.residual && !a.res_first) z += r[i + j];
         y[j] = z;
       }
-      float* op = a.out + (long long)m * a.ldo + c;
-      if (full4 && vec_ok) {
-        *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (c + j < a.Nout) op[j] = y[j];
-      }
+      *reinterpret_cast<float4*>(buf + tc::sw128_offset(lane, i >> 2)) = make_float4(y[0], y[1], y[2], y[3]);
     }
-    __syncwarp();                                                // slab is rewritten by the next block
+    tc::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tc::tma_store_3d(map_out, buf, n0 + c0, m0 + warp * 32, 0);
+      tc::bulk_commit();
+    }
+    ++parity;
   }
 }
 

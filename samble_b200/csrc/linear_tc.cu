@@ -40,7 +40,7 @@ __device__ __forceinline__ void split_store(uint8_t* hi_tile, uint8_t* lo_tile, 
 template <int NT>
 __global__ void __launch_bounds__(kLinThreads, 1) linear_tc_kernel(LinArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc::smem_align1024(smem_raw);
   using Cfg = LinCfg<NT>;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)kLinStages * Cfg::kStageBytes);
   uint64_t* full = bars;                  // [kLinStages] 128 loader arrivals

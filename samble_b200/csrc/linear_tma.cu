@@ -18,6 +18,10 @@ namespace samble {
 
 constexpr int kLtThreads = 320;
 
+// measurement switches (tools/probe_linear.py): 1 = splitters idle, 2 = epilogue idle, 4 = no MMAs, 8 / 16 = no residual loads /
+// no stores in the direct epilogue (results are garbage), 64 = 96-wide tiles + TMA stores for resident weights (K = 128).
+int g_lt_debug = 0;
+
 struct LtPlan {
   int stages;       // X (or X+W) ring depth
   int w_res;        // weight slice resident
@@ -47,12 +51,12 @@ static LtPlan lt_plan(int K) {
   const size_t room = kLtLimit - kLtFixed - wres;
   p.stages = (int)(room / p.stage_bytes);
   if (p.stages > 4) p.stages = 4;
-  p.staged = room - (size_t)p.stages * p.stage_bytes >= (size_t)kLinSlabBytes;
+  p.staged = room - (size_t)p.stages * p.stage_bytes >= (size_t)kLinStoreBytes;
   if (!p.staged && p.stages == 4) {          // 4 -> 3 stages still hides the latency
     p.stages = 3;
     p.staged = 1;
   }
-  p.smem = wres + (size_t)p.stages * p.stage_bytes + (p.staged ? kLinSlabBytes : 0) + kLtFixed;
+  p.smem = wres + (size_t)p.stages * p.stage_bytes + (p.staged ? kLinStoreBytes : 0) + kLtFixed;
   return p;
 }
 
@@ -68,16 +72,16 @@ __device__ __forceinline__ void lt_range(int total, int& t0, int& t1) {
 template <int NT, int EPI>
 __global__ void __launch_bounds__(kLtThreads, 1)
     linear_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                      const __grid_constant__ CUtensorMap map_wlo, LinArgs a, int stages, int w_res, int stage_bytes,
-                      int staged) {
+                      const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_out, LinArgs a,
+                      int stages, int w_res, int stage_bytes, int staged, int dbg) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc::smem_align1024(smem_raw);
   const int nkb = (a.K + 31) / 32;
   const int wtile = NT * 128;                                   // one K-block of the weight slice
   uint8_t* wres = base;                                         // [hi: nkb tiles][lo: nkb tiles]   (w_res only)
   uint8_t* ring = base + (w_res ? (size_t)2 * nkb * wtile : 0);
-  float* slab = reinterpret_cast<float*>(ring + (size_t)stages * stage_bytes);       // epilogue staging (4 warps)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(slab) + (staged ? kLinSlabBytes : 0));
+  uint8_t* stage_out = ring + (size_t)stages * stage_bytes;                          // TMA-store staging (4 warps x 2 x 4 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + (staged ? kLinStoreBytes : 0));
   uint64_t* landed = bars;            // [4] TMA bytes of the stage arrived
   uint64_t* ready = bars + 4;         // [4] ... and X_lo written (4 splitter-warp arrivals)
   uint64_t* empty = bars + 8;         // [4] tcgen05.commit: stage consumed
@@ -163,6 +167,7 @@ __global__ void __launch_bounds__(kLtThreads, 1)
       tc::mbar_wait(&landed[s], ph);
       uint8_t* xh = ring + (size_t)s * stage_bytes;
       uint8_t* xl = xh + 16384;
+      if (!(dbg & 1))
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t off = (uint32_t)(lt + 128 * i) * 16u;  // element-wise op: any chunk -> same chunk, no swizzle math
@@ -205,6 +210,7 @@ __global__ void __launch_bounds__(kLtThreads, 1)
           const uint64_t wh = tc::smem_desc_sw128(w_res ? wbase + kb * wtile : st + 32768);
           const uint64_t wl = tc::smem_desc_sw128(w_res ? wbase + (nkb + kb) * wtile : st + 32768 + wtile);
           const uint32_t acc = tmem + (set * nacc + kb / chain) * NT;
+          if (!(dbg & 4))
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) {
             tc::mma_tf32(acc, xh + 2 * k8, wh + 2 * k8, idesc, ((kb % chain) | k8) != 0);
@@ -226,34 +232,40 @@ __global__ void __launch_bounds__(kLtThreads, 1)
     __syncwarp();
   } else {
     // ================= epilogue: thread = output row =================
-    int it = 0;
+    int it = 0, parity = 0;
     for (int tile = t0; tile < t1; ++tile, ++it) {
       const int set = (nsets == 2) ? (it & 1) : 0;
       const int use = (nsets == 2) ? (it >> 1) : it;
       const int m0 = (tile % mtiles) * 128, n0 = (tile / mtiles) * NT;
       tc::mbar_wait(&tfull[set], use & 1);
       tc::tc_fence_after();
-      if (EPI == 3)
+      if (dbg & 2) {
+        // (measurement switch: accumulators are drained but nothing is computed or stored)
+      } else if (EPI == 3)
         linear_epilogue_tile_rowstat<NT>(a, tmem, set, nacc, m0, n0, warp, lane, ntiles);
       else if (EPI == 2)
         linear_epilogue_tile_pool<NT>(a, tmem, set, nacc, m0, n0, warp, lane);
       else if (EPI == 0)
         linear_epilogue_tile<NT>(a, tmem, set, nacc, m0, n0, warp, lane);
       else
-        linear_epilogue_tile_staged<NT>(a, tmem, set, nacc, m0, n0, warp, lane, slab);
+        linear_epilogue_tile_tma<NT>(a, &map_out, tmem, set, nacc, m0, n0, warp, lane, stage_out, parity);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[set]);
     }
+    if (EPI == 1 && lane == 0) tc::bulk_wait<0>();              // this warp's stores have left shared memory and landed
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, tcols);
 }
 
+
 template <int NT>
-int launch_linear_tma(const LinArgs& a, cudaStream_t st) {
-  const LtPlan p = lt_plan<NT>(a.K);
+int launch_linear_tma(const LinArgs& a_in, cudaStream_t st) {
+  const LtPlan p = lt_plan<NT>(a_in.K);
+  LinArgs a = a_in;
+  a.dbg = g_lt_debug;
   alignas(64) CUtensorMap mx, mw, mwl;
   // inner extent = K rounded up to 4 (the zero padding the ABI asks for); the rest of a 32-channel box reads as zero
   const int k4 = (a.K + 3) / 4 * 4;
@@ -261,7 +273,15 @@ int launch_linear_tma(const LinArgs& a, cudaStream_t st) {
   const int wb = a.w_batched ? a.M / a.npc : 1;
   if (int e = make_tile_map(&mw, a.W, k4, a.ldw, a.Nout, wb, NT)) return e;
   if (int e = make_tile_map(&mwl, a.Wlo, k4, a.ldw, a.Nout, wb, NT)) return e;
-  const int epi = a.stat_out ? 3 : (a.pool_max ? 2 : ((a.out_cm || (a.residual && a.res_cm) || !p.staged) ? 0 : 1));
+  const bool tma_out = p.staged && !a.out_cm && !(a.residual && a.res_cm) && a.out && a.ldo % 4 == 0 &&
+                       reinterpret_cast<uintptr_t>(a.out) % 16 == 0 && !a.stat_out && !a.pool_max;
+  const int epi = a.stat_out ? 3 : (a.pool_max ? 2 : (tma_out ? 1 : 0));
+  alignas(64) CUtensorMap mo;
+  if (tma_out) {
+    if (int e = make_tile_map(&mo, a.out, a.Nout, a.ldo, a.M, 1, 32)) return e;
+  } else {
+    mo = mx;                                                   // (unused by the other epilogues)
+  }
   auto kern = epi == 3 ? linear_tma_kernel<NT, 3>
                        : (epi == 2 ? linear_tma_kernel<NT, 2> : (epi == 1 ? linear_tma_kernel<NT, 1> : linear_tma_kernel<NT, 0>));
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
@@ -269,17 +289,27 @@ int launch_linear_tma(const LinArgs& a, cudaStream_t st) {
   const long long total = (long long)ceil_div(a.M, 128) * ceil_div(a.Nout, NT);
   const int grid = (int)(total < 148 ? total : 148);
   SAMBLE_PRE(st);
-  kern<<<grid, kLtThreads, p.smem, st>>>(mx, mw, mwl, a, p.stages, p.w_res, p.stage_bytes, p.staged);
+  kern<<<grid, kLtThreads, p.smem, st>>>(mx, mw, mwl, mo, a, p.stages, p.w_res, p.stage_bytes, p.staged, g_lt_debug);
   SAMBLE_LAUNCHED("linear_tma_kernel");
   return SAMBLE_OK;
 }
 
 template int launch_linear_tma<128>(const LinArgs&, cudaStream_t);
+template int launch_linear_tma<96>(const LinArgs&, cudaStream_t);
 template int launch_linear_tma<64>(const LinArgs&, cudaStream_t);
 
 int launch_linear_tma_auto(const LinArgs& a, int nacc, cudaStream_t st) {
   const bool wide_ok = a.Nout > 64 && nacc * 128 <= 512;
-  return wide_ok ? launch_linear_tma<128>(a, st) : launch_linear_tma<64>(a, st);
+  if (!wide_ok) return launch_linear_tma<64>(a, st);
+  // Row-major outputs leave through TMA stores where 32 KB of staging fit next to the operand ring (all streaming shapes,
+  // K > 128: 13 % faster than the slab-staged thread stores they replace).  With a resident 128-wide weight slice (K = 128)
+  // there is no room; a 96-wide slice would make it, but measured slower there (more n-tiles re-read X, and 4 KB TMA boxes
+  // drain no faster than 256-bit thread stores: tools/probe_linear.py, bit 64), so those shapes keep the direct epilogue.
+  if ((g_lt_debug & 64) && lt_plan<128>(a.K).w_res && !lt_plan<128>(a.K).staged && !a.out_cm && !a.stat_out && !a.pool_max)
+    return launch_linear_tma<96>(a, st);
+  return launch_linear_tma<128>(a, st);
 }
 
 }  // namespace samble
+
+extern "C" void samble_set_linear_debug(int bits) { samble::g_lt_debug = bits; }

@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(128) tc_gemm_selftest_kernel(const float* __re
                                                                int K, float* __restrict__ D, const float* __restrict__ Ax,
                                                                const float* __restrict__ Bx) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc::smem_align1024(smem_raw);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -94,7 +94,7 @@ namespace samble {
 template <int NT>
 __global__ void __launch_bounds__(128) tc_mma_rate_kernel(int iters, long long* cycles_out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc::smem_align1024(smem_raw);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -152,7 +152,7 @@ namespace samble {
 template <int NT, int NACC, int NA>
 __global__ void __launch_bounds__(128) tc_mma_rate_ex_kernel(int iters, long long* cycles_out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc::smem_align1024(smem_raw);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;

@@ -146,7 +146,7 @@ template <int EPI, int NKT>
 __global__ void __launch_bounds__(kXgThreads, 1)
     xgemm_kernel(const __grid_constant__ XgMaps maps, XgArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = tc::smem_align1024(smem_raw);
   constexpr int nkt = NKT;                                    // K tiles of 64 bf16 (128-byte rows): Cp = 64 * NKT
   uint8_t* sA = base;                                         // [plane][kt] tiles of 128 rows x 128 B
   uint8_t* sB = sA + (size_t)kXgDigits * nkt * 16384;         // ring
