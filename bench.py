@@ -499,7 +499,11 @@ def run_native(args):
         sampler.stop_flag = True
         sampler.join()
 
-        # per-kernel device time of one profiled forward (CUDA events around every launch of ours)
+        # per-kernel device time of one profiled forward (CUDA events around every launch of ours); the concurrent branches
+        # (ops.fork: neighbour search beside the projections) are serialised for this census so that every event pair
+        # times its kernel alone -- the timed steps above ran with them on
+        from samble_b200 import ops as _ops
+        _ops.CONCURRENT_BRANCHES = False
         L.profile(True)
         torch.cuda.synchronize()
         t0 = torch.cuda.Event(enable_timing=True)
@@ -512,6 +516,7 @@ def run_native(args):
         prof = L.profile_report()
         L.profile(False)
         census = linear_census(lambda: model(*ins))
+        _ops.CONCURRENT_BRANCHES = True
         north = knn_sampling_path(model, lambda: model(*ins), B, N, nb, pk, pk_src, flush) if rank == 0 else None
 
     value = B * world * args.steps / (ms / 1e3)

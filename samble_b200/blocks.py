@@ -123,7 +123,7 @@ def fused_edge_mlp(x: Tensor, idx: Tensor, weights) -> Tensor:
     """x (B,Cin,N), idx (B,N,K) -> (B,C2,N): one library GEMM over the N points + the fused kernel."""
     w_pr, bias_pr, w2, b2 = weights
     pr = ops.linear(x, w_pr, x_layout="bcn", out_layout="rows", shift=bias_pr)                  # (B,N,2*C1)
-    return ops.edge_mlp_max(pr, idx, w2, b2)
+    return ops.edge_mlp_max(pr, idx() if callable(idx) else idx, w2, b2)
 
 
 class EdgeConv(nn.Module):
@@ -156,7 +156,7 @@ class EdgeConv(nn.Module):
             x, _ = ops.group(x, self.K, self.group_type, self.normal_channel)
             return self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0]
         key = x[:, :3, :] if (self.normal_channel and x.shape[1] == 6) else x
-        idx = ops.knn_indices(key, self.K, ordered=False)
+        idx = ops.fork(lambda: ops.knn_indices(key, self.K, ordered=False))      # concurrent with the point projections
         params = [self.conv1[0].weight, self.conv2[0].weight, *self.conv1[1].parameters(), *self.conv1[1].buffers(),
                   *self.conv2[1].parameters(), *self.conv2[1].buffers()]
         weights = self._fold.get(params, lambda: edge_mlp_weights(self.conv1[0], self.conv1[1], self.conv2[0],
@@ -201,8 +201,8 @@ class Neighbor2PointAttention(nn.Module):
             raise NotImplementedError("native Neighbor2PointAttention covers group_type='diff', "
                                       "attention_mode='scalar_dot', asm='dot' (the shipped configs)")
         B, C, N = x.shape
-        idx = ops.knn_indices(x, self.K, ordered=False)                                        # (B,N,K) int32
         if differentiable(self, x):
+            idx = ops.knn_indices(x, self.K, ordered=False)                                    # (B,N,K) int32
             # train mode / gradients: the same hoisted form, projections and BatchNorm (batch statistics) in ATen, the
             # attention core and its backward native (autograd.N2PAttend) -- still no (B,C,N,K) tensor in either direction
             w = torch.cat([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C)
@@ -213,11 +213,12 @@ class Neighbor2PointAttention(nn.Module):
         w = self._wqkv.get([self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], lambda: torch.cat(
             [self.q_conv.weight, self.k_conv.weight, self.v_conv.weight], dim=0).view(3 * C, C).contiguous())
         # eval: everything point-major, projections / feed-forward on the tensor cores, BatchNorms folded into epilogues
+        join_idx = ops.fork(lambda: ops.knn_indices(x, self.K, ordered=False))  # (B,N,K) int32, concurrent with the projection
         x_pm = ops.rows_of(x)                                                   # (B,N,C)
         qkv = ops.linear(x_pm, w)                                               # (B,N,3C)
         a1, b1 = folded(self.bn1)
         a2, b2 = folded(self.bn2)
-        x1 = ops.n2p_attend(qkv, idx, self.num_heads, residual=x_pm, scale=a1, shift=b1)     # bn1(x + attention)
+        x1 = ops.n2p_attend(qkv, join_idx(), self.num_heads, residual=x_pm, scale=a1, shift=b1)     # bn1(x + attention)
         h = ops.linear(x1, self.ff[0].weight, lrelu=True)                       # (B,N,4C)
         y = ops.linear(h, self.ff[2].weight, scale=a2, shift=b2, residual=x1, residual_first=True)      # (B,N,C)
         return y.transpose(1, 2)          # the reference's (B,C,N) shape as a view of point-major storage (ops.rows_of)
@@ -330,6 +331,7 @@ class DownSampleToken(nn.Module):
         # The two contractions that decide the sampled indices run on the exact-product tensor-core GEMM (csrc/xgemm.cu):
         # fp32-class accuracy independent of accumulation order (the 3xTF32 kernels' logit error is exponentiated here).
         exact = DS_EXACT and C <= 128 and C % 4 == 0 and D == C
+        join_idx = ops.fork(lambda: ops.knn_indices(x, self.K, ordered=False))                # neighbor_mask's kNN (:301), concurrent
         if exact:
             x_rows = ops.rows_of(x)                                            # (B,N,C)
             qkv, amax = ops.xgemm(ops.digits(x_rows), ops.weight_digits(w), amax_group=C)     # (B,N,3C) + max|q|,|k|,|v| per cloud
@@ -340,7 +342,6 @@ class DownSampleToken(nn.Module):
         k_tok = torch.matmul(tok, self.k_conv.weight.view(C, C).t()).contiguous()   # (nb,D)
         v_tok = torch.matmul(tok, self.v_conv.weight.view(C, C).t())
 
-        idx = ops.knn_indices(x, self.K, ordered=False)                                       # neighbor_mask's kNN (:301)
         k_split = None
         if exact:
             qd, kd = ops.digits(q, amax, 0), ops.digits(k, amax, 1)
@@ -348,7 +349,7 @@ class DownSampleToken(nn.Module):
         else:
             k_split = ops.split_operand(k) if (self.M % 128 == 0 and N <= 4096) else None     # for the M selected rows
             rowmax, rowsum, tok_logits = ops.ds_row_stats(q, k, k_tok, k_split=k_split)
-        score = ops.ds_edge_score(q, k, rowmax, rowsum, idx)                   # (B,N)
+        score = ops.ds_edge_score(q, k, rowmax, rowsum, join_idx())            # (B,N)
         self.attention_point_score = score.view(B, 1, N)
 
         if self.dynamic_boundaries_enable:

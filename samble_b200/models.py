@@ -62,7 +62,7 @@ class STN(nn.Module):
         (seg_model.py:182-184 + embedding.py:81-85), so eval mode reuses the fused edge-MLP kernel."""
         if blocks.differentiable(self, x):
             return self.forward(ops.group(x, K, "center_diff")[0])
-        idx = ops.knn_indices(x, K, ordered=False)
+        idx = ops.fork(lambda: ops.knn_indices(x, K, ordered=False))
         params = [self.conv1[0].weight, self.conv2[0].weight, *self.conv1[1].parameters(), *self.conv1[1].buffers(),
                   *self.conv2[1].parameters(), *self.conv2[1].buffers()]
         weights = self._fold.get(params, lambda: blocks.edge_mlp_weights(self.conv1[0], self.conv1[1], self.conv2[0],

@@ -83,6 +83,44 @@ def knn_indices(pcd: Tensor, K: int, idx_dtype=torch.int32, ordered: bool = True
     return _knn_strided(pcd, pcd, K, "bcn", False, idx_dtype, ordered)[1]
 
 
+# ------------------------------------------------------------------ concurrent branches
+#
+# Inside a block the neighbour search and the dense projections depend on the same input and on nothing else, and
+# neither fills the GPU alone (a 512-point layer launches 64 search CTAs on 148 SMs; the persistent GEMM kernels have
+# tails).  `fork(fn)` runs fn on a per-device side stream and returns a join() that makes the current stream wait for
+# it; under CUDA-graph capture the two become parallel branches of the graph.  Scratch space is per (device, stream)
+# (_lib.workspace), so the branches never share a workspace.
+
+CONCURRENT_BRANCHES = True
+_SIDE_STREAMS: dict = {}
+
+
+def fork(fn):
+    """Run fn() on the side stream; returns join() -> fn's result, valid on the current stream afterwards."""
+    if not CONCURRENT_BRANCHES:
+        out = fn()
+        return lambda: out
+    main = torch.cuda.current_stream()
+    key = main.device.index
+    side = _SIDE_STREAMS.get(key)
+    if side is None:
+        side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=main.device)
+    side.wait_stream(main)                       # everything fn reads has been produced on the current stream
+    with torch.cuda.stream(side):
+        out = fn()
+    done = torch.cuda.Event()
+    done.record(side)
+
+    def join():
+        main.wait_event(done)
+        for t in (out if isinstance(out, (tuple, list)) else (out,)):
+            if isinstance(t, torch.Tensor):
+                t.record_stream(main)            # allocated on the side stream, consumed here
+        return out
+
+    return join
+
+
 # ------------------------------------------------------------------ gathers
 
 
