@@ -205,6 +205,10 @@ int samble_n2p_attend(const float* q, const float* k, const float* v, long long 
                       const float* residual, long long ld_res, const float* scale, const float* shift,
                       float* out, long long ld_out, samble_stream_t stream);
 
+/* measurement only (tools/probe_knn.py): low byte: disable phases of knn_tc_kernel (1 MMAs, 2 epilogue; results are garbage
+ * while set); bits 8..: CTAs per cluster forced to 1, 2 or 4 (0 = automatic). */
+void samble_set_knn_debug(int bits);
+
 /* measurement only (tools/probe_linear.py): disable phases of linear_tma_kernel (1 operand split, 2 epilogue, 4 MMAs);
  * results are garbage while any bit is set.  0 = normal. */
 void samble_set_linear_debug(int bits);

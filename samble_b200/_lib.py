@@ -56,6 +56,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_set_ds_mode": (None, (_i,)),
     "samble_set_n2p_mode": (None, (_i,)),
     "samble_set_linear_debug": (None, (_i,)),
+    "samble_set_knn_debug": (None, (_i,)),
     "samble_ds_row_stats": (_i, (_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p)),
     "samble_digits_bytes": (_sz, (_i, _i, _i)),
     "samble_digits": (_i, (_p, _ll, _ll, _i, _i, _i, _p, _i, _p, _p, _p, _p)),

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) n2p_attend_kernel(const float* __restrict
 // points at once.  With D = 32 channels per head, float4 number f belongs to head f / 8 = c: every lane holds one partial
 // dot product PER HEAD, and a transposing butterfly (2 + 1 + 1 shuffles) leaves head (sub >> 1)'s logit in lane `sub`.
 template <class I>
-__global__ void __launch_bounds__(256, 2) n2p_attend8_kernel(const float* __restrict__ q, const float* __restrict__ k,
+__global__ void __launch_bounds__(256, 3) n2p_attend8_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                               const float* __restrict__ v, long long ld,
                                                               const I* __restrict__ idx, int N, int K, float sqrt_d,
                                                               const float* __restrict__ residual, long long ld_res,

@@ -32,7 +32,11 @@ namespace samble {
 
 constexpr int kTcRows = 128;      // query rows per CTA
 constexpr int kTcTile = 128;      // candidates per tile
-constexpr int kTcStages = 5;      // smem ring depth (16 KB each)
+constexpr int kTcStages = 5;      // smem ring depth (16 KB each), collect pass
+// The threshold pass needs neither the query-side lo plane nor the candidate lists: their room goes to the ring.  The
+// candidate stream is LATENCY-bound by the bytes in flight per SM, not by L2 bandwidth (tools/probe_knn.py: loads alone
+// take 27 of 37 us, and halving the L2 traffic with cluster multicast changes nothing), so depth is what buys time.
+constexpr int kTcStagesA = 10;
 constexpr int kExt = 4096;        // compact non-swizzled [128 x 32 B] slice (tc::smem_desc_nosw)
 constexpr int kTcCap = 120;       // usable candidate-list entries per row (a row that reaches it is redone exactly)
 constexpr int kTcListLd = 128;    // list row pitch in global memory (32-bit entries)
@@ -40,8 +44,8 @@ constexpr int kTcListSm = 129;    // ... and in shared memory: odd, so the 32 ro
 constexpr int kTcThreads = 192;   // 4 epilogue warps + MMA issuer + TMA producer
 
 static size_t tc_smem_bytes(int nkt, bool pass_b) {
-  return (size_t)2 * nkt * 16384 + (size_t)kTcStages * 16384 /* A hi+lo + B ring */ + 3 * kExt /* A_ext, B_ext x2 */
-         + (pass_b ? (size_t)kTcRows * kTcListSm * 4 : 0) + 1024 + 256;
+  return (size_t)(pass_b ? 2 : 1) * nkt * 16384 + (size_t)(pass_b ? kTcStages : kTcStagesA) * 16384 /* A hi[+lo] + B ring */
+         + 3 * kExt /* A_ext, B_ext x2 */ + (pass_b ? (size_t)kTcRows * kTcListSm * 4 : 0) + 1024 + 256;
 }
 
 // |d~ - d_fp32| <= e.  Operands: x = hi + lo + eps, |eps| <= 2^-18 |x| (two bf16 roundings), and the al.bl product is
@@ -90,27 +94,33 @@ __device__ __forceinline__ void sort64(float (&v)[64]) {
   }
 }
 
-template <bool PASS_B>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// CS = CTAs per cluster (1, 2 or 4 consecutive query tiles of one cloud).  Every CTA streams ALL candidate tiles, so with
+// CS = 1 the L2 -> SM traffic is (Nq / 128) x the candidate planes; phase ablation (tools/probe_knn.py) showed the loads
+// alone taking 27 of 37 us (threshold) and 37 of 71 us (collect) at N = 2048, C = 128 -- the kernel is bound by that stream.
+// In a cluster each stage of the candidate ring is fetched by ONE CTA (round robin) and multicast into all of them; a stage
+// is released when the MMAs of every CTA have retired (multicast tcgen05.commit onto every CTA's empty[] barrier).
+template <bool PASS_B, int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
     knn_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                   const float* __restrict__ anorm, const float* __restrict__ bext, const unsigned* __restrict__ bbmax_bits,
                   int Nq, int Nr, int Cp, int k, float* __restrict__ thr, uint32_t* __restrict__ cand_out,
-                  int* __restrict__ cnt_out) {
+                  int* __restrict__ cnt_out, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = tc::smem_align1024(smem_raw);
   const int nkt = (Cp + 63) / 64;                           // K-tiles of 64 bf16 (128-byte rows) per plane
-  constexpr int kPlanes = PASS_B ? 2 : 1;                   // candidate-side planes streamed per tile (pass A: hi only)
-  uint8_t* sA = base;                                       // query tile: [hi: nkt tiles][lo: nkt tiles]
-  uint8_t* sB = sA + (size_t)2 * nkt * 16384;               // ring
-  uint8_t* sAx = sB + (size_t)kTcStages * 16384;            // query-side norm slice: (1,1,0,...) per row
+  constexpr int kPlanes = PASS_B ? 2 : 1;                   // planes per operand (pass A: hi only)
+  constexpr int kStages = PASS_B ? kTcStages : kTcStagesA;
+  uint8_t* sA = base;                                       // query tile: [hi: nkt tiles][lo: nkt tiles (pass B)]
+  uint8_t* sB = sA + (size_t)kPlanes * nkt * 16384;         // ring
+  uint8_t* sAx = sB + (size_t)kStages * 16384;              // query-side norm slice: (1,1,0,...) per row
   uint8_t* sBx = sAx + kExt;                                // candidate-side norm slice, double buffered per tile
   uint8_t* tail = sBx + 2 * kExt;
   uint32_t* cand = reinterpret_cast<uint32_t*>(tail);                                 // [128][kTcListSm]   (pass B)
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + (PASS_B ? kTcRows * kTcListSm * 4 : 0));
-  uint64_t* full = bars;                      // [kTcStages]
-  uint64_t* empty = bars + kTcStages;         // [kTcStages]
-  uint64_t* tfull = bars + 2 * kTcStages;     // [2]
+  uint64_t* full = bars;                      // [kStages]
+  uint64_t* empty = bars + kStages;           // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;       // [2]
   uint64_t* tempty = tfull + 2;               // [2]
   uint64_t* xempty = tempty + 2;              // [2]  norm slice of tile t may be overwritten (its MMA retired)
   uint64_t* afull = xempty + 2;               // query tile landed
@@ -119,6 +129,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, q0 = blockIdx.x * kTcRows;
   const int ntiles = (Nr + kTcTile - 1) / kTcTile;
+  const uint32_t crank = CS > 1 ? tc::cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
 
   // ---- one-time setup: query-side norm slice, barriers, TMEM ----
   for (int p = tid; p < 256; p += kTcThreads) {
@@ -128,9 +140,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
   tc::fence_proxy_async();
   if (tid == 0) {
-    for (int s = 0; s < kTcStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       tc::mbar_init(&full[s], 1);
-      tc::mbar_init(&empty[s], 1);
+      tc::mbar_init(&empty[s], CS);              // one multicast commit per CTA of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(&tfull[a], 1);
@@ -143,6 +155,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
   tc::tc_fence_before();
   __syncthreads();
+  if (CS > 1) tc::cluster_sync();               // every CTA's barriers exist before a peer multicasts into them
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -153,17 +166,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       tc::tma_prefetch_desc(&map_b_hi);
       tc::tma_prefetch_desc(&map_b_lo);
       // resident query tile, both planes: boxes of [128 rows x 64 bf16]; rows past Nq / channels past Cp read as zero
-      tc::mbar_arrive_expect_tx(afull, (uint32_t)(2 * nkt) * 16384u);
+      tc::mbar_arrive_expect_tx(afull, (uint32_t)(kPlanes * nkt) * 16384u);
       for (int kt = 0; kt < nkt; ++kt) {
         tc::tma_load_3d(sA + (size_t)kt * 16384, &map_a_hi, afull, kt * 64, q0, b);
-        tc::tma_load_3d(sA + (size_t)(nkt + kt) * 16384, &map_a_lo, afull, kt * 64, q0, b);
+        if (PASS_B) tc::tma_load_3d(sA + (size_t)(nkt + kt) * 16384, &map_a_lo, afull, kt * 64, q0, b);
       }
       const float* ext_g = bext + (size_t)b * ntiles * (kExt / 4);
       int s = 0, ph = 0;
+      uint32_t seq = 0;                                     // stage sequence number: CTA (seq mod CS) fetches it for the cluster
       for (int t = 0; t < ntiles; ++t) {
-        for (int g = 0; g < kPlanes * nkt; ++g) {           // stage order per tile: (kt 0: hi[, lo]), (kt 1: hi[, lo]), ...
+        for (int g = 0; g < kPlanes * nkt; ++g, ++seq) {    // stage order per tile: (kt 0: hi[, lo]), (kt 1: hi[, lo]), ...
           const int kt = PASS_B ? g >> 1 : g;
-          tc::mbar_wait(&empty[s], ph ^ 1);
+          tc::mbar_wait(&empty[s], ph ^ 1);                 // the MMAs of EVERY CTA of the cluster have retired from stage s
           if (g == 0) {
             // the tile's norm slice rides on the barrier of its first stage; buffer t&1 is free once the norm
             // MMA of tile t-2 retired
@@ -173,8 +187,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           } else {
             tc::mbar_arrive_expect_tx(&full[s], 16384u);
           }
-          tc::tma_load_3d(sB + (size_t)s * 16384, (PASS_B && (g & 1)) ? &map_b_lo : &map_b_hi, &full[s], kt * 64, t * kTcTile, b);
-          if (++s == kTcStages) { s = 0; ph ^= 1; }
+          const CUtensorMap* mp = (PASS_B && (g & 1)) ? &map_b_lo : &map_b_hi;
+          if (CS == 1)
+            tc::tma_load_3d(sB + (size_t)s * 16384, mp, &full[s], kt * 64, t * kTcTile, b);
+          else if (seq % CS == crank)
+            tc::tma_load_3d_multicast(sB + (size_t)s * 16384, mp, &full[s], kt * 64, t * kTcTile, b, kMask);
+          if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -197,7 +215,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const uint64_t ah = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)kt * 16384));
           const uint64_t al = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)(nkt + kt) * 16384));
           const uint64_t bd = tc::smem_desc_sw128(tc::smem_u32(sB + (size_t)s * 16384));
-          if (!PASS_B || (g & 1) == 0) {                    // B_hi tile: ah.bh (+ al.bh in pass B)
+          if (dbg & 1) {
+            // (measurement: no MMAs)
+          } else if (!PASS_B || (g & 1) == 0) {                    // B_hi tile: ah.bh (+ al.bh in pass B)
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) tc::mma_bf16(tmem + acc * kTcTile, ah + 2 * k16, bd + 2 * k16, idesc, (g | k16) != 0);
             if (PASS_B) {
@@ -210,11 +230,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           }
           if (g == kPlanes * nkt - 1) {
             // norm slice of tile t: landed with full[] of the tile's first stage, which this thread waited on
-            tc::mma_bf16(tmem + acc * kTcTile, axd, tc::smem_desc_nosw(tc::smem_u32(sBx + (size_t)(t & 1) * kExt), 128), idesc, 1);
+            if (!(dbg & 1)) tc::mma_bf16(tmem + acc * kTcTile, axd, tc::smem_desc_nosw(tc::smem_u32(sBx + (size_t)(t & 1) * kExt), 128), idesc, 1);
             tc::mma_commit(&xempty[t & 1]);
           }
-          tc::mma_commit(&empty[s]);                // smem stage reusable once these MMAs retire
-          if (++s == kTcStages) { s = 0; ph ^= 1; }
+          if (CS == 1) tc::mma_commit(&empty[s]);   // smem stage reusable once these MMAs retire ...
+          else tc::mma_commit_multicast(&empty[s], kMask);          // ... in every CTA of the cluster
+          if (++s == kStages) { s = 0; ph ^= 1; }
         }
         tc::mma_commit(&tfull[acc]);                // accumulator complete
       }
@@ -239,6 +260,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const int acc = t & 1;
       tc::mbar_wait(&tfull[acc], (t >> 1) & 1);
       tc::tc_fence_after();
+      if (!(dbg & 2))
 #pragma unroll
       for (int c0 = 0; c0 < kTcTile; c0 += 64) {
         float v[64];
@@ -298,6 +320,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (CS > 1) tc::cluster_sync();               // no CTA leaves while a peer can still arrive on its barriers
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
@@ -529,6 +552,11 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict
   }
 }
 
+// measurement switches (tools/probe_knn.py): 1 = no MMAs, 2 = idle epilogue.  Results are garbage while set.
+int g_knn_tc_debug = 0;
+// CTAs per cluster: -1 = automatic (2 when the number of query tiles is even), 1 / 2 / 4 forced (4 needs a multiple of 4 tiles)
+int g_knn_cluster = -1;
+
 // ---- host side ----
 size_t knn_tc_ext_floats(int B, int Nr);
 bool knn_tc_eligible(int Nq, int Nr, int C, int k) {
@@ -556,22 +584,23 @@ int launch_knn_tc(const float* an, const float* anorm, const float* bn, const fl
   if (int e = make_tile_map(&map_b, b_hi, Cp, Cp, Nr, B, kTcTile, 2)) return e;
   if (int e = make_tile_map(&map_bl, b_lo, Cp, Cp, Nr, B, kTcTile, 2)) return e;
   dim3 grid(ceil_div(Nq, kTcRows), B);
+  const int cs = g_knn_cluster > 0 ? g_knn_cluster : 1;     // clusters sharing the candidate stream: measured no gain (the stream is latency-, not bandwidth-bound), kept switchable
   {
     size_t smem = tc_smem_bytes(nkb, false);
-    auto kern = knn_tc_kernel<false>;
+    auto kern = cs == 2 ? knn_tc_kernel<false, 2> : (cs == 4 ? knn_tc_kernel<false, 4> : knn_tc_kernel<false, 1>);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("knn_tc pass A smem attribute");
     SAMBLE_PRE(st);
-    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_al, map_b, map_bl, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt);
+    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_al, map_b, map_bl, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt, g_knn_tc_debug);
     SAMBLE_LAUNCHED("knn_tc_threshold_kernel");
   }
   {
     size_t smem = tc_smem_bytes(nkb, true);
-    auto kern = knn_tc_kernel<true>;
+    auto kern = cs == 2 ? knn_tc_kernel<true, 2> : (cs == 4 ? knn_tc_kernel<true, 4> : knn_tc_kernel<true, 1>);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("knn_tc pass B smem attribute");
     SAMBLE_PRE(st);
-    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_al, map_b, map_bl, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt);
+    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_al, map_b, map_bl, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt, g_knn_tc_debug);
     SAMBLE_LAUNCHED("knn_tc_collect_kernel");
   }
   SAMBLE_PRE(st);
@@ -594,3 +623,5 @@ template int launch_knn_tc<long long>(const float*, const float*, const float*, 
                                       cudaStream_t);
 
 }  // namespace samble
+
+extern "C" void samble_set_knn_debug(int bits) { samble::g_knn_tc_debug = bits & 0xff; samble::g_knn_cluster = (bits >> 8) ? (bits >> 8) : -1; }
