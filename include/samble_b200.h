@@ -322,6 +322,21 @@ int samble_ds_sample(const float* score, const float* token_logits, const float*
                      long long* idx_out, uint8_t* bin_id, int* counts, int* k_out, float* w_raw, float* z_out,
                      samble_stream_t stream);
 
+/* utils/ops.py:507-592: the per-(cloud, bin) categorical distributions of the 'uniform' (mode 0) / 'random' (mode 1) sampling
+ * modes, p (B, nb, N) row-major (= p.permute(0,2,1).reshape(-1,N) of the reference), from score (B,N) and the membership mask
+ * (B,N,nb) uint8.  random: exp(tanh(zscore(score)) * inv_t) restricted to the bin and normalised, NaN -> 1e-8, with
+ * inv_t = count_of_bin / t_div when t_div > 0 (boltzmann modes 1 / 3: 100 / 200) and inv_t_const otherwise. */
+int samble_sampling_probabilities(const float* score, const uint8_t* mask, int B, int N, int nb, int mode, float inv_t_const,
+                                  float t_div, float* p, samble_stream_t stream);
+
+/* utils/ops.py:174-236 dynamic bin boundaries, the two steps around the rank average (:191-199):
+ * samble_quantile_pick: cut[j-1] = sorted_desc[int(j / nb * n)], j = 1..nb-1 (:182-189);
+ * samble_boundary_ema: cut = cut_sum / world, blended into upper[1:] / lower[:-1] (nb floats each, +-inf sentinels kept or
+ * created) with the momentum factor when has_old (:201-233). */
+int samble_quantile_pick(const float* sorted_desc, long long n, int nb, float* cut, samble_stream_t stream);
+int samble_boundary_ema(const float* cut_sum, int world, float momentum, int has_old, int nb, float* upper, float* lower,
+                        samble_stream_t stream);
+
 /* ------------------------------------------------------------- UpSample ---------
  * models/upsample.py:194-212 + utils/ops.py:68-80 fused: 3-NN of each of the N "up"
  * points among the M selected points in xyz (normalised by the up cloud's statistics,

@@ -235,6 +235,85 @@ __global__ void __launch_bounds__(kSampThreads) ds_sample_kernel(const float* __
 
 }  // namespace samble
 
+namespace samble {
+
+// ---- stochastic sampling modes (reference utils/ops.py:507-592): the per-(cloud, bin) categorical distribution that
+// torch.multinomial draws from, in ONE kernel per cloud instead of ~15 element-wise ATen launches over (B,N,nb).
+//   uniform:  p[b,j,n] = mask[b,n,j]; a bin without points draws from all N (ops.py:512-516)
+//   random:   z = tanh(zscore(score)); p = exp(z * inv_t[j]) * mask / sum_n(...); NaN -> 1e-8 (ops.py:518-592), with
+//             inv_t = count_j / t_div (boltzmann "mode_1" / "mode_3": t_div = 100 / 200) or a constant (modes 2 / 4, number)
+// Output layout (B, nb, N) row-major == p.permute(0, 2, 1).reshape(-1, N) of the reference.
+__global__ void __launch_bounds__(kSampThreads) sampling_prob_kernel(const float* __restrict__ score, const uint8_t* __restrict__ mask,
+                                                                     int N, int nb, int mode, float inv_t_const, float t_div,
+                                                                     float* __restrict__ p) {
+  __shared__ double red[32];
+  __shared__ float s_sum[kMaxBins];
+  __shared__ int s_cnt[kMaxBins];
+  const int b = blockIdx.x;
+  const float* x = score + (long long)b * N;
+  const uint8_t* mk = mask + (long long)b * N * nb;
+  float* out = p + (long long)b * nb * N;
+  if (threadIdx.x < kMaxBins) s_sum[threadIdx.x] = 0.f, s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {                          // bin sizes (deterministic block sums)
+    double c = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) c += mk[(long long)i * nb + j] ? 1.0 : 0.0;
+    const double tot = block_sum(c, red);
+    if (threadIdx.x == 0) s_cnt[j] = (int)tot;
+  }
+  __syncthreads();
+  if (mode == 0) {                                        // uniform
+    for (int j = 0; j < nb; ++j) {
+      const float fill = s_cnt[j] == 0 ? 1.f : 0.f;
+      for (int i = threadIdx.x; i < N; i += blockDim.x) out[(long long)j * N + i] = (mk[(long long)i * nb + j] ? 1.f : 0.f) + fill;
+    }
+    return;
+  }
+  float m, sd;
+  mean_std(x, N, red, m, sd);
+  for (int j = 0; j < nb; ++j) {
+    const float inv_t = t_div > 0.f ? __fdiv_rn((float)s_cnt[j], t_div) : inv_t_const;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const float z = tanhf(__fdiv_rn(__fsub_rn(x[i], m), sd));
+      const float e = mk[(long long)i * nb + j] ? expf(z * inv_t) : 0.f;
+      out[(long long)j * N + i] = e;
+      acc += (double)e;
+    }
+    const double tot = block_sum(acc, red);
+    const float tf = (float)tot;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const float v = __fdiv_rn(out[(long long)j * N + i], tf);
+      out[(long long)j * N + i] = (v != v) ? 1e-8f : v;   // empty bin: 0/0 -> 1e-8 everywhere (ops.py:590)
+    }
+    __syncthreads();
+  }
+}
+
+// dynamic bin boundaries (utils/ops.py:174-236) after the batch sort: pick the nb-1 batch quantiles ...
+__global__ void quantile_pick_kernel(const float* __restrict__ sorted_desc, long long n, int nb, float* __restrict__ cut) {
+  const int j = threadIdx.x + 1;
+  if (j < nb) {
+    const long long pos = (long long)(int)((float)j / (float)nb * (float)n);       // ops.py:182-183 (fp32 product, int truncation)
+    cut[j - 1] = sorted_desc[pos < n ? pos : n - 1];
+  }
+}
+// ... and, after the (nb-1)-float all-reduce, average over ranks and blend into the [upper, lower] pair in place
+// (or create it with the +-inf sentinels when there is no previous pair): one launch instead of ~10 element-wise ones.
+__global__ void boundary_ema_kernel(const float* __restrict__ cut_sum, float inv_world, float momentum, int has_old, int nb,
+                                    float* __restrict__ upper, float* __restrict__ lower) {
+  const int j = threadIdx.x;                              // cut index 0 .. nb-2
+  if (j == 0) upper[0] = INFINITY, lower[nb - 1] = -INFINITY;
+  if (j < nb - 1) {
+    float c = cut_sum[j] * inv_world;
+    if (has_old) c = upper[j + 1] * momentum + (1.f - momentum) * c;
+    upper[j + 1] = c;
+    lower[j] = c;
+  }
+}
+
+}  // namespace samble
+
 using namespace samble;
 
 extern "C" int samble_zscore(const float* score, int rows, int N, float* z, samble_stream_t stream) {
@@ -299,5 +378,36 @@ extern "C" int samble_ds_sample(const float* score, const float* token_logits, c
   ds_sample_kernel<<<B, kSampThreads, smem, (cudaStream_t)stream>>>(score, token_logits, cuts, N, nb, M, npad, idx_out,
                                                                      bin_id, counts, k_out, w_raw, z_out);
   SAMBLE_LAUNCHED("ds_sample_kernel");
+  return SAMBLE_OK;
+}
+
+extern "C" int samble_sampling_probabilities(const float* score, const uint8_t* mask, int B, int N, int nb, int mode, float inv_t_const,
+                                             float t_div, float* p, samble_stream_t stream) {
+  SAMBLE_REQUIRE(score && mask && p, "samble_sampling_probabilities: null pointer");
+  SAMBLE_REQUIRE(B > 0 && N > 0 && nb > 0 && nb <= kMaxBins, "samble_sampling_probabilities: bad shape (nb <= %d)", kMaxBins);
+  SAMBLE_REQUIRE(mode == 0 || mode == 1, "samble_sampling_probabilities: mode must be 0 (uniform) or 1 (random)");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAMBLE_PRE(st);
+  sampling_prob_kernel<<<B, kSampThreads, 0, st>>>(score, mask, N, nb, mode, inv_t_const, t_div, p);
+  SAMBLE_LAUNCHED("sampling_prob_kernel");
+  return SAMBLE_OK;
+}
+
+extern "C" int samble_quantile_pick(const float* sorted_desc, long long n, int nb, float* cut, samble_stream_t stream) {
+  SAMBLE_REQUIRE(sorted_desc && cut && n > 0 && nb > 1 && nb <= kMaxBins, "samble_quantile_pick: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAMBLE_PRE(st);
+  quantile_pick_kernel<<<1, 32, 0, st>>>(sorted_desc, n, nb, cut);
+  SAMBLE_LAUNCHED("quantile_pick_kernel");
+  return SAMBLE_OK;
+}
+
+extern "C" int samble_boundary_ema(const float* cut_sum, int world, float momentum, int has_old, int nb, float* upper, float* lower,
+                                   samble_stream_t stream) {
+  SAMBLE_REQUIRE(cut_sum && upper && lower && world > 0 && nb > 1 && nb <= kMaxBins, "samble_boundary_ema: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAMBLE_PRE(st);
+  boundary_ema_kernel<<<1, 32, 0, st>>>(cut_sum, 1.f / (float)world, momentum, has_old, nb, upper, lower);
+  SAMBLE_LAUNCHED("boundary_ema_kernel");
   return SAMBLE_OK;
 }

@@ -97,7 +97,7 @@ _SIDE_STREAMS: dict = {}
 
 def fork(fn):
     """Run fn() on the side stream; returns join() -> fn's result, valid on the current stream afterwards."""
-    if not CONCURRENT_BRANCHES:
+    if not CONCURRENT_BRANCHES or not torch.cuda.is_available():     # (no GPU: fn raises the library's own "CUDA only" error)
         out = fn()
         return lambda: out
     main = torch.cuda.current_stream()
@@ -706,27 +706,44 @@ def interpolate3_rows(xyz_up: Tensor, xyz_sel: Tensor, feat_rows: Tensor, out: T
 # ------------------------------------------------------------------ bins (reference signatures)
 
 
+def _quantile_pick(ranked: Tensor, num_bins: int) -> Tensor:
+    """cut[j-1] = ranked[int(j / num_bins * n)] (utils/ops.py:182-189), one native launch."""
+    dev = L.need_cuda(ranked)
+    cut = torch.empty(num_bins - 1, dtype=torch.float32, device=dev)
+    L.check(L.lib().samble_quantile_pick(L.ptr(ranked), ranked.numel(), num_bins, L.ptr(cut), L.stream()), "samble_quantile_pick")
+    return cut
+
+
+def _boundary_ema(cut_sum: Tensor, world: int, old_bin_boundaries, num_bins: int, momentum_update_factor: float):
+    """rank average + EMA blend (or creation with the +-inf sentinels) of the [upper, lower] pair (utils/ops.py:198-233), one
+    native launch."""
+    dev = L.need_cuda(cut_sum)
+    if old_bin_boundaries is not None:
+        upper = old_bin_boundaries[0].detach().to(device=dev, dtype=torch.float32).contiguous()
+        lower = old_bin_boundaries[1].detach().to(device=dev, dtype=torch.float32).contiguous()
+    else:
+        upper = torch.empty(1, 1, 1, num_bins, dtype=torch.float32, device=dev)
+        lower = torch.empty(1, 1, 1, num_bins, dtype=torch.float32, device=dev)
+    L.check(L.lib().samble_boundary_ema(L.ptr(cut_sum), world, float(momentum_update_factor), 1 if old_bin_boundaries is not None else 0,
+                                        num_bins, L.ptr(upper), L.ptr(lower), L.stream()), "samble_boundary_ema")
+    return [upper, lower]
+
+
 def update_sampling_score_bin_boundary(old_bin_boundaries, attention_point_score: Tensor, num_bins: int,
                                        momentum_update_factor: float):
-    """utils/ops.py:174-236.  Batch quantiles of the z-scored point score -> [upper, lower] pair,
-    rank-averaged when a process group exists (:191-199) and EMA-blended into the old pair.
-    A training-time, latency-bound step (nb-1 floats): one device sort + NCCL all_reduce."""
+    """utils/ops.py:174-236.  Batch quantiles of the z-scored point score -> [upper, lower] pair, rank-averaged when a
+    process group exists (:191-199) and EMA-blended into the old pair.  One device sort (ATen's radix sort of B*N keys),
+    then two native launches around ONE all_reduce of nb-1 floats (quantile pick; average + EMA + sentinels): a
+    training-time, latency-bound step.  The collective plumbing is covered by a world_size-2 gloo test in which the two
+    native steps are replaced by their oracle statements (tests/test_distributed_cpu.py)."""
     z = attention_point_score
-    n = z.nelement()
-    pos = (torch.arange(1, num_bins) / num_bins * n).int().long().to(z.device)
-    ranked, _ = torch.sort(z.flatten(), dim=0, descending=True)
-    cut = ranked[pos]
+    ranked, _ = torch.sort(z.detach().flatten(), dim=0, descending=True)
+    cut = _quantile_pick(ranked, num_bins)
+    world = 1
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.all_reduce(cut)
-        cut = cut / torch.distributed.get_world_size()
-    if old_bin_boundaries is not None:
-        upper, lower = old_bin_boundaries[0].detach(), old_bin_boundaries[1].detach()
-        cut = upper[0, 0, 0, 1:] * momentum_update_factor + (1 - momentum_update_factor) * cut
-        upper[0, 0, 0, 1:] = cut
-        lower[0, 0, 0, :-1] = cut
-        return [upper, lower]
-    inf = torch.full((1,), float("inf"), device=z.device)
-    return [torch.cat([inf, cut]).reshape(1, 1, 1, num_bins), torch.cat([cut, -inf]).reshape(1, 1, 1, num_bins)]
+        world = torch.distributed.get_world_size()
+    return _boundary_ema(cut, world, old_bin_boundaries, num_bins, momentum_update_factor)
 
 
 def bin_partition(attention_point_score: Tensor, bin_boundaries, dynamic_boundaries_enable: bool,
@@ -762,20 +779,22 @@ def calculate_num_points_to_choose(bin_prob: Tensor, max_num_points: Tensor, tot
 
 
 def sampling_probabilities(attention_point_score: Tensor, bin_points_mask: Tensor, bin_sample_mode: str, boltzmann_t) -> Tensor:
-    """utils/ops.py:507-592: the per-(cloud, bin) categorical distribution the 'uniform' / 'random' sampling modes
-    draw from, (B*nb, N) on the device.  A handful of element-wise ops over (B,N,nb): latency-bound, left to ATen."""
+    """utils/ops.py:507-592: the per-(cloud, bin) categorical distribution the 'uniform' / 'random' sampling modes draw
+    from, (B*nb, N) on the device -- one native launch per batch (csrc/sampler.cu: z-score, tanh, exp, mask, per-bin
+    normalisation in one CTA per cloud) instead of the reference's chain of element-wise ops over (B,N,nb)."""
     import numbers
 
-    B, _, N, nb = bin_points_mask.shape
+    dev = L.need_cuda(attention_point_score, bin_points_mask)
+    B, H, N, nb = bin_points_mask.shape
+    if H != 1:
+        raise ValueError("sampling_probabilities: one attention head expected (reference: 'has to be 1 head')")
+    inv_t, t_div = 0.0, 0.0
     if bin_sample_mode == "uniform":
-        p = bin_points_mask.float().squeeze(dim=1)
-        p = p + (torch.sum(p, dim=1, keepdim=True) == 0)
+        mode = 0
     elif bin_sample_mode == "random":
-        z = (attention_point_score - torch.mean(attention_point_score, dim=2, keepdim=True)) / torch.std(
-            attention_point_score, dim=2, unbiased=False, keepdim=True)
-        z = torch.tanh(z)
+        mode = 1
         if boltzmann_t in ("mode_1", "mode_3"):
-            inv_t = torch.sum(bin_points_mask, dim=2, keepdim=True).float() / (100.0 if boltzmann_t == "mode_1" else 200.0)
+            t_div = 100.0 if boltzmann_t == "mode_1" else 200.0
         elif boltzmann_t == "mode_2":
             inv_t = N / (100.0 * nb)
         elif boltzmann_t == "mode_4":
@@ -784,13 +803,14 @@ def sampling_probabilities(attention_point_score: Tensor, bin_points_mask: Tenso
             inv_t = 1 / boltzmann_t
         else:
             raise NotImplementedError
-        p = torch.exp(z.unsqueeze(3) * inv_t) * bin_points_mask
-        p = p / torch.sum(p, dim=2, keepdim=True)
-        p = p.squeeze(dim=1)
-        p = torch.where(torch.isnan(p), torch.full_like(p, 1e-8), p)
     else:
         raise ValueError("Please check the setting of bin sample mode. It must be topk, multinomial or random!")
-    return p.permute(0, 2, 1).reshape(-1, N)
+    score = _f32(attention_point_score.detach(), "score").reshape(B, N).contiguous()
+    mask = bin_points_mask.reshape(B, N, nb).to(torch.uint8).contiguous()
+    p = torch.empty(B * nb, N, dtype=torch.float32, device=dev)
+    L.check(L.lib().samble_sampling_probabilities(L.ptr(score), L.ptr(mask), B, N, nb, mode, float(inv_t), float(t_div), L.ptr(p),
+                                                  L.stream()), "samble_sampling_probabilities")
+    return p
 
 
 def generating_downsampled_index(M: int, attention_point_score: Tensor, bin_points_mask: Tensor, bin_sample_mode: str,

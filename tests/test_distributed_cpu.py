@@ -11,9 +11,33 @@ from oracle import samble_oracle as O
 from samble_b200 import ops
 
 
+def _cpu_quantile_pick(ranked, num_bins):
+    """the oracle's statement of utils/ops.py:182-189 (stands in for the native launch: this box has no GPU)"""
+    n = ranked.nelement()
+    pos = (torch.arange(1, num_bins) / num_bins * n).int().long()
+    return ranked[pos].clone()
+
+
+def _cpu_boundary_ema(cut_sum, world, old, num_bins, momentum):
+    """the oracle's statement of utils/ops.py:198-233"""
+    cut = cut_sum / world
+    if old is not None:
+        upper, lower = old[0].detach().clone(), old[1].detach().clone()
+        cut = upper[0, 0, 0, 1:] * momentum + (1 - momentum) * cut
+        upper[0, 0, 0, 1:] = cut
+        lower[0, 0, 0, :-1] = cut
+        return [upper, lower]
+    inf = torch.full((1,), float("inf"))
+    return [torch.cat([inf, cut]).reshape(1, 1, 1, num_bins), torch.cat([cut, -inf]).reshape(1, 1, 1, num_bins)]
+
+
 def _worker(rank, world, port, z_all, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    # host logic under test: sort -> local quantiles -> ONE all_reduce of nb-1 floats -> / world -> EMA, state threaded
+    # through calls.  The two native launches are GPU-only; their CPU statements stand in here (and are checked
+    # against the kernels on the GPU by tests/test_gpu_ops.py).
+    ops._quantile_pick, ops._boundary_ema = _cpu_quantile_pick, _cpu_boundary_ema
     try:
         z = z_all[rank]
         bnd = ops.update_sampling_score_bin_boundary(None, z, 4, 0.99)                    # init: rank-mean of local quantiles

@@ -192,6 +192,7 @@ def test_bin_partition_and_topk_ops(N, nb, M):
     bnd_ref, mask_ref = O.bin_partition(score, None, True, 0.99, nb)          # dynamic init
     bnd, mask = ops.bin_partition(cu(score), None, True, 0.99, nb)
     torch.testing.assert_close(bnd[0].cpu(), bnd_ref[0], rtol=2e-6, atol=1e-6)
+    torch.testing.assert_close(bnd[1].cpu(), bnd_ref[1], rtol=2e-6, atol=1e-6)           # [upper, lower], +-inf sentinels included
     # a dynamic cut IS some point's z (ops.py:189), so points tied with it flip on a last-ulp difference of z (ours comes
     # from an fp64 mean / std, the reference's from fp32 ones): every flipped point must sit within a few roundings
     # of a cut, and only whole tie groups may flip (at most one distinct z per cut and cloud)
@@ -204,6 +205,7 @@ def test_bin_partition_and_topk_ops(N, nb, M):
     bnd2_ref, _ = O.bin_partition(score * 1.1, [t.clone() for t in bnd_ref], True, 0.99, nb)
     bnd2, _ = ops.bin_partition(cu(score * 1.1), [t.clone() for t in bnd_ref], True, 0.99, nb)
     torch.testing.assert_close(bnd2[0].cpu(), bnd2_ref[0], rtol=2e-6, atol=1e-6)
+    torch.testing.assert_close(bnd2[1].cpu(), bnd2_ref[1], rtol=2e-6, atol=1e-6)
     w = torch.rand(B, nb, generator=g)
     cnt = mask_s_ref.squeeze(1).sum(1)
     kk = O.calculate_num_points_to_choose(w, cnt, M)
