@@ -184,13 +184,15 @@ int samble_linear_pool(const float* X, long long ldx, const float* W, const floa
  * -> max over K.  conv1 is linear in [x_i ; x_j - x_i], so the caller projects the N points once:
  *   pr (B,N,ld_pr) point-major = [P' | R'],  P'_i = a1*((W1a-W1b) x_i) + b1,  R'_j = a1*(W1b x_j)
  * (a1,b1 = folded BN1), w2 (C2,C1) = diag(a2) W2, b2 (C2) = folded BN2 shift.  idx (B,N,K) from the kNN.
- * out (B,C2,N) channel-major = lrelu(max_k (w2 . lrelu(P'_i + R'_idx[i,k]) + b2)).
+ * out = lrelu(max_k (w2 . lrelu(P'_i + R'_idx[i,k]) + b2)): (B,C2,N) channel-major when out_ld == 0, point-major rows
+ * out[(b*N + n)*out_ld + c] when out_ld >= C2 (a column slice of a wider row-major buffer: the concatenation of several
+ * EdgeConv outputs, models/seg_model.py:98-102, then costs nothing).
  * Limits: K <= 32, C1 % 4 == 0, C1 <= 128, C2 in {32,64,128}.
  * C1 % 32 == 0 and C2 in {64,128} run on the tensor cores (tcgen05, 3xTF32 split, fp32-class accuracy);
  * samble_set_edge_mode(1) forces the FFMA kernel (used by the tests as the cross-check). */
 void samble_set_edge_mode(int mode);
 int samble_edge_mlp_max(const float* pr, long long ld_pr, const void* idx, int idx_bits, const float* w2,
-                        const float* b2, int B, int N, int K, int C1, int C2, float* out, samble_stream_t stream);
+                        const float* b2, int B, int N, int K, int C1, int C2, float* out, long long out_ld, samble_stream_t stream);
 
 /* ------------------------------------------------- Neighbor2Point attention -----
  * models/attention.py:165-185,207-250 (scalar_dot, asm "dot"), with the bias-free

@@ -119,11 +119,11 @@ def edge_mlp_weights(conv1, bn1, conv2, bn2, group_type: str):
     return w_pr, bias_pr, w2, b2.contiguous()
 
 
-def fused_edge_mlp(x: Tensor, idx: Tensor, weights) -> Tensor:
+def fused_edge_mlp(x: Tensor, idx: Tensor, weights, out_rows: Tensor = None) -> Tensor:
     """x (B,Cin,N), idx (B,N,K) -> (B,C2,N): one library GEMM over the N points + the fused kernel."""
     w_pr, bias_pr, w2, b2 = weights
     pr = ops.linear(x, w_pr, x_layout="bcn", out_layout="rows", shift=bias_pr)                  # (B,N,2*C1)
-    return ops.edge_mlp_max(pr, idx() if callable(idx) else idx, w2, b2)
+    return ops.edge_mlp_max(pr, idx() if callable(idx) else idx, w2, b2, out_rows=out_rows)
 
 
 class EdgeConv(nn.Module):
@@ -147,21 +147,26 @@ class EdgeConv(nn.Module):
         self._fold = _FoldCache()
 
     @fp32_forward
-    def forward(self, x: Tensor) -> Tensor:
+    def forward(self, x: Tensor, out_rows: Tensor = None) -> Tensor:
+        """out_rows (optional, ours): a (B,N,C2) row-major slot -- e.g. this layer's columns of the concatenated embedding
+        (seg_model.py:98-102) -- that the fused kernel fills in place; the result is returned as its (B,C2,N) view."""
         if self.group_type not in ("neighbor", "diff", "center_neighbor", "center_diff"):
             raise ValueError(
                 f"group_type should be neighbor, diff, center_neighbor or center_diff, but got {self.group_type}")
         c2 = self.conv2[0].out_channels
         if differentiable(self, x) or self.K > 32 or c2 not in (32, 64, 128) or self.conv1[0].out_channels % 4:
             x, _ = ops.group(x, self.K, self.group_type, self.normal_channel)
-            return self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0]
+            y = self.conv2(self.conv1(x)).max(dim=-1, keepdim=False)[0]
+            if out_rows is not None:
+                out_rows.copy_(y.transpose(1, 2))
+            return y
         key = x[:, :3, :] if (self.normal_channel and x.shape[1] == 6) else x
         idx = ops.fork(lambda: ops.knn_indices(key, self.K, ordered=False))      # concurrent with the point projections
         params = [self.conv1[0].weight, self.conv2[0].weight, *self.conv1[1].parameters(), *self.conv1[1].buffers(),
                   *self.conv2[1].parameters(), *self.conv2[1].buffers()]
         weights = self._fold.get(params, lambda: edge_mlp_weights(self.conv1[0], self.conv1[1], self.conv2[0],
                                                                   self.conv2[1], self.group_type))
-        return fused_edge_mlp(x, idx, weights)
+        return fused_edge_mlp(x, idx, weights, out_rows)
 
 
 class Neighbor2PointAttention(nn.Module):

@@ -24,7 +24,7 @@ template <class I, int CPT>      // CPT = output channels per lane (C2 = 32*CPT)
 __global__ void __launch_bounds__(256, CPT <= 2 ? 2 : 1)
     edge_mlp_max_kernel(const float* __restrict__ pr, long long ld_pr, const I* __restrict__ idx,
                         const float* __restrict__ w2, const float* __restrict__ b2, int N, int K, int C1,
-                        float* __restrict__ out /* (B, C2, N) */) {
+                        float* __restrict__ out /* (B, C2, N), or point-major rows when out_ld > 0 */, long long out_ld) {
   extern __shared__ __align__(16) float sm[];
   const int C2 = 32 * CPT;
   const int ldw = C1 + 4;
@@ -97,20 +97,20 @@ __global__ void __launch_bounds__(256, CPT <= 2 ? 2 : 1)
       if (e < K) m = fmaxf(m, acc[e][c]);
     const int ch = lane + 32 * c;
     m += __ldg(b2 + ch);
-    out[((long long)b * C2 + ch) * N + n] = m > 0.f ? m : 0.2f * m;
+    out[out_ld ? ((long long)b * N + n) * out_ld + ch : ((long long)b * C2 + ch) * N + n] = m > 0.f ? m : 0.2f * m;
   }
 }
 
 template <class I, int CPT>
 static int launch_edge_mlp(const float* pr, long long ld_pr, const I* idx, const float* w2, const float* b2, int B,
-                           int N, int K, int C1, float* out, cudaStream_t st) {
+                           int N, int K, int C1, float* out, long long out_ld, cudaStream_t st) {
   const int C2 = 32 * CPT;
   size_t smem = ((size_t)C2 * (C1 + 4) + (size_t)kEcPoints * K * C1) * sizeof(float);
   auto kern = edge_mlp_max_kernel<I, CPT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("edge_mlp_max smem attribute");
   SAMBLE_PRE(st);
-  kern<<<dim3(ceil_div(N, kEcPoints), B), 256, smem, st>>>(pr, ld_pr, idx, w2, b2, N, K, C1, out);
+  kern<<<dim3(ceil_div(N, kEcPoints), B), 256, smem, st>>>(pr, ld_pr, idx, w2, b2, N, K, C1, out, out_ld);
   SAMBLE_LAUNCHED("edge_mlp_max_kernel");
   return SAMBLE_OK;
 }
@@ -119,7 +119,7 @@ static int launch_edge_mlp(const float* pr, long long ld_pr, const I* idx, const
 bool edge_tc_eligible(int K, int C1, int C2);
 template <class I>
 int edge_mlp_tc(const float* pr, long long ld_pr, const I* idx, const float* w2, const float* b2, int B, int N, int K, int C1,
-                int C2, float* out, cudaStream_t st);
+                int C2, float* out, long long out_ld, cudaStream_t st);
 static int g_edge_mode = 0;   // 0 auto (tcgen05 when eligible), 1 FFMA kernel only
 
 }  // namespace samble
@@ -129,7 +129,7 @@ using namespace samble;
 extern "C" void samble_set_edge_mode(int mode) { g_edge_mode = mode; }
 
 extern "C" int samble_edge_mlp_max(const float* pr, long long ld_pr, const void* idx, int idx_bits, const float* w2,
-                                   const float* b2, int B, int N, int K, int C1, int C2, float* out,
+                                   const float* b2, int B, int N, int K, int C1, int C2, float* out, long long out_ld,
                                    samble_stream_t stream) {
   SAMBLE_REQUIRE(pr && idx && w2 && b2 && out, "samble_edge_mlp_max: null pointer");
   SAMBLE_REQUIRE(B > 0 && N > 0 && B <= 65535, "samble_edge_mlp_max: bad shape");
@@ -139,14 +139,15 @@ extern "C" int samble_edge_mlp_max(const float* pr, long long ld_pr, const void*
   SAMBLE_REQUIRE(ld_pr % 4 == 0 && ld_pr >= 2 * C1 && ((uintptr_t)pr | (uintptr_t)w2) % 16 == 0,
                  "samble_edge_mlp_max: PR/W2 need 16-byte aligned rows");
   SAMBLE_REQUIRE(idx_bits == 32 || idx_bits == 64, "samble_edge_mlp_max: idx_bits must be 32 or 64");
+  SAMBLE_REQUIRE(out_ld == 0 || out_ld >= C2, "samble_edge_mlp_max: out_ld=%lld < C2", out_ld);
   cudaStream_t st = (cudaStream_t)stream;
   if (g_edge_mode == 0 && edge_tc_eligible(K, C1, C2)) {
-    if (idx_bits == 64) return edge_mlp_tc<long long>(pr, ld_pr, (const long long*)idx, w2, b2, B, N, K, C1, C2, out, st);
-    return edge_mlp_tc<int>(pr, ld_pr, (const int*)idx, w2, b2, B, N, K, C1, C2, out, st);
+    if (idx_bits == 64) return edge_mlp_tc<long long>(pr, ld_pr, (const long long*)idx, w2, b2, B, N, K, C1, C2, out, out_ld, st);
+    return edge_mlp_tc<int>(pr, ld_pr, (const int*)idx, w2, b2, B, N, K, C1, C2, out, out_ld, st);
   }
 #define EC_DISPATCH(CPT)                                                                                              \
-  (idx_bits == 64 ? launch_edge_mlp<long long, CPT>(pr, ld_pr, (const long long*)idx, w2, b2, B, N, K, C1, out, st)   \
-                  : launch_edge_mlp<int, CPT>(pr, ld_pr, (const int*)idx, w2, b2, B, N, K, C1, out, st))
+  (idx_bits == 64 ? launch_edge_mlp<long long, CPT>(pr, ld_pr, (const long long*)idx, w2, b2, B, N, K, C1, out, out_ld, st)   \
+                  : launch_edge_mlp<int, CPT>(pr, ld_pr, (const int*)idx, w2, b2, B, N, K, C1, out, out_ld, st))
   if (C2 == 32) return EC_DISPATCH(1);
   if (C2 == 64) return EC_DISPATCH(2);
   return EC_DISPATCH(4);

@@ -22,7 +22,7 @@ __device__ __forceinline__ float ord2f(unsigned u) { return __uint_as_float((u &
 template <class I, int C2>
 __global__ void __launch_bounds__(kEtThreads, 1)
     edge_mlp_tc_kernel(const float* __restrict__ pr, long long ld_pr, const I* __restrict__ idx, const float* __restrict__ w2,
-                       const float* __restrict__ b2, int B, int N, int K, int C1, float* __restrict__ out) {
+                       const float* __restrict__ b2, int B, int N, int K, int C1, float* __restrict__ out, long long out_ld) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = tc::smem_align1024(smem_raw);
   const int nkb = C1 / 32;
@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(kEtThreads, 1)
         if (n < N) {
           const int c = c0 + lane;
           const float y = mine + __ldg(b2 + c);
-          out[((long long)b * C2 + c) * N + n] = y > 0.f ? y : 0.2f * y;
+          // point-major rows (out_ld > 0): lane = channel -> one 128-byte line per warp store; channel-major: stride N
+          out[out_ld ? ((long long)b * N + n) * out_ld + c : ((long long)b * C2 + c) * N + n] = y > 0.f ? y : 0.2f * y;
         }
       }
       tc::tc_fence_before();
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kEtThreads, 1)
 
 template <class I, int C2>
 static int launch_edge_tc(const float* pr, long long ld_pr, const I* idx, const float* w2, const float* b2, int B, int N,
-                          int K, int C1, float* out, cudaStream_t st) {
+                          int K, int C1, float* out, long long out_ld, cudaStream_t st) {
   const int nkb = C1 / 32;
   size_t smem = (size_t)2 * nkb * C2 * 128 + (size_t)kEtStages * 32768 + 1024 + 256;
   auto kern = edge_mlp_tc_kernel<I, C2>;
@@ -203,7 +204,7 @@ static int launch_edge_tc(const float* pr, long long ld_pr, const I* idx, const 
   const long long total = (long long)B * ((N + 3) / 4);
   const int grid = (int)(total < 148 ? total : 148);
   SAMBLE_PRE(st);
-  kern<<<grid, kEtThreads, smem, st>>>(pr, ld_pr, idx, w2, b2, B, N, K, C1, out);
+  kern<<<grid, kEtThreads, smem, st>>>(pr, ld_pr, idx, w2, b2, B, N, K, C1, out, out_ld);
   SAMBLE_LAUNCHED("edge_mlp_tc_kernel");
   return SAMBLE_OK;
 }
@@ -215,11 +216,11 @@ bool edge_tc_eligible(int K, int C1, int C2) {
 
 template <class I>
 int edge_mlp_tc(const float* pr, long long ld_pr, const I* idx, const float* w2, const float* b2, int B, int N, int K, int C1,
-                int C2, float* out, cudaStream_t st) {
-  if (C2 == 64) return launch_edge_tc<I, 64>(pr, ld_pr, idx, w2, b2, B, N, K, C1, out, st);
-  return launch_edge_tc<I, 128>(pr, ld_pr, idx, w2, b2, B, N, K, C1, out, st);
+                int C2, float* out, long long out_ld, cudaStream_t st) {
+  if (C2 == 64) return launch_edge_tc<I, 64>(pr, ld_pr, idx, w2, b2, B, N, K, C1, out, out_ld, st);
+  return launch_edge_tc<I, 128>(pr, ld_pr, idx, w2, b2, B, N, K, C1, out, out_ld, st);
 }
-template int edge_mlp_tc<int>(const float*, long long, const int*, const float*, const float*, int, int, int, int, int, float*, cudaStream_t);
-template int edge_mlp_tc<long long>(const float*, long long, const long long*, const float*, const float*, int, int, int, int, int, float*, cudaStream_t);
+template int edge_mlp_tc<int>(const float*, long long, const int*, const float*, const float*, int, int, int, int, int, float*, long long, cudaStream_t);
+template int edge_mlp_tc<long long>(const float*, long long, const long long*, const float*, const float*, int, int, int, int, int, float*, long long, cudaStream_t);
 
 }  // namespace samble

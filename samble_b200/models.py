@@ -82,11 +82,22 @@ class _BlockBase(nn.Module):
             [blocks.Neighbor2PointAttention(cfg.attention, l) for l in range(len(cfg.attention.K))])
 
     def _front(self, x: Tensor):
-        feats = []
-        for emb in self.embedding_list:
-            x = emb(x)
-            feats.append(x)
-        return self.feature_learning_layer_list[0](torch.cat(feats, dim=1))
+        if blocks.differentiable(self, x):
+            feats = []
+            for emb in self.embedding_list:
+                x = emb(x)
+                feats.append(x)
+            return self.feature_learning_layer_list[0](torch.cat(feats, dim=1))
+        # inference: every EdgeConv writes its columns of the concatenated embedding (seg_model.py:98-102) in place, as
+        # point-major rows -- no torch.cat, and the attention layer reads the rows without a transpose
+        widths = [emb.conv2[0].out_channels for emb in self.embedding_list]
+        B, _, N = x.shape
+        both = torch.empty(B, N, sum(widths), dtype=torch.float32, device=x.device)
+        c0 = 0
+        for emb, w in zip(self.embedding_list, widths):
+            x = emb(x, out_rows=both[..., c0:c0 + w])
+            c0 += w
+        return self.feature_learning_layer_list[0](both.transpose(1, 2))
 
 
 class SegFeatureLearningBlock(_BlockBase):

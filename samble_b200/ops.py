@@ -227,8 +227,8 @@ def rows_of(x: Tensor) -> Tensor:
     """Point-major rows (B,N,C), contiguous, of a cloud given in the reference's (B,C,N) shape.  Block outputs are
     (B,C,N) VIEWS of point-major storage (stride(1) == 1), so between our own blocks this is free; a genuinely
     channel-major tensor is transposed once (samble_transpose)."""
-    if x.dim() == 3 and x.stride(1) == 1 and x.stride(2) == x.shape[1] and x.stride(0) == x.shape[1] * x.shape[2]:
-        return x.transpose(1, 2)
+    if x.dim() == 3 and x.stride(1) == 1 and x.stride(2) >= x.shape[1] and x.stride(0) == x.stride(2) * x.shape[2]:
+        return x.transpose(1, 2)            # (B,N,C) rows, possibly a column slice of a wider buffer (row pitch = stride)
     return transpose12(x)
 
 
@@ -427,17 +427,22 @@ def linear_pool(x: Tensor, weight: Tensor, *, scale: Optional[Tensor] = None, sh
     return omax, omean
 
 
-def edge_mlp_max(pr: Tensor, idx: Tensor, w2: Tensor, b2: Tensor) -> Tensor:
+def edge_mlp_max(pr: Tensor, idx: Tensor, w2: Tensor, b2: Tensor, out_rows: Optional[Tensor] = None) -> Tensor:
     """Fused EdgeConv core (csrc/edgeconv.cu): pr (B,N,2*C1) = [P'|R'] point projections, idx (B,N,K),
-    w2 (C2,C1), b2 (C2) -> (B,C2,N).  models/embedding.py:29-39 after folding eval-mode BatchNorm."""
-    dev = L.need_cuda(pr, idx, w2, b2)
+    w2 (C2,C1), b2 (C2) -> (B,C2,N).  models/embedding.py:29-39 after folding eval-mode BatchNorm.
+    The result is stored point-major -- in `out_rows` (B,N,C2), which may be a column slice of a wider row-major buffer, or
+    in fresh storage -- and handed back in the reference's (B,C2,N) shape as a view of it (ops.rows_of is then free)."""
+    dev = L.need_cuda(pr, idx, w2, b2, out_rows)
     B, N, two_c1 = pr.shape
     C1, C2, K = two_c1 // 2, w2.shape[0], idx.shape[-1]
     w2, b2 = w2.contiguous(), b2.contiguous()
-    out = torch.empty(B, C2, N, dtype=torch.float32, device=dev)
+    if out_rows is None:
+        out_rows = torch.empty(B, N, C2, dtype=torch.float32, device=dev)
+    elif tuple(out_rows.shape) != (B, N, C2) or out_rows.stride(2) != 1 or out_rows.stride(0) != N * out_rows.stride(1):
+        raise RuntimeError("edge_mlp_max: out_rows must be (B,N,C2) rows with unit inner stride and a common pitch")
     L.check(L.lib().samble_edge_mlp_max(L.ptr(pr), pr.stride(1), L.ptr(idx), _idx_bits(idx), L.ptr(w2), L.ptr(b2), B, N, K,
-                                        C1, C2, L.ptr(out), L.stream()), "samble_edge_mlp_max")
-    return out
+                                        C1, C2, L.ptr(out_rows), out_rows.stride(1), L.stream()), "samble_edge_mlp_max")
+    return out_rows.transpose(1, 2)
 
 
 def n2p_attend(qkv: Tensor, idx: Tensor, heads: int, residual: Optional[Tensor] = None,
