@@ -191,6 +191,8 @@ int samble_linear_pool(const float* X, long long ldx, const float* W, const floa
  * C1 % 32 == 0 and C2 in {64,128} run on the tensor cores (tcgen05, 3xTF32 split, fp32-class accuracy);
  * samble_set_edge_mode(1) forces the FFMA kernel (used by the tests as the cross-check). */
 void samble_set_edge_mode(int mode);
+/* measurement only (tools/probe_edge.py): disable phases of edge_mlp_tc_kernel (1 gathers, 8 stage build, 2 MMAs, 4 epilogue). */
+void samble_set_edge_debug(int bits);
 int samble_edge_mlp_max(const float* pr, long long ld_pr, const void* idx, int idx_bits, const float* w2,
                         const float* b2, int B, int N, int K, int C1, int C2, float* out, long long out_ld, samble_stream_t stream);
 

@@ -51,6 +51,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_linear_pool": (_i, (_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p)),
     "samble_linear": (_i, (_p, _ll, _i, _p, _p, _ll, _p, _p, _ll, _i, _p, _ll, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p)),
     "samble_set_edge_mode": (None, (_i,)),
+    "samble_set_edge_debug": (None, (_i,)),
     "samble_edge_mlp_max": (_i, (_p, _ll, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p)),
     "samble_n2p_attend": (_i, (_p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p, _p, _ll, _p)),
     "samble_set_ds_mode": (None, (_i,)),

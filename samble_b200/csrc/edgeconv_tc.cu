@@ -22,7 +22,7 @@ __device__ __forceinline__ float ord2f(unsigned u) { return __uint_as_float((u &
 template <class I, int C2>
 __global__ void __launch_bounds__(kEtThreads, 1)
     edge_mlp_tc_kernel(const float* __restrict__ pr, long long ld_pr, const I* __restrict__ idx, const float* __restrict__ w2,
-                       const float* __restrict__ b2, int B, int N, int K, int C1, float* __restrict__ out, long long out_ld) {
+                       const float* __restrict__ b2, int B, int N, int K, int C1, float* __restrict__ out, long long out_ld, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = tc::smem_align1024(smem_raw);
   const int nkb = C1 / 32;
@@ -98,12 +98,13 @@ __global__ void __launch_bounds__(kEtThreads, 1)
         rv[t] = ok ? __ldg(reinterpret_cast<const float4*>(rbase + (long long)jr * ld_pr) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    if (grp < G) fetch(grp);
+    if (grp < G && !(dbg & 1)) fetch(grp);
     for (int g = grp; g < G; g += 2) {
       const int s = g % kEtStages;
       tc::mbar_wait(&empty[s], ((g / kEtStages) & 1) ^ 1);
       uint8_t* hh = sH + (size_t)s * 32768;
       uint8_t* hl = hh + 16384;
+      if (!(dbg & 8))
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         float4 h;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(kEtThreads, 1)
         *reinterpret_cast<float4*>(hl + off) = lo;
       }
       // this group's next stage: its gathers fly while the fence / arrive / next barrier wait happen
-      if (g + 2 < G) fetch(g + 2);
+      if (g + 2 < G && !(dbg & 1)) fetch(g + 2);
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full[s]);
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(kEtThreads, 1)
           const uint64_t wh = tc::smem_desc_sw128(tc::smem_u32(sWh + (size_t)kb * kWBlock));
           const uint64_t wl = tc::smem_desc_sw128(tc::smem_u32(sWl + (size_t)kb * kWBlock));
           const uint32_t acc = tmem + set * C2;
+          if (!(dbg & 2))
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) {
             tc::mma_tf32(acc, hh + 2 * k8, wh + 2 * k8, idesc, (kb | k8) != 0);
@@ -166,16 +168,26 @@ __global__ void __launch_bounds__(kEtThreads, 1)
       tc::mbar_wait(&tfull[set], (it >> 1) & 1);
       tc::tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + set * C2;
+      if (!(dbg & 4))
 #pragma unroll 1
       for (int c0 = 0; c0 < C2; c0 += 32) {
         float v[32];
         tc::tmem_ld32(taddr + c0, v);
-        float mine = 0.f;
+        // max over the 32 lanes (= the 32 edges of this point) of each of the 32 columns, by a halving butterfly: at
+        // every step a lane keeps the half of its columns selected by one of its lane bits and hands the other half to
+        // its partner -- 31 shuffles + 31 max, after which lane l holds column l.  (One REDUX per column, round 1's
+        // form, needs an order-preserving float->uint map each way: ~300 instructions per block instead of ~125; the
+        // epilogue was 40 % of the kernel at C2 = 128, tools/probe_edge.py.)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float m = ord2f(__reduce_max_sync(kFull, f2ord(v[i])));
-          mine = (lane == i) ? m : mine;
+        for (int w = 16; w >= 1; w >>= 1) {
+          const bool upper = (lane & w) != 0;
+#pragma unroll
+          for (int i = 0; i < w; ++i) {
+            const float keep = upper ? v[i + w] : v[i], send = upper ? v[i] : v[i + w];
+            v[i] = fmaxf(keep, __shfl_xor_sync(kFull, send, w));
+          }
         }
+        const float mine = v[0];
         if (n < N) {
           const int c = c0 + lane;
           const float y = mine + __ldg(b2 + c);
@@ -193,6 +205,9 @@ __global__ void __launch_bounds__(kEtThreads, 1)
   if (warp == 0) tc::tmem_dealloc(tmem, 2 * C2);
 }
 
+// measurement switches (tools/probe_edge.py): 1 = no gathers, 8 = no stage build, 2 = no MMAs, 4 = idle epilogue (garbage results)
+int g_edge_debug = 0;
+
 template <class I, int C2>
 static int launch_edge_tc(const float* pr, long long ld_pr, const I* idx, const float* w2, const float* b2, int B, int N,
                           int K, int C1, float* out, long long out_ld, cudaStream_t st) {
@@ -204,7 +219,7 @@ static int launch_edge_tc(const float* pr, long long ld_pr, const I* idx, const 
   const long long total = (long long)B * ((N + 3) / 4);
   const int grid = (int)(total < 148 ? total : 148);
   SAMBLE_PRE(st);
-  kern<<<grid, kEtThreads, smem, st>>>(pr, ld_pr, idx, w2, b2, B, N, K, C1, out, out_ld);
+  kern<<<grid, kEtThreads, smem, st>>>(pr, ld_pr, idx, w2, b2, B, N, K, C1, out, out_ld, g_edge_debug);
   SAMBLE_LAUNCHED("edge_mlp_tc_kernel");
   return SAMBLE_OK;
 }
@@ -224,3 +239,5 @@ template int edge_mlp_tc<int>(const float*, long long, const int*, const float*,
 template int edge_mlp_tc<long long>(const float*, long long, const long long*, const float*, const float*, int, int, int, int, int, float*, long long, cudaStream_t);
 
 }  // namespace samble
+
+extern "C" void samble_set_edge_debug(int bits) { samble::g_edge_debug = bits; }
