@@ -462,11 +462,11 @@ __device__ __forceinline__ void select_classify(const uint32_t* __restrict__ lis
   }
 }
 
-constexpr int kSelBatch = 8;          // candidate rows fetched per round
+constexpr int kSelBatch = 4;          // candidate rows fetched per round
 constexpr int kSelRowLd = 132;        // floats per parked row (pad 4: the 8 evaluating lanes hit distinct banks)
 
 template <class I>
-__global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict__ an, const float* __restrict__ anorm,
+__global__ void __launch_bounds__(256, 5) knn_select_kernel(const float* __restrict__ an, const float* __restrict__ anorm,
                                                          const float* __restrict__ bn, const float* __restrict__ bnorm,
                                                          const unsigned* __restrict__ bbmax_bits,
                                                          const uint32_t* __restrict__ cand,

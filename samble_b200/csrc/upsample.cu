@@ -13,53 +13,85 @@ int launch_knn_prep_xyz(const float* x, long long sb, long long sn, long long sc
 
 constexpr int kUpChunk = 2048;
 
+// Four threads per up-point (round 2: one thread per point left 2 warps per scheduler scanning 1024 candidates each through a
+// dependent compare chain -- 10 % of the warp slots busy, profiles/r2_step_full.md).  Thread `sub` of a point scans the
+// candidates j = sub (mod 4) in ascending order into its own top 3; the four triples are merged by (distance, index),
+// which is exactly the order the sequential scan's strict `<` produces (ties keep the lower index).
+struct Top3 {
+  float d0, d1, d2;
+  int i0, i1, i2;
+};
+__device__ __forceinline__ bool before(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+__device__ __forceinline__ void top3_insert(Top3& t, float dd, int ii) {           // general insert by (distance, index)
+  if (before(dd, ii, t.d2, t.i2)) {
+    if (before(dd, ii, t.d1, t.i1)) {
+      t.d2 = t.d1, t.i2 = t.i1;
+      if (before(dd, ii, t.d0, t.i0)) t.d1 = t.d0, t.i1 = t.i0, t.d0 = dd, t.i0 = ii;
+      else t.d1 = dd, t.i1 = ii;
+    } else {
+      t.d2 = dd, t.i2 = ii;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) interpolate3_kernel(const float4* __restrict__ up, const float4* __restrict__ sel,
                                                            const float* __restrict__ feat, int N, int M, int C,
                                                            float* __restrict__ out, long long* __restrict__ idx_out,
                                                            float* __restrict__ dist_out, int* __restrict__ nn_idx,
                                                            float* __restrict__ nn_w) {
   __shared__ float4 cand[kUpChunk];
-  const int b = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sub = threadIdx.x & 3;
+  const int b = blockIdx.y, n = blockIdx.x * 32 + (threadIdx.x >> 2);
   const bool live = n < N;
   const float4 q = up[(long long)b * N + (live ? n : N - 1)];
   const float ax = -2.f * q.x, ay = -2.f * q.y, az = -2.f * q.z;
-  float d0 = INFINITY, d1 = INFINITY, d2 = INFINITY;
-  int i0 = 0, i1 = 0, i2 = 0;
+  Top3 t{INFINITY, INFINITY, INFINITY, 0x7ffffffd, 0x7ffffffe, 0x7fffffff};
   for (int c0 = 0; c0 < M; c0 += kUpChunk) {
     const int cn = min(kUpChunk, M - c0);
     __syncthreads();
     for (int j = threadIdx.x; j < cn; j += blockDim.x) cand[j] = sel[(long long)b * M + c0 + j];
     __syncthreads();
-    // four candidates per trip: their distance chains are independent (the kernel has only ~2 warps per scheduler, so
-    // instruction-level parallelism is what hides the FMA latency); the inserts stay in ascending-j order
-    for (int j = 0; j < cn; j += 4) {
+    // four candidates of this thread's residue class per trip: independent distance chains, inserts in ascending j
+    for (int j = sub; j < cn; j += 16) {
       float d[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float4 p = cand[min(j + u, cn - 1)];
-        // same 5-term row as the xyz kNN (knn.cu), ascending j so ties keep the lower index
+        const float4 p = cand[min(j + 4 * u, cn - 1)];
+        // same 5-term row as the xyz kNN (knn.cu)
         float acc = __fmul_rn(ax, p.x);
         acc = __fmaf_rn(ay, p.y, acc);
         acc = __fmaf_rn(az, p.z, acc);
         acc = __fadd_rn(acc, q.w);
         acc = __fadd_rn(acc, p.w);
-        d[u] = (j + u < cn) ? (acc > 0.f ? acc : 0.f) : INFINITY;
+        d[u] = (j + 4 * u < cn) ? (acc > 0.f ? acc : 0.f) : INFINITY;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float dd = d[u];
-        if (dd < d2) {
-          if (dd < d1) {
-            d2 = d1, i2 = i1;
-            if (dd < d0) d1 = d0, i1 = i0, d0 = dd, i0 = c0 + j + u;
-            else d1 = dd, i1 = c0 + j + u;
+        if (dd < t.d2) {                      // (ascending j within a thread: strict < keeps the lower index on ties)
+          const int ii = c0 + j + 4 * u;
+          if (dd < t.d1) {
+            t.d2 = t.d1, t.i2 = t.i1;
+            if (dd < t.d0) t.d1 = t.d0, t.i1 = t.i0, t.d0 = dd, t.i0 = ii;
+            else t.d1 = dd, t.i1 = ii;
           } else {
-            d2 = dd, i2 = c0 + j + u;
+            t.d2 = dd, t.i2 = ii;
           }
         }
       }
     }
   }
+  // merge the four partial triples (lanes sub = 0..3 of the point) -- after two exchange rounds every lane holds the result
+#pragma unroll
+  for (int w = 1; w <= 2; w <<= 1) {
+    const float od0 = __shfl_xor_sync(kFull, t.d0, w), od1 = __shfl_xor_sync(kFull, t.d1, w), od2 = __shfl_xor_sync(kFull, t.d2, w);
+    const int oi0 = __shfl_xor_sync(kFull, t.i0, w), oi1 = __shfl_xor_sync(kFull, t.i1, w), oi2 = __shfl_xor_sync(kFull, t.i2, w);
+    top3_insert(t, od0, oi0);
+    top3_insert(t, od1, oi1);
+    top3_insert(t, od2, oi2);
+  }
+  const float d0 = t.d0, d1 = t.d1, d2 = t.d2;
+  const int i0 = t.i0, i1 = t.i1, i2 = t.i2;
   if (!live) return;
   const float e0 = sqrtf(d0), e1 = sqrtf(d1), e2 = sqrtf(d2);
   // weights = 1/(d+1e-8), normalised by their left-to-right sum (upsample.py:206-209)
@@ -68,15 +100,15 @@ __global__ void __launch_bounds__(128) interpolate3_kernel(const float4* __restr
   float w2 = __fdiv_rn(1.0f, __fadd_rn(e2, 1e-8f));
   const float ws = __fadd_rn(__fadd_rn(w0, w1), w2);
   w0 = __fdiv_rn(w0, ws), w1 = __fdiv_rn(w1, ws), w2 = __fdiv_rn(w2, ws);
-  if (idx_out) {
+  if (idx_out && sub == 0) {
     long long* o = idx_out + ((long long)b * N + n) * 3;
     o[0] = i0, o[1] = i1, o[2] = i2;
   }
-  if (dist_out) {
+  if (dist_out && sub == 0) {
     float* o = dist_out + ((long long)b * N + n) * 3;
     o[0] = e0, o[1] = e1, o[2] = e2;
   }
-  if (nn_idx) {                                       // point-major form: the gather runs in interp3_rows_kernel
+  if (nn_idx && sub == 0) {                           // point-major form: the gather runs in interp3_rows_kernel
     int* o = nn_idx + ((long long)b * N + n) * 3;
     float* ow = nn_w + ((long long)b * N + n) * 3;
     o[0] = i0, o[1] = i1, o[2] = i2;
@@ -85,7 +117,7 @@ __global__ void __launch_bounds__(128) interpolate3_kernel(const float4* __restr
   if (!feat) return;
   const float* f = feat + (long long)b * C * M;
   float* y = out + (long long)b * C * N + n;
-  for (int c = 0; c < C; ++c) {
+  for (int c = sub; c < C; c += 4) {                  // the point's four threads share its channels
     const float* fr = f + (long long)c * M;
     // sum over the 3 neighbours of (feature * weight), products rounded separately (upsample.py:210-212)
     float v = __fmul_rn(__ldg(fr + i0), w0);
@@ -152,7 +184,7 @@ extern "C" int samble_interpolate3(const float* xyz_up, const float* xyz_sel, co
   if (int e = launch_knn_prep_xyz(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, up, st)) return e;
   if (int e = launch_knn_prep_xyz(xyz_sel, 3LL * M, 1, M, B, M, 3, mean, stdv, sel, st)) return e;
   SAMBLE_PRE(st);
-  interpolate3_kernel<<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(up, sel, feat, N, M, C, out, idx_out, dist_out, nullptr,
+  interpolate3_kernel<<<dim3(ceil_div(N, 32), B), 128, 0, st>>>(up, sel, feat, N, M, C, out, idx_out, dist_out, nullptr,
                                                                   nullptr);
   SAMBLE_LAUNCHED("interpolate3_kernel");
   return SAMBLE_OK;
@@ -180,7 +212,7 @@ extern "C" int samble_interpolate3_rows(const float* xyz_up, const float* xyz_se
   if (int e = launch_knn_prep_xyz(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, up, st)) return e;
   if (int e = launch_knn_prep_xyz(xyz_sel, 3LL * M, 1, M, B, M, 3, mean, stdv, sel, st)) return e;
   SAMBLE_PRE(st);
-  interpolate3_kernel<<<dim3(ceil_div(N, 128), B), 128, 0, st>>>(up, sel, nullptr, N, M, C, nullptr, nullptr, nullptr, nn_idx,
+  interpolate3_kernel<<<dim3(ceil_div(N, 32), B), 128, 0, st>>>(up, sel, nullptr, N, M, C, nullptr, nullptr, nullptr, nn_idx,
                                                                   nn_w);
   SAMBLE_LAUNCHED("interpolate3_kernel");
   SAMBLE_PRE(st);
