@@ -360,13 +360,17 @@ __global__ void __launch_bounds__(256) knn_xyz_kernel(const float4* __restrict__
 // ------------------------------------------------------------------------------------------
 constexpr int kXyzCap = 128;          // list entries per query
 
-__device__ __forceinline__ unsigned xyz_dist_bits(float ax, float ay, float az, float aw, const float4 p) {
+// the 5-term GEMM row of torch.cdist in k order, before the clamp at zero
+__device__ __forceinline__ float xyz_dist_raw(float ax, float ay, float az, float aw, const float4 p) {
   float acc = __fmul_rn(ax, p.x);
   acc = __fmaf_rn(ay, p.y, acc);
   acc = __fmaf_rn(az, p.z, acc);
   acc = __fadd_rn(acc, aw);
   acc = __fadd_rn(acc, p.w);
-  return dist_bits(acc);
+  return acc;
+}
+__device__ __forceinline__ unsigned xyz_dist_bits(float ax, float ay, float az, float aw, const float4 p) {
+  return dist_bits(xyz_dist_raw(ax, ay, az, aw, p));
 }
 
 size_t knn_xyz2_smem() { return (size_t)kXyzChunk * sizeof(float4) + (size_t)8 * kXyzQW * kXyzCap * sizeof(unsigned long long); }
@@ -389,24 +393,27 @@ __global__ void __launch_bounds__(256) knn_xyz2_kernel(const float4* __restrict_
     ax[i] = -2.f * q.x, ay[i] = -2.f * q.y, az[i] = -2.f * q.z, aw[i] = q.w;
   }
   // ---- pass 1: 64 group minima per query ----
-  unsigned m0[kXyzQW], m1[kXyzQW];
+  // (round 2, ncu: the kernel issues on the ALU pipe 57 % / FMA pipe 30 % of the time -- the clamp, validity selects and
+  // integer minima cost more than the five float operations of a distance.  Minima are now taken on the RAW
+  // accumulators with one FMNMX and clamped once at the end -- min_j max(x_j, 0) = max(min_j x_j, 0) -- and the tail of
+  // a chunk is padded with sentinel candidates at distance NaN instead of per-pair validity selects.)
+  float m0[kXyzQW], m1[kXyzQW];
 #pragma unroll
-  for (int i = 0; i < kXyzQW; ++i) m0[i] = m1[i] = 0xffffffffu;
+  for (int i = 0; i < kXyzQW; ++i) m0[i] = m1[i] = INFINITY;
+  // NaN distance: ignored by fminf in pass 1, never <= T in pass 2 (even if T is +inf)
+  const float4 sentinel = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00000));
   for (int c0 = 0; c0 < Nr; c0 += kXyzChunk) {
-    const int n = min(kXyzChunk, Nr - c0);
+    const int n = min(kXyzChunk, Nr - c0), npad = (n + 63) & ~63;
     __syncthreads();
-    for (int j = threadIdx.x; j < n; j += blockDim.x) cand[j] = rp[(long long)b * Nr + c0 + j];
+    for (int j = threadIdx.x; j < npad; j += blockDim.x) cand[j] = j < n ? rp[(long long)b * Nr + c0 + j] : sentinel;
     __syncthreads();
     if (!warp_live) continue;
-    for (int j0 = 0; j0 < n; j0 += 64) {
-      const int ja = j0 + lane, jb = j0 + 32 + lane;
-      const float4 pa = cand[ja < n ? ja : 0], pb = cand[jb < n ? jb : 0];
+    for (int j0 = 0; j0 < npad; j0 += 64) {
+      const float4 pa = cand[j0 + lane], pb = cand[j0 + 32 + lane];
 #pragma unroll
       for (int i = 0; i < kXyzQW; ++i) {
-        const unsigned da = xyz_dist_bits(ax[i], ay[i], az[i], aw[i], pa);
-        const unsigned db = xyz_dist_bits(ax[i], ay[i], az[i], aw[i], pb);
-        m0[i] = min(m0[i], ja < n ? da : 0xffffffffu);
-        m1[i] = min(m1[i], jb < n ? db : 0xffffffffu);
+        m0[i] = fminf(m0[i], xyz_dist_raw(ax[i], ay[i], az[i], aw[i], pa));
+        m1[i] = fminf(m1[i], xyz_dist_raw(ax[i], ay[i], az[i], aw[i], pb));
       }
     }
   }
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(256) knn_xyz2_kernel(const float4* __restrict_
   unsigned T[kXyzQW];
 #pragma unroll
   for (int i = 0; i < kXyzQW; ++i) {
-    unsigned x[2] = {m0[i], m1[i]};
+    unsigned x[2] = {dist_bits(m0[i]), dist_bits(m1[i])};
 #pragma unroll
     for (int size = 2; size <= 64; size <<= 1) {
 #pragma unroll
@@ -437,29 +444,29 @@ __global__ void __launch_bounds__(256) knn_xyz2_kernel(const float4* __restrict_
   }
   // ---- pass 2: collect d <= T ----
   int cnt[kXyzQW];
+  float Tf[kXyzQW];                                     // T >= 0, so  max(x, 0) <= T  <=>  x <= T  on the raw accumulator
 #pragma unroll
-  for (int i = 0; i < kXyzQW; ++i) cnt[i] = 0;
+  for (int i = 0; i < kXyzQW; ++i) cnt[i] = 0, Tf[i] = __uint_as_float(T[i]);
   const unsigned lt = (1u << lane) - 1u;
   for (int c0 = 0; c0 < Nr; c0 += kXyzChunk) {
-    const int n = min(kXyzChunk, Nr - c0);
+    const int n = min(kXyzChunk, Nr - c0), npad = (n + 63) & ~63;
     if (Nr > kXyzChunk) {                               // single-chunk clouds keep pass 1's copy
       __syncthreads();
-      for (int j = threadIdx.x; j < n; j += blockDim.x) cand[j] = rp[(long long)b * Nr + c0 + j];
+      for (int j = threadIdx.x; j < npad; j += blockDim.x) cand[j] = j < n ? rp[(long long)b * Nr + c0 + j] : sentinel;
       __syncthreads();
     }
     if (!warp_live) continue;
-    for (int j0 = 0; j0 < n; j0 += 32) {
+    for (int j0 = 0; j0 < npad; j0 += 32) {
       const int j = j0 + lane;
-      const bool valid = j < n;
-      const float4 p = cand[valid ? j : 0];
+      const float4 p = cand[j];
 #pragma unroll
       for (int i = 0; i < kXyzQW; ++i) {
-        const unsigned db = xyz_dist_bits(ax[i], ay[i], az[i], aw[i], p);
-        const bool hit = valid && db <= T[i];
+        const float raw = xyz_dist_raw(ax[i], ay[i], az[i], aw[i], p);
+        const bool hit = raw <= Tf[i];                  // (false for the NaN sentinels)
         const unsigned m = __ballot_sync(kFull, hit);
         if (m) {
           const int pos = cnt[i] + __popc(m & lt);
-          if (hit && pos < kXyzCap) mylist[i * kXyzCap + pos] = ((unsigned long long)db << 32) | (unsigned)(c0 + j);
+          if (hit && pos < kXyzCap) mylist[i * kXyzCap + pos] = ((unsigned long long)dist_bits(raw) << 32) | (unsigned)(c0 + j);
           cnt[i] += __popc(m);
         }
       }
