@@ -328,15 +328,30 @@ def knn_sampling_path(model, run_model, B, N, nb, pk, pk_src, flush):
                     "the algorithmic products, so `executed_frac_of_peak` is the pipe utilisation and `frac` the price of exactness"}
 
 
-def linear_roofline(ms, census, pk):
+def ncu_traffic(family):
+    """DRAM bytes per step of one kernel family from the committed `ncu --set full` capture of the seg step
+    (profiles/r2_traffic.json, written by tools/ncu_table.py); None when the file is absent."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_traffic.json")) as f:
+            return json.load(f)["families"][family]
+    except Exception:
+        return None
+
+
+def linear_roofline(ms, census, pk, workload="seg"):
     """The point-wise linear layers (linear_tma_kernel): 3xTF32 => fp32-equivalent tensor peak = tf32 peak / 3."""
     sec = ms * 1e-3
     tf32 = pk["bf16_tflops_sustained"] / 2
     ach = census["flops"] / sec / 1e12
+    tr = ncu_traffic("linear_tma_kernel") if workload == "seg" else None
     return {"kernel": "linear_tma_kernel (all point-wise linear layers of the step)", "bound": "tensor", "achieved": ach, "peak": tf32 / 3,
             "unit": "TFLOP/s (fp32-equivalent)", "frac": ach / (tf32 / 3), "ms_per_step": ms, "calls_per_step": census["calls"],
             "algorithmic_gb_per_step": census["bytes"] / 1e9, "hbm_gbs": census["bytes"] / sec / 1e9,
             "flop_per_byte": census["flops"] / census["bytes"],
+            "traffic": (tr["dram_bytes_per_step"] / tr["launches_per_step"]) if tr else None,
+            "traffic_note": "DRAM read+write bytes per launch (ncu --set full, profiles/r2_final_full.md), average over the family's "
+                            f"{tr['launches_per_step']} launches of the seg step; algorithmic bytes per launch: "
+                            f"{census['bytes'] / max(census['calls'], 1):.0f}" if tr else None,
             "note": "3 kind::tf32 MMAs per fp32-class product: peak = (bf16 sustained / 2) / 3; the layers sit above the 3xTF32 ridge "
                     "(35 FLOP/B), so the tensor pipe is the binding roof"}
 
@@ -539,7 +554,7 @@ def run_native(args):
                     "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in ins_h)), "d2h_bytes_per_step": int(out_h.numel() * 4)},
             "gpu_launches": launches_per_step * args.steps, "launch_mode": "eager" if args.no_graph else "cuda_graph",
             "roofline": north,
-            "roofline_linear": linear_roofline(native_ms.get("linear_tma_kernel", 0.0) or 1e-9, census, pk),
+            "roofline_linear": linear_roofline(native_ms.get("linear_tma_kernel", 0.0) or 1e-9, census, pk, args.workload),
             "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(native_ms.items(), key=lambda kv: -kv[1])},
             "native_share_of_step": min(1.0, sum(native_ms.values()) / step_ms)}
     if not args.no_cpu_baseline and world == 1:
