@@ -357,6 +357,14 @@ int samble_interpolate3_rows(const float* xyz_up, const float* xyz_sel, const fl
                              int B, int N, int M, int C, float* out, long long ld_out,
                              void* ws, size_t ws_bytes, samble_stream_t stream);
 
+/* the two halves of samble_interpolate3_rows as separate calls: the 3-NN search needs the xyz sets only (so it can run beside
+ * the convolution that produces feat), nn_idx (B,N,3) int32 / nn_w (B,N,3) normalised inverse-distance weights;
+ * the gather then forms out[b,n,:] = sum_j nn_w[b,n,j] * feat[b, nn_idx[b,n,j], :]  (models/upsample.py:206-212). */
+int samble_interpolate3_search(const float* xyz_up, const float* xyz_sel, int B, int N, int M, int* nn_idx, float* nn_w,
+                               void* ws, size_t ws_bytes, samble_stream_t stream);
+int samble_interpolate3_gather_rows(const int* nn_idx, const float* nn_w, const float* feat, long long ld_feat, int B, int N,
+                                    int M, int C, float* out, long long ld_out, samble_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

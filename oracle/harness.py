@@ -32,7 +32,7 @@ def record_decisions(log: List):
     """Record (signature, idx[, dist]) of every neighbour search the native path issues, in call order.  Every search
     goes through ops._knn_strided (knn, knn_indices, group, select_neighbors, select_neighbors_interpolate) except the
     fused 3-NN interpolation, which is asked separately for its neighbours."""
-    real_knn, real_i3r = ops._knn_strided, ops.interpolate3_rows
+    real_knn, real_i3r, real_i3s = ops._knn_strided, ops.interpolate3_rows, ops.interpolate3_search
 
     inputs = getattr(log, "inputs", None)
 
@@ -56,11 +56,21 @@ def record_decisions(log: List):
             inputs.append((xyz_up.detach().transpose(1, 2).cpu(), xyz_sel.detach().transpose(1, 2).cpu()))
         return real_i3r(xyz_up, xyz_sel, feat_rows, out)
 
-    ops._knn_strided, ops.interpolate3_rows = _knn_strided, interpolate3_rows
+    def interpolate3_search(xyz_up, xyz_sel):
+        probe = torch.zeros(xyz_sel.shape[0], 4, xyz_sel.shape[2], device=xyz_sel.device)
+        _, idx, dist = ops.interpolate3(xyz_up, xyz_sel, probe, want_idx=True)
+        log.append(((xyz_up.shape[2], xyz_sel.shape[2], 3, 3), idx.detach().cpu().long(), dist.detach().cpu()))
+        if inputs is not None:
+            inputs.append((xyz_up.detach().transpose(1, 2).cpu(), xyz_sel.detach().transpose(1, 2).cpu()))
+        nn_idx, nn_w = real_i3s(xyz_up, xyz_sel)
+        assert torch.equal(nn_idx.long(), idx)                     # the split search is the fused kernel's search
+        return nn_idx, nn_w
+
+    ops._knn_strided, ops.interpolate3_rows, ops.interpolate3_search = _knn_strided, interpolate3_rows, interpolate3_search
     try:
         yield log
     finally:
-        ops._knn_strided, ops.interpolate3_rows = real_knn, real_i3r
+        ops._knn_strided, ops.interpolate3_rows, ops.interpolate3_search = real_knn, real_i3r, real_i3s
 
 
 class _Log(list):

@@ -78,6 +78,8 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_boundary_ema": (_i, (_p, _i, _f, _i, _i, _p, _p, _p)),
     "samble_interpolate3_workspace_bytes": (_sz, (_i, _i, _i)),
     "samble_interpolate3": (_i, (_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p)),
+    "samble_interpolate3_search": (_i, (_p, _p, _i, _i, _i, _p, _p, _p, _sz, _p)),
+    "samble_interpolate3_gather_rows": (_i, (_p, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p)),
     "samble_interpolate3_rows": (_i, (_p, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p, _sz, _p)),
 }
 

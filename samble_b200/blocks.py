@@ -429,10 +429,12 @@ class UpSampleInterpolation(nn.Module):
             # point-major throughout: [pcd_up | interpolated] is assembled as rows (the interpolation writes its half in
             # place), res_conv reads it as a GEMM operand, the result is handed on as a (B,C,N) view of rows
             B, C, N = pcd_up.shape
+            search = ops.fork(lambda: ops.interpolate3_search(pcd_up_xyz, points_select_xyz))   # needs xyz only: parallel branch
             feat = cbl(self.conv, points_select, out_layout="rows")                        # (B,M,C')
             both = torch.empty(B, N, C + feat.shape[2], dtype=torch.float32, device=pcd_up.device)
             both[..., :C].copy_(ops.rows_of(pcd_up))
-            ops.interpolate3_rows(pcd_up_xyz, points_select_xyz, feat, both[..., C:])
+            nn_idx, nn_w = search()
+            ops.interpolate3_gather_rows(nn_idx, nn_w, feat, both[..., C:])
             return cbl(self.res_conv, both, x_layout="rows", out_layout="rows").transpose(1, 2)
         interpolated = self.interpolate(pcd_up, points_select, pcd_up_xyz, points_select_xyz,
                                         distance_type=self.distance_type, K=self.K)

@@ -221,3 +221,40 @@ extern "C" int samble_interpolate3_rows(const float* xyz_up, const float* xyz_se
   return SAMBLE_OK;
 }
 
+
+// The two halves of samble_interpolate3_rows as separate calls, so that the 3-NN search (xyz only) can run as a parallel
+// graph branch beside the convolution that produces `feat` (samble_b200.ops.fork).
+extern "C" int samble_interpolate3_search(const float* xyz_up, const float* xyz_sel, int B, int N, int M, int* nn_idx, float* nn_w,
+                                          void* ws, size_t ws_bytes, samble_stream_t stream) {
+  SAMBLE_REQUIRE(xyz_up && xyz_sel && nn_idx && nn_w && ws, "samble_interpolate3_search: null pointer");
+  SAMBLE_REQUIRE(B > 0 && N > 0 && B <= 65535, "samble_interpolate3_search: bad shape");
+  SAMBLE_REQUIRE(M >= 3, "samble_interpolate3_search: need at least 3 selected points, got %d", M);
+  SAMBLE_REQUIRE(ws_bytes >= interp_bytes(B, N, M), "samble_interpolate3_search: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w(ws, ws_bytes);
+  float* mean = w.take<float>((size_t)B * 3);
+  float* stdv = w.take<float>((size_t)B * 3);
+  float4* up = w.take<float4>((size_t)B * N);
+  float4* sel = w.take<float4>((size_t)B * M);
+  if (int e = launch_knn_stats(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, st, nullptr)) return e;
+  if (int e = launch_knn_prep_xyz(xyz_up, 3LL * N, 1, N, B, N, 3, mean, stdv, up, st)) return e;
+  if (int e = launch_knn_prep_xyz(xyz_sel, 3LL * M, 1, M, B, M, 3, mean, stdv, sel, st)) return e;
+  SAMBLE_PRE(st);
+  interpolate3_kernel<<<dim3(ceil_div(N, 32), B), 128, 0, st>>>(up, sel, nullptr, N, M, 0, nullptr, nullptr, nullptr, nn_idx, nn_w);
+  SAMBLE_LAUNCHED("interpolate3_kernel");
+  return SAMBLE_OK;
+}
+
+extern "C" int samble_interpolate3_gather_rows(const int* nn_idx, const float* nn_w, const float* feat, long long ld_feat, int B, int N,
+                                               int M, int C, float* out, long long ld_out, samble_stream_t stream) {
+  SAMBLE_REQUIRE(nn_idx && nn_w && feat && out, "samble_interpolate3_gather_rows: null pointer");
+  SAMBLE_REQUIRE(B > 0 && N > 0 && M >= 3 && C > 0 && B <= 65535, "samble_interpolate3_gather_rows: bad shape");
+  SAMBLE_REQUIRE(C % 4 == 0 && ld_feat % 4 == 0 && ld_out % 4 == 0 && ld_feat >= C && ld_out >= C &&
+                     ((uintptr_t)feat | (uintptr_t)out) % 16 == 0,
+                 "samble_interpolate3_gather_rows: rows must be 16-byte aligned multiples of 4 channels");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAMBLE_PRE(st);
+  interp3_rows_kernel<<<dim3(ceil_div(N, 8), B), 256, 0, st>>>(nn_idx, nn_w, feat, ld_feat, N, M, C, out, ld_out);
+  SAMBLE_LAUNCHED("interp3_rows_kernel");
+  return SAMBLE_OK;
+}

@@ -708,6 +708,43 @@ def interpolate3_rows(xyz_up: Tensor, xyz_sel: Tensor, feat_rows: Tensor, out: T
     return out
 
 
+def interpolate3_search(xyz_up: Tensor, xyz_sel: Tensor):
+    """3-NN of every up point among the selected points + normalised inverse-distance weights (models/upsample.py:194-209):
+    xyz_up (B,3,N), xyz_sel (B,3,M) -> nn_idx (B,N,3) int32, nn_w (B,N,3).  Needs the coordinates only."""
+    dev = L.need_cuda(xyz_up, xyz_sel)
+    L.no_grad_check(xyz_up, xyz_sel)
+    xyz_up, xyz_sel = (_f32(t, "xyz").contiguous() for t in (xyz_up, xyz_sel))
+    B, three, N = xyz_up.shape
+    M = xyz_sel.shape[2]
+    if three != 3 or xyz_sel.shape[1] != 3:
+        raise ValueError("interpolate3: xyz tensors must be (B,3,N)")
+    nn_idx = torch.empty(B, N, 3, dtype=torch.int32, device=dev)
+    nn_w = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.samble_interpolate3_workspace_bytes(B, N, M), dev)
+    L.check(lib.samble_interpolate3_search(L.ptr(xyz_up), L.ptr(xyz_sel), B, N, M, L.ptr(nn_idx), L.ptr(nn_w), L.ptr(ws), ws.numel(),
+                                           L.stream()), "samble_interpolate3_search")
+    return nn_idx, nn_w
+
+
+def interpolate3_gather_rows(nn_idx: Tensor, nn_w: Tensor, feat_rows: Tensor, out: Tensor) -> Tensor:
+    """out[b,n,:] = sum_j nn_w[b,n,j] * feat_rows[b, nn_idx[b,n,j], :] (models/upsample.py:210-212); feat_rows (B,M,C), out
+    (B,N,C) rows with unit inner stride (may be a column slice of a wider buffer)."""
+    L.need_cuda(nn_idx, nn_w, feat_rows, out)
+    L.no_grad_check(feat_rows)
+    feat_rows = _f32(feat_rows, "feat")
+    if feat_rows.stride(2) != 1:
+        feat_rows = feat_rows.contiguous()
+    B, N, _ = nn_idx.shape
+    M, Cc = feat_rows.shape[1], feat_rows.shape[2]
+    if tuple(out.shape) != (B, N, Cc) or out.stride(2) != 1 or out.stride(0) != N * out.stride(1) or \
+            feat_rows.stride(0) != M * feat_rows.stride(1):
+        raise RuntimeError("interpolate3_gather_rows: out must be (B,N,C) rows with a common pitch")
+    L.check(L.lib().samble_interpolate3_gather_rows(L.ptr(nn_idx), L.ptr(nn_w), L.ptr(feat_rows), feat_rows.stride(1), B, N, M, Cc,
+                                                    L.ptr(out), out.stride(1), L.stream()), "samble_interpolate3_gather_rows")
+    return out
+
+
 # ------------------------------------------------------------------ bins (reference signatures)
 
 
