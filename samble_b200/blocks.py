@@ -288,12 +288,24 @@ class DownSampleToken(nn.Module):
 
     # -- helpers -------------------------------------------------------------------------------
     def _cuts(self, device) -> Tensor:
-        """the nb-1 finite thresholds of the [upper, lower] pair, checked non-increasing once per change."""
+        """the nb-1 finite thresholds of the [upper, lower] pair.  The native partition assigns a point to the FIRST bin whose
+        interval holds its z-score, which equals the reference's mask (utils/ops.py:460-462) only for non-increasing cuts
+        with lower[j] == upper[j+1]; that is checked once per boundary update outside graph capture (one host sync) and
+        anything else is refused rather than partitioned differently."""
         upper = self.bin_boundaries[0]
         if upper.device != device:
             self.bin_boundaries = [t.to(device) for t in self.bin_boundaries]
             upper = self.bin_boundaries[0]
-        return upper.reshape(-1)[1:].to(torch.float32).contiguous()
+        cuts = upper.reshape(-1)[1:].to(torch.float32).contiguous()
+        key = (upper.data_ptr(), upper._version, self.bin_boundaries[1].data_ptr(), self.bin_boundaries[1]._version)
+        if key != getattr(self, "_cuts_checked", None) and not self.dynamic_boundaries_enable and not torch.cuda.is_current_stream_capturing():
+            lower = self.bin_boundaries[1].reshape(-1)[:-1].to(device=device, dtype=torch.float32)
+            ok = bool(((cuts[:-1] >= cuts[1:]).all() if cuts.numel() > 1 else torch.tensor(True)) & (lower == cuts).all())
+            if not ok:
+                raise ValueError("DownSampleToken: bin boundaries must be non-increasing with lower[j] == upper[j+1] "
+                                 "(the [upper, lower] pair utils/ops.py:174-236 maintains)")
+            self._cuts_checked = key
+        return cuts
 
     @fp32_forward
     def forward(self, x: Tensor, x_xyz=None):

@@ -601,3 +601,25 @@ def test_n2p_attend_eight_lane_kernel_vs_warp_per_point_and_fp64(B, N, C, K, H):
         finally:
             L.lib().samble_set_n2p_mode(0)
     assert close_frac(outs[0][0], outs[1][0].cpu(), 1e-5, 1e-5) == 1.0
+
+
+@pytest.mark.parametrize("D,K", [(64, 32), (192, 20), (32, 8)])
+def test_ds_edge_score_other_widths(D, K):
+    """samble_ds_edge_score accepts any D % 4 == 0; widths whose 16-byte chunk count is not a multiple of 32
+    (D = 64: 16 chunks, D = 192: 48) leave some lanes without a chunk -- the neighbour-index broadcasts must not sit in that
+    divergent loop.  Checked against the fp64 statement of models/downsample.py:300-344."""
+    B, N, nb = 2, 384, 4
+    g = torch.Generator().manual_seed(D + K)
+    q, k = torch.randn(B, N, D, generator=g), torch.randn(B, N, D, generator=g)
+    idx = torch.stack([torch.stack([torch.randperm(N, generator=g)[:K] for _ in range(N)]) for _ in range(B)])
+    logits = q.double() @ k.double().transpose(1, 2) / math.sqrt(D)
+    m = logits.max(-1)[0]
+    ssum = torch.exp(logits - m.unsqueeze(-1)).sum(-1)
+    amap = torch.exp(logits - m.unsqueeze(-1)) / ssum.unsqueeze(-1)
+    mask = torch.zeros(B, N, N, dtype=torch.float64).scatter_(2, idx, 1.0)
+    indeg = mask.sum(1)
+    ref = (amap * mask).sum(1) / (indeg + 1e-8) / (indeg + 1e-8)
+    ref = torch.where(torch.isnan(ref), torch.zeros_like(ref), ref)
+    for bits in (torch.int32, torch.int64):
+        score = ops.ds_edge_score(cu(q), cu(k), cu(m.float()), cu(ssum.float()), cu(idx.to(bits)))
+        torch.testing.assert_close(score.cpu().double(), ref, atol=1e-12, rtol=2e-4)
