@@ -513,6 +513,12 @@ def run_native(args):
         ms_e2e, per_rank_e2e, _ = timed(step_e2e, args.steps, tail_fn=(pipe.wait_all if pipe is not None else None))
         sampler.stop_flag = True
         sampler.join()
+        # every rank samples ITS OWN GPU: a rank that runs slower than its peers shows here whether clocks / a power or
+        # thermal cap explain it (the job is timed as the maximum over ranks)
+        clocks_all = [sampler.result()]
+        if world > 1:
+            clocks_all = [None] * world
+            dist.all_gather_object(clocks_all, sampler.result())
 
         # per-kernel device time of one profiled forward (CUDA events around every launch of ours); the concurrent branches
         # (ops.fork: neighbour search beside the projections) are serialised for this census so that every event pair
@@ -549,6 +555,7 @@ def run_native(args):
             "scaling": "strong" if args.global_batch is not None else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, B), "clocks": sampler.result(),
             "per_rank_ms_per_step": [round(t / args.steps, 4) for t in per_rank],
+            "per_rank_clocks": [{"sm_mhz": c["sm_mhz"], "reasons": c["reasons"]} for c in clocks_all],
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "per_rank_ms_per_step": [round(t / args.steps, 4) for t in per_rank_e2e],
                     "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in ins_h)), "d2h_bytes_per_step": int(out_h.numel() * 4)},

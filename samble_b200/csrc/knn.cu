@@ -769,8 +769,8 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
     if (int e = launch_knn_tc<I>(an, anorm, bn, bnorm, a_hi, a_lo, b_hi, b_lo, bext, bbmax, B, Nq, Nr, Cp, k, thr, cand, cand_cnt, ordered, idx_out,
                                  dist_out, row_flags, st))
       return e;
-    // rows whose candidate buffer overflowed are redone by the exact kernel (normally none: every tile exits at once)
-    return launch_knn_feat<DotTileCfg<4>, I>(an, anorm, bn, bnorm, B, Nq, Nr, C, Cp, k, idx_out, dist_out, row_flags, st);
+    // (rows whose candidate list saturated were searched exactly by their own warp inside knn_select / knn_rerank)
+    return SAMBLE_OK;
   }
   // 128-row CTAs when they still give every SM at least ~2 CTAs of work, else 64-row CTAs
   const bool big = (long long)ceil_div(Nq, 128) * B >= 2 * 148 && knn_feat_smem<DotTileCfg<8>>(Cp) <= 200 * 1024;

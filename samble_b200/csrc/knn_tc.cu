@@ -324,6 +324,51 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+// A row the tensor-core passes could not finish (list saturated: more than kTcCap candidates above the threshold, e.g. many
+// near-duplicate points) is searched exactly by ITS OWN warp: every candidate's fp32 distance with the exact kernel's
+// arithmetic (ascending channels, one accumulator, d2 = fma(-2, dot, |a|^2 + |b|^2)) through the running k-set.  Round 1
+// sent such rows to the exact TILE kernel, which recomputes all 128 rows of the row's tile against every candidate on one
+// SM: ~0.25 ms for a single flagged row -- the whole of the unexplained rank skew of the multi-GPU runs
+// (profiles/r2_scaling.md: two of eight batch slices hold a few such rows).  Here it costs that warp ~40 us.
+template <class I>
+__device__ __forceinline__ void knn_exact_row(const float* __restrict__ arow, float aa, const float* __restrict__ B_g,
+                                              const float* __restrict__ bnorm_g, int Nr, int Cp, int k, int lane,
+                                              I* __restrict__ idx_row, float* __restrict__ dist_row, bool ordered) {
+  const float4* ar = reinterpret_cast<const float4*>(arow);
+  LaneTopK top;
+  top.init(lane, k);
+  for (int j0 = 0; j0 < Nr; j0 += 128) {                 // four candidates per lane and trip: independent FMA chains
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* br[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) br[u] = reinterpret_cast<const float4*>(B_g + (size_t)min(j0 + 32 * u + lane, Nr - 1) * Cp);
+#pragma unroll 2
+    for (int c4 = 0; c4 < Cp / 4; ++c4) {
+      const float4 a4 = __ldg(ar + c4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 b4 = __ldg(br[u] + c4);
+        acc[u] = fmaf(a4.x, b4.x, acc[u]);
+        acc[u] = fmaf(a4.y, b4.y, acc[u]);
+        acc[u] = fmaf(a4.z, b4.z, acc[u]);
+        acc[u] = fmaf(a4.w, b4.w, acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                        // offered in ascending index order: LaneTopK's contract
+      const int j = j0 + 32 * u + lane;
+      const bool have = j < Nr;
+      const float d2 = __fmaf_rn(-2.f, acc[u], __fadd_rn(aa, __ldg(bnorm_g + min(j, Nr - 1))));
+      top.offer(dist_bits(d2), j, have);
+    }
+  }
+  const int pos = ordered ? top.rank() : lane;
+  if (top.active) {
+    idx_row[pos] = (I)top.i;
+    if (dist_row) dist_row[pos] = -sqrtf(__uint_as_float(top.d));
+  }
+}
+
 // ---- pass C: exact fp32 re-rank.  One warp per query row, lanes across its candidates. ----
 template <class I>
 __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict__ an, const float* __restrict__ anorm,
@@ -337,14 +382,14 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   if (q >= Nq) return;
   const size_t rowi = (size_t)b * Nq + q;
   const int cnt = cnt_in[rowi];
-  if (cnt >= kTcCap) {                                  // saturated list: hand the row to the exact kernel
-    if (lane == 0) row_flags[rowi] = 1, row_flags[(size_t)gridDim.y * Nq] = 1;   // (last slot: "some row needs repair")
-    return;
-  }
   const float aa = anorm[rowi];
   const float4* ar = reinterpret_cast<const float4*>(an + rowi * Cp);
   const float* B_g = bn + (size_t)b * Nr * Cp;
   const float* bnorm_g = bnorm + (size_t)b * Nr;
+  if (cnt >= kTcCap) {                                  // saturated list: this warp searches the row exactly
+    knn_exact_row<I>(an + rowi * Cp, aa, B_g, bnorm_g, Nr, Cp, k, lane, idx_out + rowi * k, dist_out ? dist_out + rowi * k : nullptr, true);
+    return;
+  }
   LaneTopK top;
   top.init(lane, k);
   for (int r = 0; r < cnt; r += 32) {
@@ -482,11 +527,11 @@ __global__ void __launch_bounds__(256, 5) knn_select_kernel(const float* __restr
   if (q >= Nq) return;
   const size_t rowi = (size_t)b * Nq + q;
   const int cnt = cnt_in[rowi];
-  if (cnt >= kTcCap) {                                  // saturated list: hand the row to the exact kernel
-    if (lane == 0) row_flags[rowi] = 1, row_flags[(size_t)gridDim.y * Nq] = 1;   // (last slot: "some row needs repair")
+  const float aa = anorm[rowi];
+  if (cnt >= kTcCap) {                                  // saturated list: this warp searches the row exactly
+    knn_exact_row<I>(an + rowi * Cp, aa, bn + (size_t)b * Nr * Cp, bnorm + (size_t)b * Nr, Nr, Cp, k, lane, idx_out + rowi * k, nullptr, false);
     return;
   }
-  const float aa = anorm[rowi];
   const float e = knn_margin(aa, __uint_as_float(bbmax_bits[b])) * 1.001f;
   int n_in = 0, n_amb = 0;
   const uint32_t* list = cand + rowi * kTcListLd;
@@ -501,7 +546,8 @@ __global__ void __launch_bounds__(256, 5) knn_select_kernel(const float* __restr
   const int need = k - n_in;
   if (need <= 0) return;                                // (n_in <= k always: an "in" entry has at most k-1 rivals)
   if (n_amb < need) {                                   // cannot happen while the margin holds; stay safe
-    if (lane == 0) row_flags[rowi] = 1, row_flags[(size_t)gridDim.y * Nq] = 1;   // (last slot: "some row needs repair")
+    __syncwarp();
+    knn_exact_row<I>(an + rowi * Cp, aa, bn + (size_t)b * Nr * Cp, bnorm + (size_t)b * Nr, Nr, Cp, k, lane, idx_out + rowi * k, nullptr, false);
     return;
   }
   __syncwarp();
