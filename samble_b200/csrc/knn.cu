@@ -748,9 +748,8 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   __nv_bfloat16* b_hi = self ? a_hi : w.take<__nv_bfloat16>((size_t)B * Nr * Cp);
   __nv_bfloat16* b_lo = self ? a_lo : w.take<__nv_bfloat16>((size_t)B * Nr * Cp);
   const bool use_tc = g_knn_mode != 1 && knn_tc_eligible(Nq, Nr, C, k);
-  if (use_tc) {   // row_flags and bbmax are adjacent (256-byte granules): one memset node
-    const size_t span = (size_t)((char*)(bbmax + B) - (char*)row_flags);
-    if (cudaMemsetAsync(row_flags, 0, span, st) != cudaSuccess) return check_launch("memset knn flags");
+  if (use_tc) {   // per-cloud maximum candidate norm: an atomicMax target of the prep kernel
+    if (cudaMemsetAsync(bbmax, 0, (size_t)B * sizeof(unsigned), st) != cudaSuccess) return check_launch("memset knn bbmax");
     count_launch();
   }
   SAMBLE_PRE(st);
