@@ -102,6 +102,9 @@ int samble_knn(const float* a, long long a_sb, long long a_sn, long long a_sc,
  * R = M*K rows per cloud. */
 int samble_index_points(const float* points, const void* idx, int idx_bits, int B, int N, int C, int R,
                         float* out, samble_stream_t stream);
+/* 0 (default): rows move through the copy engine (cp.async.bulk loads into a shared-memory tile, one bulk store per tile) when they
+ * are 16-byte aligned; 1: the thread-copy kernel only (cross-check). */
+void samble_set_gather_mode(int mode);
 
 /* utils/ops.py:47-65,83-112  select_neighbors/group, AFTER the kNN.
  * pcd (B,C,N) channel-major, idx (B,N,K).

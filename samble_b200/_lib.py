@@ -56,6 +56,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_n2p_attend": (_i, (_p, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p, _p, _ll, _p)),
     "samble_set_ds_mode": (None, (_i,)),
     "samble_set_n2p_mode": (None, (_i,)),
+    "samble_set_gather_mode": (None, (_i,)),
     "samble_set_linear_debug": (None, (_i,)),
     "samble_set_knn_debug": (None, (_i,)),
     "samble_ds_row_stats": (_i, (_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p)),

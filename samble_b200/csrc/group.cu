@@ -3,6 +3,7 @@
 // All are HBM-write-bound copies; the job is to keep every store a full 128 B line and every
 // gather an L1/L2 hit.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace samble {
 
@@ -24,6 +25,51 @@ __global__ void __launch_bounds__(256) index_points_kernel(const float* __restri
       out[((long long)b * R + r) * C + l] = __ldg(pts + ((long long)b * N + j) * C + l);
     }
   }
+}
+
+// The same gather with the copy engine (north star: "neighbour-gather kernels with TMA-staged feature tiles").  A warp owns
+// a run of G consecutive output rows: every lane issues ONE bulk copy (cp.async.bulk, UBLKCP) of its source row into the
+// warp's shared-memory tile, the byte count lands on an mbarrier, and one lane hands the whole tile -- G rows, contiguous
+// in the output -- back to the copy engine as a single bulk store.  No data passes through registers; loads of run r+1
+// are issued while the store of run r drains (two tiles per warp).  Needs 16-byte aligned rows (C % 4 == 0).
+constexpr int kIpWarps = 8;
+template <class I>
+__global__ void __launch_bounds__(kIpWarps * 32) index_points_bulk_kernel(const float* __restrict__ pts, const I* __restrict__ idx,
+                                                                          int N, int C, long long R, float* __restrict__ out, int G) {
+  extern __shared__ __align__(128) uint8_t ip_smem[];
+  __shared__ uint64_t bars[kIpWarps][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
+  const uint32_t row_bytes = (uint32_t)C * 4u;
+  uint8_t* tile = ip_smem + (size_t)warp * 2 * G * row_bytes;
+  if (lane == 0) {
+    tc::mbar_init(&bars[warp][0], 1);
+    tc::mbar_init(&bars[warp][1], 1);
+    tc::mbar_init_fence();
+  }
+  __syncwarp();
+  const long long runs = (R + G - 1) / G;
+  int use = 0;
+  for (long long run = (long long)blockIdx.x * kIpWarps + warp; run < runs; run += (long long)gridDim.x * kIpWarps, ++use) {
+    const int buf = use & 1;
+    const long long r0 = run * G;
+    const int g = (int)min((long long)G, R - r0);
+    uint8_t* dst = tile + (size_t)buf * G * row_bytes;
+    if (lane == 0) {
+      tc::bulk_wait_read<1>();                           // the store issued from this buffer two runs ago has read it
+      tc::mbar_arrive_expect_tx(&bars[warp][buf], (uint32_t)g * row_bytes);
+    }
+    __syncwarp();
+    for (int t = lane; t < g; t += 32) {
+      const int j = ld_idx(idx, (long long)b * R + r0 + t);
+      tc::bulk_load_1d(dst + (size_t)t * row_bytes, pts + ((long long)b * N + j) * C, row_bytes, &bars[warp][buf]);
+    }
+    tc::mbar_wait(&bars[warp][buf], (use >> 1) & 1);
+    if (lane == 0) {
+      tc::bulk_store_1d(out + ((long long)b * R + r0) * C, dst, (uint32_t)g * row_bytes);
+      tc::bulk_commit();
+    }
+  }
+  if (lane == 0) tc::bulk_wait<0>();
 }
 
 // neighbor / diff from a CHANNEL-major cloud into (B,N,K,C): a 32-point x 32-channel tile is
@@ -141,6 +187,9 @@ static int group_impl(const float* pcd, const I* idx, int B, int C, int N, int K
 
 using namespace samble;
 
+static int g_gather_mode = 0;   // 0: copy-engine (bulk) row gather where rows are 16-byte aligned, 1: thread-copy kernel only
+extern "C" void samble_set_gather_mode(int mode) { g_gather_mode = mode; }
+
 #define IDX_DISPATCH(bits, CALL64, CALL32) ((bits) == 64 ? (CALL64) : (CALL32))
 
 extern "C" int samble_index_points(const float* points, const void* idx, int idx_bits, int B, int N, int C, int R,
@@ -150,6 +199,28 @@ extern "C" int samble_index_points(const float* points, const void* idx, int idx
   SAMBLE_REQUIRE(idx_bits == 32 || idx_bits == 64, "samble_index_points: idx_bits must be 32 or 64");
   if (R == 0) return SAMBLE_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_gather_mode == 0 && C % 4 == 0 && C >= 16 && (size_t)C * 4 <= 4096 && ((uintptr_t)points | (uintptr_t)out) % 16 == 0) {
+    // copy-engine path: tiles of G rows (<= 32, one bulk load per lane) up to 16 KB, two per warp
+    int G = (int)(8192 / ((size_t)C * 4));
+    G = G > 32 ? 32 : (G < 1 ? 1 : G);
+    const size_t smem = (size_t)kIpWarps * 2 * G * C * 4;
+    auto k64 = index_points_bulk_kernel<long long>;
+    auto k32 = index_points_bulk_kernel<int>;
+    if (cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch("index_points_bulk smem attribute");
+    const long long runs = ((long long)R + G - 1) / G;
+    long long gx = (runs + kIpWarps - 1) / kIpWarps;
+    const long long cap = (148LL * 8 + B - 1) / B;
+    dim3 gridb((unsigned)(gx < 1 ? 1 : (gx > cap ? cap : gx)), B);
+    SAMBLE_PRE(st);
+    if (idx_bits == 64)
+      k64<<<gridb, kIpWarps * 32, smem, st>>>(points, (const long long*)idx, N, C, R, out, G);
+    else
+      k32<<<gridb, kIpWarps * 32, smem, st>>>(points, (const int*)idx, N, C, R, out, G);
+    SAMBLE_LAUNCHED("index_points_bulk_kernel");
+    return SAMBLE_OK;
+  }
   dim3 grid(grid_for((long long)R * (C % 4 == 0 ? C / 4 : C), 256), B);
   SAMBLE_PRE(st);
   if (idx_bits == 64)

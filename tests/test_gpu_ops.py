@@ -450,3 +450,21 @@ def test_index_topk_with_negative_and_zero_scores():
         rest = torch.ones(N, dtype=torch.bool)
         rest[seg] = False
         assert float(got.min()) >= float(v[rest].max())                                # nothing better was left out
+
+
+@pytest.mark.parametrize("B,N,C,M,K", [(2, 2048, 128, 2048, 32), (3, 300, 64, 77, 5), (1, 1000, 16, 1000, 3), (2, 500, 1024, 33, 2), (2, 100, 12, 50, 7)])
+def test_index_points_copy_engine_vs_thread_copy(B, N, C, M, K):
+    """samble_index_points: the cp.async.bulk staged gather (tiles of rows loaded by the copy engine, one bulk store per
+    tile) and the thread-copy kernel both equal torch.gather (utils/ops.py:5-14), int32 and int64 indices."""
+    from samble_b200 import _lib as L
+    g = torch.Generator().manual_seed(B * N + C)
+    pts = torch.randn(B, N, C, generator=g)
+    idx = torch.randint(0, N, (B, M, K), generator=g)
+    ref = torch.gather(pts, 1, idx.reshape(B, -1, 1).expand(-1, -1, C)).view(B, M, K, C)
+    for mode in (0, 1):
+        L.lib().samble_set_gather_mode(mode)
+        try:
+            for dt in (torch.int64, torch.int32):
+                assert torch.equal(ops.index_points(cu(pts), cu(idx).to(dt)).cpu(), ref), (mode, dt)
+        finally:
+            L.lib().samble_set_gather_mode(0)
