@@ -59,6 +59,12 @@ int samble_selftest_tc_gemm(const float* A, const float* B, int K, float* D, con
                             const float* Bx /* 128x8 or NULL: adds Ax*Bx^T from a non-swizzled slice */,
                             samble_stream_t stream);
 
+/* the same product with the A operand read from TENSOR MEMORY (parked there with tcgen05.st): the form csrc/mlp2.cu uses to
+ * feed the hidden activations of a two-layer point-wise MLP to its second GEMM.  K % 32 == 0, K <= 256.  iters > 0 repeats
+ * the MMA sequence (D = iters * A B^T) on `ctas` CTAs and writes the SM cycles of each to cycles_out (may be NULL). */
+int samble_selftest_tc_gemm_ts(const float* A, const float* B, int K, float* D, int iters, int ctas, long long* cycles_out,
+                               samble_stream_t stream);
+
 /* issue-rate probe: `ctas` CTAs each issue iters*4 back-to-back kind::tf32 128 x n_tile x 8 MMAs on resident smem tiles;
  * cycles_out[cta] = SM cycles from first issue to completion (measured tensor-pipe ceiling of the SS form). */
 int samble_selftest_mma_rate(int n_tile, int iters, int ctas, long long* cycles_out, samble_stream_t stream);
@@ -151,6 +157,25 @@ int samble_linear(const float* X, long long ldx, int x_channel_major, const floa
                   const float* residual, long long ldr, int residual_channel_major, int residual_first,
                   float* out, long long ldo, int out_channel_major, int M, int K, int Nout, int points_per_cloud,
                   samble_stream_t stream);
+
+/* Two such layers back to back in ONE kernel, the hidden activation never written to memory (csrc/mlp2.cu):
+ *   h   = LeakyReLU?( (X W1^T) * scale1[c] + shift1[b?][c] )                       M x Hd, lives in tensor memory only
+ *   out = [ (h W2^T (+res if residual_first)) * scale2 + shift2[b?] ] -> LeakyReLU? -> (+res)
+ * Neighbor2PointAttention's feed-forward with its residual + bn2 (models/attention.py:187-192: K1 = C = 128, Hd = 512,
+ * N2 = 128) and the segmentation head's conv2 -> conv3 (models/seg_model.py:205-214: Hd = 1024, N2 = 256).
+ * X: M x K1 row-major, K1 <= 128; W1: Hd x K1, W2: N2 x Hd (the stored weights, with their samble_split_tf32 companions);
+ * Hd % 128 == 0; N2 = 128 or 256; scale / shift as in samble_linear (16-byte aligned; a *_cloud_stride != 0 selects a per-cloud
+ * shift row and needs points_per_cloud % 128 == 0); residual / out row-major.  For N2 = 128 the result equals the two
+ * samble_linear calls it replaces bit for bit (same products, same accumulation chains). */
+int samble_mlp2(const float* X, long long ldx, int M, int K1, const float* W1, const float* W1_lo, long long ldw1, int Hd,
+                const float* scale1, const float* shift1, long long shift1_cloud_stride, int lrelu1, const float* W2,
+                const float* W2_lo, long long ldw2, int N2, const float* scale2, const float* shift2,
+                long long shift2_cloud_stride, int lrelu2, const float* residual, long long ldr, int residual_first,
+                float* out, long long ldo, int points_per_cloud, samble_stream_t stream);
+void samble_set_mlp2_debug(int bits);   /* measurement switches, tools/probe_mlp2.py */
+/* while non-NULL every samble_mlp2 CTA writes [total, wait weights, wait conversion, wait output drain, wait X] cycles of its
+ * MMA-issuing thread to wait_cycles[5 * cta] (device memory, 5 * 148 entries) */
+void samble_set_mlp2_probe(long long* wait_cycles);
 
 /* The same layer followed by max and/or mean over the points of each cloud -- conv -> max/avg pool of
  * models/seg_model.py:199-203, cls_model.py:104/133 (res-link max), embedding.py:88-89 (STN) -- without ever storing

@@ -29,6 +29,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_profile_enable": (None, (_i,)),
     "samble_profile_report": (_i, (C.c_char_p, _sz)),
     "samble_selftest_tc_gemm": (_i, (_p, _p, _i, _p, _p, _p, _p)),
+    "samble_selftest_tc_gemm_ts": (_i, (_p, _p, _i, _p, _i, _i, _p, _p)),
     "samble_selftest_mma_rate": (_i, (_i, _i, _i, _p, _p)),
     "samble_selftest_mma_rate_ex": (_i, (_i, _i, _i, _i, _i, _i, _p, _p)),
     "samble_set_knn_mode": (None, (_i,)),
@@ -50,6 +51,9 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_linear_pool_workspace_bytes": (_sz, (_i, _i)),
     "samble_linear_pool": (_i, (_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p)),
     "samble_linear": (_i, (_p, _ll, _i, _p, _p, _ll, _p, _p, _ll, _i, _p, _ll, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p)),
+    "samble_mlp2": (_i, (_p, _ll, _i, _i, _p, _p, _ll, _i, _p, _p, _ll, _i, _p, _p, _ll, _i, _p, _p, _ll, _i, _p, _ll, _i, _p, _ll, _i, _p)),
+    "samble_set_mlp2_debug": (None, (_i,)),
+    "samble_set_mlp2_probe": (None, (_p,)),
     "samble_set_edge_mode": (None, (_i,)),
     "samble_set_edge_debug": (None, (_i,)),
     "samble_edge_mlp_max": (_i, (_p, _ll, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p)),

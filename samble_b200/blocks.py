@@ -224,8 +224,13 @@ class Neighbor2PointAttention(nn.Module):
         a1, b1 = folded(self.bn1)
         a2, b2 = folded(self.bn2)
         x1 = ops.n2p_attend(qkv, join_idx(), self.num_heads, residual=x_pm, scale=a1, shift=b1)     # bn1(x + attention)
-        h = ops.linear(x1, self.ff[0].weight, lrelu=True)                       # (B,N,4C)
-        y = ops.linear(h, self.ff[2].weight, scale=a2, shift=b2, residual=x1, residual_first=True)      # (B,N,C)
+        w1, w2 = self.ff[0].weight, self.ff[2].weight
+        if ops.FUSED_MLP2 and ops.mlp2_eligible(w1.shape[1], w1.shape[0], w2.shape[0]):
+            # feed-forward + residual + bn2 in one kernel, the (B,N,4C) hidden activation stays in tensor memory (csrc/mlp2.cu)
+            y = ops.mlp2(x1, w1, w2, lrelu1=True, scale2=a2, shift2=b2, residual=x1, residual_first=True)
+        else:
+            h = ops.linear(x1, w1, lrelu=True)                                  # (B,N,4C)
+            y = ops.linear(h, w2, scale=a2, shift=b2, residual=x1, residual_first=True)      # (B,N,C)
         return y.transpose(1, 2)          # the reference's (B,C,N) shape as a view of point-major storage (ops.rows_of)
 
 

@@ -49,7 +49,7 @@ struct LinArgs {
 // summed over the tile's accumulation chunks, stored row-major or channel-major.
 template <int NT>
 __device__ __forceinline__ void linear_epilogue_tile(const LinArgs& a, uint32_t tmem, int set, int nacc, int m0, int n0, int warp,
-                                                     int lane) {
+                                                     int lane, int c_begin = 0, int c_end = NT) {
   const int m = m0 + warp * 32 + lane;
   const uint32_t lane_base = ((uint32_t)(warp * 32) << 16) + set * nacc * NT;
   const bool live = m < a.M;
@@ -60,7 +60,7 @@ __device__ __forceinline__ void linear_epilogue_tile(const LinArgs& a, uint32_t 
   }
   const float* shift = a.shift ? a.shift + ob * a.shift_ldb : nullptr;
 #pragma unroll 1
-  for (int c0 = 0; c0 < NT; c0 += 32) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {   // (a column range: csrc/mlp2.cu shares a tile between two warps per lane quadrant)
     float v[32];
     tc::tmem_ld32(tmem + lane_base + c0, v);      // warp-collective: every lane takes part, stores are predicated
     for (int ac = 1; ac < nacc; ++ac) {           // add the accumulation chunks in fp32

@@ -252,6 +252,30 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
   for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+
+// registers -> TMEM: this thread's lane, 32 consecutive 32-bit columns (the inverse of tmem_ld32); the wait makes the
+// data visible to later tcgen05 operations once followed by tc_fence_before + a barrier.
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr), "r"(r[0]),"r"(r[1]),"r"(r[2]),"r"(r[3]),"r"(r[4]),"r"(r[5]),"r"(r[6]),"r"(r[7]),"r"(r[8]),"r"(r[9]),"r"(r[10]),"r"(r[11]),"r"(r[12]),"r"(r[13]),"r"(r[14]),"r"(r[15]),"r"(r[16]),"r"(r[17]),"r"(r[18]),"r"(r[19]),"r"(r[20]),"r"(r[21]),"r"(r[22]),"r"(r[23]),"r"(r[24]),"r"(r[25]),"r"(r[26]),"r"(r[27]),"r"(r[28]),"r"(r[29]),"r"(r[30]),"r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand is read from tensor memory (lane = row, one 32-bit column per tf32
+// K element, 8 columns per instruction), so an activation produced by a previous MMA can feed the next one without a
+// round trip through shared memory (csrc/mlp2.cu).
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .b64 db;\n setp.ne.b32 p, %4, 0;\n mov.b64 db, {%2, %5};\n"
+      " tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %3, p;\n}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescSw128Hi)
+      : "memory");
+}
+
 }  // namespace tc
 
 // host: rank-3 fp32 tensor map over a (batch, rows, inner) array with row pitch `ld` floats (16-byte multiple) and

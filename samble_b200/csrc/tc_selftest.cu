@@ -215,3 +215,88 @@ extern "C" int samble_selftest_mma_rate_ex(int kind, int n_tile, int n_acc, int 
   SAMBLE_LAUNCHED("tc_mma_rate_ex_kernel");
   return SAMBLE_OK;
 }
+
+// ---- A operand from tensor memory (the hidden activations of csrc/mlp2.cu): every thread parks its row of A in TMEM
+// columns [128, 128+K) with tcgen05.st; D = A * B^T then reads A from there.  With iters > 0 the MMA sequence is repeated
+// (accumulating) and timed: the issue rate of the TMEM-A form. ----
+namespace samble {
+__global__ void __launch_bounds__(128) tc_gemm_ts_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, int K,
+                                                                  float* __restrict__ D, int iters, long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = tc::smem_align1024(smem_raw);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = K / 32;
+  uint8_t* sB = base;
+  for (int kb = 0; kb < nkb; ++kb)
+    for (int p = tid; p < 1024; p += 128) {
+      const int row = p >> 3, ch = p & 7;
+      *reinterpret_cast<float4*>(sB + (size_t)kb * 16384 + tc::sw128_offset(row, ch)) =
+          *reinterpret_cast<const float4*>(B + (size_t)row * K + kb * 32 + ch * 4);
+    }
+  tc::fence_proxy_async();
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < K; c0 += 32) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = A[(size_t)row * K + c0 + i];
+    tc::tmem_st32(tmem + lane_base + 128 + c0, v);
+  }
+  tc::tmem_st_wait();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = tc::instr_desc(2, 128, 128);
+    const long long t0 = clock64();
+    for (int it = 0; it < (iters > 0 ? iters : 1); ++it)
+      for (int kb = 0; kb < nkb; ++kb) {
+        const uint32_t bl = tc::smem_desc_sw128_lo(tc::smem_u32(sB + (size_t)kb * 16384));
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) tc::mma_tf32_ts(tmem, tmem + 128 + kb * 32 + k8 * 8, bl + 2 * k8, idesc, (it | kb | k8) != 0);
+      }
+    tc::mma_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    if (cycles_out) cycles_out[blockIdx.x] = clock64() - t0;
+  }
+  __syncthreads();
+  tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  if (blockIdx.x == 0)
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      float v[32];
+      tc::tmem_ld32(tmem + lane_base + c0, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) D[(size_t)row * 128 + c0 + i] = v[i];
+    }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace samble
+
+extern "C" int samble_selftest_tc_gemm_ts(const float* A, const float* B, int K, float* D, int iters, int ctas, long long* cycles_out,
+                                          samble_stream_t stream) {
+  SAMBLE_REQUIRE(A && B && D, "samble_selftest_tc_gemm_ts: null pointer");
+  SAMBLE_REQUIRE(K > 0 && K % 32 == 0 && K <= 256, "samble_selftest_tc_gemm_ts: K=%d must be a multiple of 32, <= 256", K);
+  SAMBLE_REQUIRE(ctas >= 1 && iters >= 0, "samble_selftest_tc_gemm_ts: bad iters / ctas");
+  size_t smem = (size_t)(K / 32) * 16384 + 1024;
+  if (cudaFuncSetAttribute(tc_gemm_ts_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("tc_gemm_ts_selftest smem attribute");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAMBLE_PRE(st);
+  tc_gemm_ts_selftest_kernel<<<ctas, 128, smem, st>>>(A, B, K, D, iters, cycles_out);
+  SAMBLE_LAUNCHED("tc_gemm_ts_selftest_kernel");
+  return SAMBLE_OK;
+}

@@ -180,8 +180,14 @@ class ShapeNetModel(nn.Module):
             ng = g.shape[1]
             a2, b2 = blocks.folded(self.conv2[1])
             gv = g @ w2[:, :ng, 0].t()                                        # (B,1024)
-            y = ops.linear(f_rows, w2[:, ng:, 0], scale=a2, shift=gv * a2 + b2, lrelu=True)      # (B,N,1024)
-            y = blocks.cbl(self.conv3, y, x_layout="rows", out_layout="rows")
+            w3 = self.conv3[0].weight
+            if ops.FUSED_MLP2 and N % 128 == 0 and ops.mlp2_eligible(f_rows.shape[-1], w2.shape[0], w3.shape[0]):
+                # conv2 -> conv3 in one kernel: the (B,N,1024) activation stays in tensor memory (csrc/mlp2.cu)
+                a3, b3 = blocks.folded(self.conv3[1])
+                y = ops.mlp2(f_rows, w2[:, ng:, 0], w3, scale1=a2, shift1=gv * a2 + b2, lrelu1=True, scale2=a3, shift2=b3, lrelu2=True)
+            else:
+                y = ops.linear(f_rows, w2[:, ng:, 0], scale=a2, shift=gv * a2 + b2, lrelu=True)      # (B,N,1024)
+                y = blocks.cbl(self.conv3, y, x_layout="rows", out_layout="rows")
             y = ops.linear(y, self.conv4.weight, out_layout="bcn")
         return (y, trans) if self.stn_regularization_loss_factor > 0 else y
 

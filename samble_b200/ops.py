@@ -396,6 +396,72 @@ def cloud_matmul(x: Tensor, w: Tensor, *, row_max: Optional[Tensor] = None, row_
     return out
 
 
+# two-layer MLPs (N2P feed-forward, seg head conv2 -> conv3) as one kernel; False = the two `linear` launches (A/B measurements)
+FUSED_MLP2 = True
+
+
+def mlp2_eligible(K1: int, Hd: int, N2: int) -> bool:
+    """shapes the fused two-layer kernel (csrc/mlp2.cu) takes; anything else stays two `linear` calls."""
+    return K1 <= 128 and K1 % 4 == 0 and Hd >= 128 and Hd % 128 == 0 and N2 in (128, 256)
+
+
+def mlp2(x: Tensor, w1: Tensor, w2: Tensor, *, scale1: Optional[Tensor] = None, shift1: Optional[Tensor] = None,
+         lrelu1: bool = True, scale2: Optional[Tensor] = None, shift2: Optional[Tensor] = None, lrelu2: bool = False,
+         residual: Optional[Tensor] = None, residual_first: bool = False) -> Tensor:
+    """Two point-wise linear layers in one kernel, the hidden activation kept in tensor memory (csrc/mlp2.cu):
+        h = lrelu?((x W1^T) * scale1 + shift1);  y = ((h W2^T [+ residual if residual_first]) * scale2 + shift2) -> lrelu? [-> + residual]
+    x: (B, P, K1) rows (K1 <= 128); w1: (Hd, K1[,1]); w2: (N2, Hd[,1]) with N2 in {128, 256}; shifts (C,) or per cloud (B, C).
+    models/attention.py:187-192 (feed-forward + bn2 of Neighbor2PointAttention), models/seg_model.py:205-214 (conv2 -> conv3)."""
+    dev = L.need_cuda(x, w1, w2, scale1, shift1, scale2, shift2, residual)
+    L.no_grad_check(x, w1, w2)
+    w1s, w1lo = _split_weight(w1)
+    w2s, w2lo = _split_weight(w2)
+    Hd, K1 = w1.shape[0], w1[0].numel()
+    N2 = w2.shape[0]
+    if w2[0].numel() != Hd or not mlp2_eligible(K1, Hd, N2):
+        raise RuntimeError(f"mlp2: unsupported widths {K1} -> {Hd} -> {N2} (K1 <= 128, Hd % 128 == 0, N2 in (128, 256))")
+    x = _f32(x, "x")
+    if x.dim() != 3 or x.shape[-1] != K1:
+        raise RuntimeError(f"mlp2: x must be (B, P, {K1}) rows, got {tuple(x.shape)}")
+    B, P, _ = x.shape
+    x2 = x.reshape(B * P, K1)
+    if x2.stride(1) != 1 or x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = B * P
+
+    def col(v, name, width):
+        if v is None:
+            return None, 0
+        v = _f32(v, name).contiguous()
+        if v.shape[-1] != width or v.dim() > 2 or (v.dim() == 2 and v.shape[0] != B):
+            raise RuntimeError(f"mlp2: {name} must be ({width},) or ({B}, {width}), got {tuple(v.shape)}")
+        if v.data_ptr() % 16 != 0:
+            v = v.clone()
+        return v, (width if v.dim() == 2 else 0)
+
+    scale1, _ = col(scale1, "scale1", Hd)
+    shift1, s1_ldb = col(shift1, "shift1", Hd)
+    scale2, _ = col(scale2, "scale2", N2)
+    shift2, s2_ldb = col(shift2, "shift2", N2)
+    if (s1_ldb or s2_ldb) and P % 128 != 0:
+        raise RuntimeError("mlp2: per-cloud shifts need clouds of a multiple of 128 points")
+    ldr = 0
+    if residual is not None:
+        residual = _f32(residual, "residual")
+        if residual.numel() != M * N2 or residual.shape[-1] != N2:
+            raise RuntimeError(f"mlp2: residual shape {tuple(residual.shape)} does not match a {M} x {N2} result")
+        if residual.stride(-1) != 1:
+            residual = residual.contiguous()
+        residual = residual.reshape(-1, N2)
+        ldr = residual.stride(0)
+    out = torch.empty(B, P, N2, dtype=torch.float32, device=dev)
+    L.check(L.lib().samble_mlp2(L.ptr(x2), x2.stride(0), M, K1, L.ptr(w1s), L.ptr(w1lo), w1s.stride(0), Hd, L.ptr(scale1), L.ptr(shift1),
+                                s1_ldb, 1 if lrelu1 else 0, L.ptr(w2s), L.ptr(w2lo), w2s.stride(0), N2, L.ptr(scale2), L.ptr(shift2),
+                                s2_ldb, 1 if lrelu2 else 0, L.ptr(residual), ldr, 1 if residual_first else 0, L.ptr(out), N2, P,
+                                L.stream()), "samble_mlp2")
+    return out
+
+
 def linear_pool(x: Tensor, weight: Tensor, *, scale: Optional[Tensor] = None, shift: Optional[Tensor] = None,
                 lrelu: bool = False, want_max: bool = True, want_mean: bool = True):
     """max / mean over the points of each cloud of  lrelu(x W^T * scale + shift)  without storing the activation

@@ -27,6 +27,20 @@ def test_tc_gemm_selftest(K):
     assert err_exact < 0.05 * (K ** 0.5), "tcgen05 result is not the GEMM: descriptor/swizzle/TMEM mapping is wrong"
 
 
+@pytest.mark.parametrize("K", [32, 128, 256])
+def test_tc_gemm_selftest_a_in_tmem(K):
+    """tcgen05.mma reading A from tensor memory (parked with tcgen05.st): the operand path of csrc/mlp2.cu."""
+    g = torch.Generator().manual_seed(K)
+    A, B = torch.randn(128, K, generator=g).cuda(), torch.randn(128, K, generator=g).cuda()
+    D = torch.zeros(128, 128, device="cuda")
+    L.check(L.lib().samble_selftest_tc_gemm_ts(L.ptr(A), L.ptr(B), K, L.ptr(D), 0, 1, None, L.stream()), "selftest ts")
+    torch.cuda.synchronize()
+    ref = _tf32_trunc(A).double() @ _tf32_trunc(B).double().t()
+    err = (D.double() - ref).abs().max().item()
+    print(f"K={K}: max|D-tf32trunc| = {err:.3e}")
+    assert err < 2e-3
+
+
 def test_tc_gemm_selftest_nonswizzled_extra_k_step():
     """the compact SWIZZLE_NONE [128 x 32 B] slice that carries |b|^2 through the kNN GEMM."""
     g = torch.Generator().manual_seed(1)
