@@ -46,8 +46,9 @@ def _fp64(x, w1, w2, s1, h1, s2, h2, res, res_first, lrelu2):
 
 
 @pytest.mark.parametrize("B,P,K1,Hd", [(2, 2048, 128, 512), (3, 300, 128, 512), (1, 130, 64, 256), (16, 1024, 128, 512), (2, 128, 128, 128)])
-def test_mlp2_feed_forward_equals_two_linear_launches(B, P, K1, Hd):
-    """N2 = 128: same products in the same accumulation chains as linear_tma.cu -> the same bits."""
+def test_mlp2_feed_forward_matches_two_linear_launches(B, P, K1, Hd):
+    """N2 = 128: the same products as the two launches; the second layer accumulates in one chain instead of 8-K-block
+    chains, so the results agree to fp32 rounding (and are identical when Hd <= 256 = one chain either way)."""
     args = _case(B, P, K1, Hd, 128, seed=P + Hd)
     x, w1, w2, s1, h1, s2, h2, res, rf, l2 = args
     y = ops.mlp2(x, w1, w2, scale1=s1, shift1=h1, scale2=s2, shift2=h2, residual=res, residual_first=rf, lrelu2=l2)
@@ -60,7 +61,9 @@ def test_mlp2_feed_forward_equals_two_linear_launches(B, P, K1, Hd):
           f"identical: {torch.equal(y, ref2)}")
     assert torch.isfinite(y).all()
     assert err <= 2e-5 * max(1.0, ref64.abs().max().item())
-    assert torch.equal(y, ref2)
+    assert err <= 2.0 * err2 + 1e-6
+    if Hd <= 256:
+        assert torch.equal(y, ref2)
 
 
 @pytest.mark.parametrize("B,P,Hd,per_cloud", [(2, 2048, 1024, True), (3, 384, 1024, True), (2, 200, 512, False)])
@@ -83,10 +86,15 @@ def test_mlp2_variants_no_scale_residual_last():
     args = _case(2, 512, 128, 512, 128, seed=5, scale1=False, res_first=False, lrelu2=True)
     x, w1, w2, s1, h1, s2, h2, res, rf, l2 = args
     y = ops.mlp2(x, w1, w2, scale1=None, shift1=h1, scale2=s2, shift2=h2, residual=res, residual_first=False, lrelu2=True)
-    assert torch.equal(y, _two_launches(*args))
+    ref = _fp64(*args)
+    assert (y.double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    w1s, w2s = w1[:256].contiguous(), w2[:, :256].contiguous()
+    y = ops.mlp2(x, w1s, w2s, lrelu1=True)                     # no scale / shift at all (the feed-forward as the model calls it)
+    h = ops.linear(x, w1s, lrelu=True)
+    assert torch.equal(y, ops.linear(h, w2s))
     y = ops.mlp2(x, w1, w2, lrelu1=True)
-    h = ops.linear(x, w1, lrelu=True)
-    assert torch.equal(y, ops.linear(h, w2))
+    ref = torch.nn.functional.leaky_relu(x.double() @ w1.double().t(), 0.2) @ w2.double().t()
+    assert (y.double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
 
 
 def test_mlp2_rejects_unsupported_widths():

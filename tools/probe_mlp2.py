@@ -25,7 +25,8 @@ def timed(fn, n=20):
 for (B, P, Hd, N2) in [(16, 2048, 512, 128), (16, 1024, 512, 128), (16, 512, 512, 128), (16, 2048, 1024, 256)]:
     x = torch.randn(B, P, 128, device="cuda")
     w1, w2 = torch.randn(Hd, 128, device="cuda") / 11, torch.randn(N2, Hd, device="cuda") / Hd ** 0.5
-    s1, h1 = torch.rand(Hd, device="cuda") + 0.5, torch.randn(B, Hd, device="cuda") * 0.1
+    # the feed-forward has no scale / shift between its layers (attention.py:187-192); the head has both (folded BatchNorm, per-cloud shift)
+    s1, h1 = (torch.rand(Hd, device="cuda") + 0.5, torch.randn(B, Hd, device="cuda") * 0.1) if N2 == 256 else (None, None)
     s2, h2 = torch.rand(N2, device="cuda") + 0.5, torch.randn(N2, device="cuda") * 0.1
     res = torch.randn(B, P, N2, device="cuda") if N2 == 128 else None
     two = lambda: ops.linear(ops.linear(x, w1, scale=s1, shift=h1, lrelu=True), w2, scale=s2, shift=h2, residual=res, residual_first=True, lrelu=N2 == 256)
@@ -33,7 +34,7 @@ for (B, P, Hd, N2) in [(16, 2048, 512, 128), (16, 1024, 512, 128), (16, 512, 512
     t2, t1 = timed(two), timed(one)
     parts = []
     wc = torch.zeros(148 * 5, dtype=torch.int64, device="cuda")
-    for bits, name in ((0, "full"), (1, "no conversion"), (8, "no scale/shift loads"), (2, "no output epilogue"), (4, "no MMA"), (7, "weights stream only")):
+    for bits, name in ((0, "full"), (1, "no conversion"), (8, "no scale/shift"), (2, "no output epilogue"), (4, "no MMA"), (7, "weights stream only")):
         lib.samble_set_mlp2_debug(bits)
         t = timed(one)
         lib.samble_set_mlp2_probe(L.ptr(wc))
