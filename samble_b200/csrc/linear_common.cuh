@@ -41,6 +41,7 @@ struct LinArgs {
   // acc / logit_div and the sum of exp(. - max):  stat_out[m * ntiles + n_tile] = (max, sum)
   float2* stat_out;
   int dbg;                            // measurement switches (samble_set_linear_debug): 8 = no residual loads, 16 = no stores
+  int pool_rows;                      // rows per pooling group: 32 (row-per-thread epilogue) or 128 (swapped orientation); 0 = 32
 };
 
 
@@ -237,6 +238,56 @@ __device__ __forceinline__ void linear_epilogue_tile_tma(const LinArgs& a, const
       tc::bulk_commit();
     }
     ++parity;
+  }
+}
+
+// ---- swapped orientation (linear_tma.cu, EPI 5): the MMAs are issued with the WEIGHT tile as the A operand and the X tile as B,
+// so the accumulator holds the transposed tile: TMEM lane = output channel n0 + lane, column = point m0 + col; the products and
+// their accumulation order per output element are unchanged (bit-identical pre-activations).
+// (A direct-store epilogue in this orientation -- one whole 128-byte line per store instruction instead of 32 sectors of 32
+// different lines -- was built and measured SLOWER than the row-per-thread stores: 54.8 vs 43.6 us at 32768 x 128 -> 384,
+// 114 vs 88 us at -> 1024.  Without any store the kernel takes 27.9 / 49.6 us, so the 50 / 134 MB of output drain at
+// 3.1 - 3.4 TB/s either way: the epilogue of these layers is bound by the HBM write stream, not by the LSU.  Removed.)
+// swapped pooling: a thread owns one channel and 128 points of ONE cloud (npc % 128 == 0): the reduction over the points runs
+// down the thread's own columns -- no shuffles at all (the row-per-thread version needs a 31-shuffle butterfly per 32 columns
+// for each of max and sum).  One partial per (128-row tile, channel): pool_max / pool_sum [M/128][Nout].
+template <int NT>
+__device__ __forceinline__ void linear_epilogue_tile_pool_swapped(const LinArgs& a, uint32_t tmem, int set, int nacc, int m0, int n0,
+                                                                  int warp, int lane) {
+  const int c = n0 + warp * 32 + lane;
+  const bool live = c < a.Nout;
+  const int cc = live ? c : a.Nout - 1;
+  const uint32_t lane_base = ((uint32_t)(warp * 32) << 16) + set * nacc * NT;
+  const float sc = a.scale ? __ldg(a.scale + cc) : 1.f;
+  const float sh = a.shift ? __ldg(a.shift + (long long)(m0 / a.npc) * a.shift_ldb + cc) : 0.f;
+  const int cols = min(128, a.M - m0);
+  float mx = -INFINITY, sum = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    float v[32];
+    tc::tmem_ld32(tmem + lane_base + c0, v);
+    for (int ac = 1; ac < nacc; ++ac) {
+      float w[32];
+      tc::tmem_ld32(tmem + lane_base + ac * NT + c0, w);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += w[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float y = v[i];
+      if (a.scale) y *= sc;
+      if (a.shift) y += sh;
+      if (a.lrelu) y = y > 0.f ? y : 0.2f * y;
+      if (c0 + i < cols) {
+        mx = fmaxf(mx, y);
+        sum += y;
+      }
+    }
+  }
+  if (live) {
+    const long long o = (long long)(m0 >> 7) * a.Nout + c;
+    a.pool_max[o] = mx;
+    if (a.pool_sum) a.pool_sum[o] = sum;
   }
 }
 

@@ -232,6 +232,7 @@ static int launch_linear(const LinArgs& a, cudaStream_t st) {
 }
 
 int launch_linear_tma_auto(const LinArgs& a, int nacc, cudaStream_t st);   // linear_tma.cu
+extern int g_lt_debug;
 template <int NT>
 int launch_linear_tma(const LinArgs& a, cudaStream_t st);
 
@@ -323,10 +324,14 @@ extern "C" int samble_linear_pool(const float* X, long long ldx, const float* W,
   LinArgs a{X, ldx, W, ldw, W_lo, scale, shift, nullptr, 0, nullptr, 0, M, K, Nout, points_per_cloud,
             lrelu, 0, 0, 0, 0, shift_cloud_stride, pmax, out_mean ? psum : nullptr, 0, nullptr, nullptr, 1.f, 0, nullptr};
   cudaStream_t st = (cudaStream_t)stream;
+  // clouds of whole 128-row tiles and 128-channel tiles: swapped orientation, the reduction over the points runs down each
+  // thread's own accumulator columns (linear_common.cuh); one partial per (tile, channel) instead of per (32 rows, channel)
+  const bool wide = Nout > 64 && nacc * 128 <= 512;
+  a.pool_rows = (points_per_cloud % 128 == 0 && wide && !(g_lt_debug & (64 | 128))) ? 128 : 32;
   if (int e = launch_linear_tma_auto(a, nacc, st)) return e;
   SAMBLE_PRE(st);
   linear_pool_finalize_kernel<<<dim3(ceil_div(Nout, 128), M / points_per_cloud), 128, 0, st>>>(
-      pmax, out_mean ? psum : nullptr, points_per_cloud / 32, Nout, points_per_cloud, out_max, out_mean);
+      pmax, out_mean ? psum : nullptr, points_per_cloud / a.pool_rows, Nout, points_per_cloud, out_max, out_mean);
   SAMBLE_LAUNCHED("linear_pool_finalize_kernel");
   return SAMBLE_OK;
 }

@@ -68,7 +68,8 @@ __device__ __forceinline__ void lt_range(int total, int& t0, int& t1) {
 }
 
 // EPI selects the one epilogue compiled into an instantiation (0 direct, 1 smem-staged row-major, 2 pooling, 3 row
-// statistics): with all of them in one function ptxas sized the kernel for their union and spilled.
+// statistics, 5 pooling in the SWAPPED orientation: weight tile as the A operand, accumulator = transposed tile, see
+// linear_common.cuh): with all of them in one function ptxas sized the kernel for their union and spilled.
 template <int NT, int EPI>
 __global__ void __launch_bounds__(kLtThreads, 1)
     linear_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -213,9 +214,15 @@ __global__ void __launch_bounds__(kLtThreads, 1)
           if (!(dbg & 4))
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) {
-            tc::mma_tf32(acc, xh + 2 * k8, wh + 2 * k8, idesc, ((kb % chain) | k8) != 0);
-            tc::mma_tf32(acc, xl + 2 * k8, wh + 2 * k8, idesc, 1);
-            tc::mma_tf32(acc, xh + 2 * k8, wl + 2 * k8, idesc, 1);
+            if (EPI == 5) {                                      // swapped: D^T = W X^T (same products, same order)
+              tc::mma_tf32(acc, wh + 2 * k8, xh + 2 * k8, idesc, ((kb % chain) | k8) != 0);
+              tc::mma_tf32(acc, wh + 2 * k8, xl + 2 * k8, idesc, 1);
+              tc::mma_tf32(acc, wl + 2 * k8, xh + 2 * k8, idesc, 1);
+            } else {
+              tc::mma_tf32(acc, xh + 2 * k8, wh + 2 * k8, idesc, ((kb % chain) | k8) != 0);
+              tc::mma_tf32(acc, xl + 2 * k8, wh + 2 * k8, idesc, 1);
+              tc::mma_tf32(acc, xh + 2 * k8, wl + 2 * k8, idesc, 1);
+            }
           }
           tc::mma_commit(&empty[s]);
           if (++s == stages) { s = 0; ph ^= 1; }
@@ -247,6 +254,8 @@ __global__ void __launch_bounds__(kLtThreads, 1)
         linear_epilogue_tile_pool<NT>(a, tmem, set, nacc, m0, n0, warp, lane);
       else if (EPI == 0)
         linear_epilogue_tile<NT>(a, tmem, set, nacc, m0, n0, warp, lane);
+      else if (EPI == 5)
+        linear_epilogue_tile_pool_swapped<NT>(a, tmem, set, nacc, m0, n0, warp, lane);
       else
         linear_epilogue_tile_tma<NT>(a, &map_out, tmem, set, nacc, m0, n0, warp, lane, stage_out, parity);
       tc::tc_fence_before();
@@ -275,7 +284,14 @@ int launch_linear_tma(const LinArgs& a_in, cudaStream_t st) {
   if (int e = make_tile_map(&mwl, a.Wlo, k4, a.ldw, a.Nout, wb, NT)) return e;
   const bool tma_out = p.staged && !a.out_cm && !(a.residual && a.res_cm) && a.out && a.ldo % 4 == 0 &&
                        reinterpret_cast<uintptr_t>(a.out) % 16 == 0 && !a.stat_out && !a.pool_max;
-  const int epi = a.stat_out ? 3 : (a.pool_max ? 2 : (tma_out ? 1 : 0));
+  // pooling in the swapped orientation (linear_common.cuh): 128-channel tiles, whole 128-row tiles inside one cloud.
+  // samble_set_linear_debug(128) turns it off (the caller then asks for 32-row groups).
+  const bool swap_pool = NT == 128 && !(g_lt_debug & 128) && a.pool_max && a.pool_rows == 128;
+  if (a.pool_max && a.pool_rows == 128 && !swap_pool) {
+    set_error("linear_tma: 128-row pooling groups need the swapped 128-channel kernel");
+    return SAMBLE_E_INVALID;
+  }
+  const int epi = a.stat_out ? 3 : (a.pool_max ? (swap_pool ? 5 : 2) : (tma_out ? 1 : 0));
   alignas(64) CUtensorMap mo;
   if (tma_out) {
     if (int e = make_tile_map(&mo, a.out, a.Nout, a.ldo, a.M, 1, 32)) return e;
@@ -284,6 +300,7 @@ int launch_linear_tma(const LinArgs& a_in, cudaStream_t st) {
   }
   auto kern = epi == 3 ? linear_tma_kernel<NT, 3>
                        : (epi == 2 ? linear_tma_kernel<NT, 2> : (epi == 1 ? linear_tma_kernel<NT, 1> : linear_tma_kernel<NT, 0>));
+  if (NT == 128 && epi == 5) kern = linear_tma_kernel<128, 5>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) != cudaSuccess)
     return check_launch("linear_tma smem attribute");
   const long long total = (long long)ceil_div(a.M, 128) * ceil_div(a.Nout, NT);

@@ -106,6 +106,35 @@ def test_linear_3xtf32_matches_fp64(case):
     assert err < 2e-5 * max(1.0, ref.abs().max().item())
 
 
+SWAP_CASES = [(2, 2048, 128, 1024, False, None, True), (3, 384, 128, 512, True, "cloud", True), (2, 512, 512, 128, True, "shared", False),
+              (16, 128, 64, 200, True, "shared", True)]
+
+
+@pytest.mark.parametrize("case", SWAP_CASES, ids=[f"B{c[0]}_P{c[1]}_K{c[2]}_N{c[3]}" for c in SWAP_CASES])
+def test_linear_pool_swapped_orientation_matches_row_per_thread(case):
+    """samble_linear_pool on clouds of whole 128-row tiles runs linear_tma in the swapped orientation (weight tile as the A
+    operand, the reduction over the points down each thread's own accumulator columns): same products in the same order as the
+    row-per-thread butterfly kernel (samble_set_linear_debug(128)), so the maxima are identical; the means differ by the
+    summation order only."""
+    from samble_b200 import ops
+
+    B, P, K, Nout, use_scale, shift_kind, lrelu = case
+    g = torch.Generator().manual_seed(P + K + Nout)
+    x = (torch.randn(B, P, K, generator=g) * 2).cuda()
+    w = (torch.randn(Nout, K, generator=g) / K ** 0.5).cuda()
+    scale = (torch.rand(Nout, generator=g) + 0.5).cuda() if use_scale else None
+    shift = None if shift_kind is None else (torch.randn(Nout, generator=g) if shift_kind == "shared" else torch.randn(B, Nout, generator=g)).cuda()
+    mx, mean = ops.linear_pool(x, w, scale=scale, shift=shift, lrelu=lrelu)
+    L.lib().samble_set_linear_debug(128)
+    try:
+        mx0, mean0 = ops.linear_pool(x, w, scale=scale, shift=shift, lrelu=lrelu)
+    finally:
+        L.lib().samble_set_linear_debug(0)
+    torch.cuda.synchronize()
+    assert torch.equal(mx, mx0)
+    assert (mean - mean0).abs().max().item() <= 1e-5 * max(1.0, mean0.abs().max().item())
+
+
 POOL_CASES = [(2, 256, 128, 1024, True, "shared", True), (3, 96, 64, 200, False, None, False), (1, 2048, 128, 1024, True, "cloud", True),
               (4, 32, 36, 50, True, "shared", True), (2, 512, 512, 128, False, "shared", True)]
 
