@@ -51,10 +51,13 @@ __global__ void __launch_bounds__(256) knn_stats_kernel(const float* __restrict_
 // Point-major input (unit channel stride): lane = channel, so a warp reads 128 contiguous bytes of one point; the 16
 // warps of the CTA take points w, w+16, ... and their fp64 partial sums are combined in warp order (deterministic).
 __global__ void __launch_bounds__(512) knn_stats_pm_kernel(const float* __restrict__ a, long long sb, long long sn, int N,
-                                                           int C, double* __restrict__ part) {
+                                                           int C, double* __restrict__ part, unsigned* __restrict__ zero_me) {
   __shared__ double ps[16][32], pq[16][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 32 + lane, b = blockIdx.y, z = blockIdx.z, Z = gridDim.z;
+  // (the per-cloud max-norm word the next kernel of the neighbour search accumulates into with atomicMax: cleared here
+  // instead of by a memset node of its own)
+  if (zero_me && threadIdx.x == 0 && blockIdx.x == 0 && z == 0) zero_me[b] = 0u;
   const bool live = c < C;
   const float* p = a + b * sb + (live ? c : 0);
   // this CTA's slice of the points: [n_lo, n_hi)
@@ -228,14 +231,41 @@ __global__ void __launch_bounds__(256) knn_prep_feat_pm_kernel(const float* __re
                                                                const float* __restrict__ stdv, float* __restrict__ out,
                                                                float* __restrict__ norms, unsigned* __restrict__ maxnorm,
                                                                float* __restrict__ ext, __nv_bfloat16* __restrict__ out_hi,
-                                                               __nv_bfloat16* __restrict__ out_lo) {
+                                                               __nv_bfloat16* __restrict__ out_lo,
+                                                               const double* __restrict__ part, int Z, int Nstat,
+                                                               float* __restrict__ mean_out, float* __restrict__ stdv_out) {
   __shared__ float tile[32][33];                        // [channel of the block][point]
+  __shared__ __align__(16) float s_mean[512];
+  __shared__ float s_std[512];
+  __shared__ float s_sigma;
   const int b = blockIdx.y, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (n0 >= N) {
     if (ty == 0) knn_store_ext(ext, b, N, n0 + tx, -1e30f);
     return;
   }
-  const float sigma = cloud_sigma(stdv + b * C, C);
+  float sigma;
+  if (part) {
+    // the statistics arrive as per-slice fp64 partial sums (knn_stats_pm_kernel): every CTA combines them itself, in slice
+    // order with the arithmetic of knn_stats_pm_combine_kernel (same bits), instead of waiting for one more launch
+    for (int c = threadIdx.x; c < C; c += 256) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int z = 0; z < Z; ++z) {
+        const double* o = part + (((long long)b * Z + z) * C + c) * 2;
+        s1 += o[0], s2 += o[1];
+      }
+      const double m = s1 / Nstat;
+      const double var = (s2 - s1 * m) / (double)(Nstat - 1);
+      s_mean[c] = (float)m;
+      s_std[c] = (float)sqrt(var > 0.0 ? var : 0.0);
+      if (blockIdx.x == 0 && mean_out) mean_out[b * C + c] = s_mean[c], stdv_out[b * C + c] = s_std[c];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_sigma = cloud_sigma(s_std, C);
+    __syncthreads();
+    sigma = s_sigma;
+  } else {
+    sigma = cloud_sigma(stdv + b * C, C);
+  }
   const int row = threadIdx.x >> 3, f4 = threadIdx.x & 7;
   const int n = n0 + row;
   float nn = 0.f;
@@ -244,7 +274,7 @@ __global__ void __launch_bounds__(256) knn_prep_feat_pm_kernel(const float* __re
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < N && c < C) {
       const float4 xv = __ldg(reinterpret_cast<const float4*>(x + b * sb + n * sn + c));
-      const float4 mv = __ldg(reinterpret_cast<const float4*>(mean + b * C + c));
+      const float4 mv = part ? *reinterpret_cast<const float4*>(s_mean + c) : __ldg(reinterpret_cast<const float4*>(mean + b * C + c));
       v.x = __fdiv_rn(__fsub_rn(xv.x, mv.x), sigma);
       v.y = __fdiv_rn(__fsub_rn(xv.y, mv.y), sigma);
       v.z = __fdiv_rn(__fsub_rn(xv.z, mv.z), sigma);
@@ -633,12 +663,14 @@ static int launch_knn_feat(const float* an, const float* anorm, const float* bn,
 constexpr int kStatsSlices = 4;     // point slices per (cloud, 32-channel block) in the point-major form
 size_t knn_stats_scratch_bytes(int B, int C) { return (size_t)B * kStatsSlices * C * 2 * sizeof(double); }
 
-int launch_knn_stats(const float* a, long long sb, long long sn, long long sc, int B, int N, int C, float* mean,
-                     float* stdv, cudaStream_t st, double* scratch) {
-  if (sc == 1 && C >= 8 && scratch) {     // point-major rows (the blocks' own activations)
+bool knn_stats_point_major(long long sc, int C) { return sc == 1 && C >= 8; }
+static int launch_knn_stats_ex(const float* a, long long sb, long long sn, long long sc, int B, int N, int C, float* mean,
+                               float* stdv, cudaStream_t st, double* scratch, bool defer_combine, unsigned* zero_me) {
+  if (knn_stats_point_major(sc, C) && scratch) {     // point-major rows (the blocks' own activations)
     SAMBLE_PRE(st);
-    knn_stats_pm_kernel<<<dim3(ceil_div(C, 32), B, kStatsSlices), 512, 0, st>>>(a, sb, sn, N, C, scratch);
+    knn_stats_pm_kernel<<<dim3(ceil_div(C, 32), B, kStatsSlices), 512, 0, st>>>(a, sb, sn, N, C, scratch, zero_me);
     SAMBLE_LAUNCHED("knn_stats_kernel");
+    if (defer_combine) return SAMBLE_OK;    // the consumer (knn_prep_feat_pm_kernel) combines the slices itself
     SAMBLE_PRE(st);
     knn_stats_pm_combine_kernel<<<dim3(ceil_div(C, 128), B), 128, 0, st>>>(scratch, kStatsSlices, N, C, mean, stdv);
     SAMBLE_LAUNCHED("knn_stats_combine_kernel");
@@ -648,6 +680,10 @@ int launch_knn_stats(const float* a, long long sb, long long sn, long long sc, i
   knn_stats_kernel<<<dim3(ceil_div(C, 8), B), 256, 0, st>>>(a, sb, sn, sc, N, C, mean, stdv);
   SAMBLE_LAUNCHED("knn_stats_kernel");
   return SAMBLE_OK;
+}
+int launch_knn_stats(const float* a, long long sb, long long sn, long long sc, int B, int N, int C, float* mean,
+                     float* stdv, cudaStream_t st, double* scratch) {
+  return launch_knn_stats_ex(a, sb, sn, sc, B, N, C, mean, stdv, st, scratch, false, nullptr);
 }
 int launch_knn_prep_xyz(const float* x, long long sb, long long sn, long long sc, int B, int N, int C,
                         const float* mean, const float* stdv, float4* out, cudaStream_t st) {
@@ -687,12 +723,16 @@ static KnnPlan knn_plan(int B, int Nq, int Nr, int C) {
   return p;
 }
 
+static bool prep_point_major(const float* x, long long sb, long long sn, long long sc, int C) {
+  return sc == 1 && C % 4 == 0 && sn % 4 == 0 && sb % 4 == 0 && (uintptr_t)x % 16 == 0;
+}
 static void launch_prep_feat(dim3 grid, cudaStream_t st, const float* x, long long sb, long long sn, long long sc, int N, int C,
                              int Cp, const float* mean, const float* stdv, float* out, float* norms, unsigned* maxnorm,
-                             float* ext, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
-  const bool pm = sc == 1 && C % 4 == 0 && sn % 4 == 0 && sb % 4 == 0 && (uintptr_t)x % 16 == 0;
+                             float* ext, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, const double* part = nullptr, int Nstat = 0) {
+  const bool pm = prep_point_major(x, sb, sn, sc, C);
   if (pm)
-    knn_prep_feat_pm_kernel<<<grid, 256, 0, st>>>(x, sb, sn, N, C, Cp, mean, stdv, out, norms, maxnorm, ext, out_hi, out_lo);
+    knn_prep_feat_pm_kernel<<<grid, 256, 0, st>>>(x, sb, sn, N, C, Cp, mean, stdv, out, norms, maxnorm, ext, out_hi, out_lo, part,
+                                                  kStatsSlices, Nstat, const_cast<float*>(mean), const_cast<float*>(stdv));
   else
     knn_prep_feat_kernel<<<grid, 256, 0, st>>>(x, sb, sn, sc, N, C, Cp, mean, stdv, out, norms, maxnorm, ext, out_hi, out_lo);
 }
@@ -708,7 +748,13 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   float* mean = w.take<float>((size_t)B * C);
   float* stdv = w.take<float>((size_t)B * C);
   double* stats_scratch = w.take<double>(knn_stats_scratch_bytes(B, C) / sizeof(double));
-  if (int e = launch_knn_stats(a, a_sb, a_sn, a_sc, B, Nq, C, mean, stdv, st, stats_scratch)) return e;
+  unsigned* bbmax = w.take<unsigned>((size_t)B);
+  // feature path on point-major activations: the prep kernels combine the statistics slices themselves (one launch less on the
+  // critical path of every neighbour search)
+  const bool fuse_stats = !plan.xyz && C <= 512 && knn_stats_point_major(a_sc, C) && prep_point_major(a, a_sb, a_sn, a_sc, C) &&
+                          (self || prep_point_major(b, b_sb, b_sn, b_sc, C));
+  if (int e = launch_knn_stats_ex(a, a_sb, a_sn, a_sc, B, Nq, C, mean, stdv, st, stats_scratch, fuse_stats, fuse_stats ? bbmax : nullptr)) return e;
+  const double* part = fuse_stats ? stats_scratch : nullptr;
   if (plan.xyz) {
     float4* qa = w.take<float4>((size_t)B * Nq);
     float4* qb = self ? qa : w.take<float4>((size_t)B * Nr);
@@ -738,7 +784,6 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   SAMBLE_PRE(st);
   float* thr = w.take<float>((size_t)B * Nq);
   int* row_flags = w.take<int>((size_t)B * Nq + 1);          // + one "any row flagged" word
-  unsigned* bbmax = w.take<unsigned>((size_t)B);
   uint32_t* cand = w.take<uint32_t>((size_t)B * Nq * 128);
   int* cand_cnt = w.take<int>((size_t)B * Nq);
   float* bext = w.take<float>(knn_tc_ext_floats(B, Nr));
@@ -748,7 +793,7 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   __nv_bfloat16* b_hi = self ? a_hi : w.take<__nv_bfloat16>((size_t)B * Nr * Cp);
   __nv_bfloat16* b_lo = self ? a_lo : w.take<__nv_bfloat16>((size_t)B * Nr * Cp);
   const bool use_tc = g_knn_mode != 1 && knn_tc_eligible(Nq, Nr, C, k);
-  if (use_tc) {   // per-cloud maximum candidate norm: an atomicMax target of the prep kernel
+  if (use_tc && !fuse_stats) {   // per-cloud maximum candidate norm: an atomicMax target of the prep kernel (else cleared by the stats kernel)
     if (cudaMemsetAsync(bbmax, 0, (size_t)B * sizeof(unsigned), st) != cudaSuccess) return check_launch("memset knn bbmax");
     count_launch();
   }
@@ -756,12 +801,13 @@ static int knn_impl(const float* a, long long a_sb, long long a_sn, long long a_
   // the candidate-side launch also covers the padding rows of the last 128-candidate tile (norm slice only)
   const bool a_is_cand = use_tc && self;
   launch_prep_feat(dim3(ceil_div(a_is_cand ? (int)align_up(Nq, 128) : Nq, 32), B), st, a, a_sb, a_sn, a_sc, Nq, C, Cp, mean, stdv,
-                   an, anorm, a_is_cand ? bbmax : nullptr, a_is_cand ? bext : nullptr, use_tc ? a_hi : nullptr, use_tc ? a_lo : nullptr);
+                   an, anorm, a_is_cand ? bbmax : nullptr, a_is_cand ? bext : nullptr, use_tc ? a_hi : nullptr, use_tc ? a_lo : nullptr,
+                   part, Nq);
   SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   if (!self) {
     SAMBLE_PRE(st);
     launch_prep_feat(dim3(ceil_div(use_tc ? (int)align_up(Nr, 128) : Nr, 32), B), st, b, b_sb, b_sn, b_sc, Nr, C, Cp, mean, stdv, bn,
-                     bnorm, use_tc ? bbmax : nullptr, use_tc ? bext : nullptr, use_tc ? b_hi : nullptr, use_tc ? b_lo : nullptr);
+                     bnorm, use_tc ? bbmax : nullptr, use_tc ? bext : nullptr, use_tc ? b_hi : nullptr, use_tc ? b_lo : nullptr, part, Nq);
     SAMBLE_LAUNCHED("knn_prep_feat_kernel");
   }
   if (use_tc) {
