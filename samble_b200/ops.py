@@ -101,7 +101,7 @@ def fork(fn):
         out = fn()
         return lambda: out
     main = torch.cuda.current_stream()
-    key = main.device.index
+    key = (main.device.index, main.cuda_stream)      # one side stream per calling stream (sub-batches may run side by side)
     side = _SIDE_STREAMS.get(key)
     if side is None:
         side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=main.device)
