@@ -356,13 +356,17 @@ def linear_roofline(ms, census, pk, workload="seg"):
     sec = ms * 1e-3
     tf32 = pk["bf16_tflops_sustained"] / 2
     ach = census["flops"] / sec / 1e12
-    tr = ncu_traffic("linear_tma_kernel") if workload == "seg" else None
+    tr = None
+    if workload == "seg":
+        fams = [f for f in (ncu_traffic("linear_tma_kernel"), ncu_traffic("mlp2_kernel")) if f]
+        if fams:
+            tr = {"dram_bytes_per_step": sum(f["dram_bytes_per_step"] for f in fams), "launches_per_step": sum(f["launches_per_step"] for f in fams)}
     return {"kernel": "linear_tma_kernel + mlp2_kernel (all point-wise linear layers of the step)", "bound": "tensor", "achieved": ach, "peak": tf32 / 3,
             "unit": "TFLOP/s (fp32-equivalent)", "frac": ach / (tf32 / 3), "ms_per_step": ms, "calls_per_step": census["calls"],
             "algorithmic_gb_per_step": census["bytes"] / 1e9, "hbm_gbs": census["bytes"] / sec / 1e9,
             "flop_per_byte": census["flops"] / census["bytes"],
             "traffic": (tr["dram_bytes_per_step"] / tr["launches_per_step"]) if tr else None,
-            "traffic_note": "DRAM read+write bytes per launch (ncu --set full, profiles/r2_final_full.md), average over the family's "
+            "traffic_note": "DRAM read+write bytes per launch (ncu --set full, profiles/r2k_final_full.md), average over the two families' "
                             f"{tr['launches_per_step']} launches of the seg step; algorithmic bytes per launch: "
                             f"{census['bytes'] / max(census['calls'], 1):.0f}" if tr else None,
             "note": "3 kind::tf32 MMAs per fp32-class product: peak = (bf16 sustained / 2) / 3; the layers sit above the 3xTF32 ridge "

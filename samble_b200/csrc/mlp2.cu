@@ -70,11 +70,11 @@ __global__ void __launch_bounds__(kM2Threads, 1)
   uint64_t* wfull = bars + 9;               // [3]
   uint64_t* wempty = bars + 12;             // [3]
   uint64_t* hfull = bars + 15;              // [2] acc1 buffer complete
-  uint64_t* hready = bars + 17;             // [2 buffers][2] columns [0,64) / [64,128) of [hi|lo] written (4 warps each)
-  uint64_t* g2done = bars + 21;             // second product of a chunk retired: the lo plane may be rewritten (LA)
-  uint64_t* yfull = bars + 22;              // Y of the tile complete
-  uint64_t* yempty = bars + 23;             // Y drained (8 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* hready = bars + 17;             // [2 buffers][4] 32-column block of [hi|lo] written (4 warps each): = one K-block of G2
+  uint64_t* g2done = bars + 25;             // second product of a chunk retired: the lo plane may be rewritten (LA)
+  uint64_t* yfull = bars + 26;              // Y of the tile complete
+  uint64_t* yempty = bars + 27;             // Y drained (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
   float* s_scale2 = reinterpret_cast<float*>(bars + 32);       // [N2] second layer's per-column scale (1 when absent)
   float* s_shift2 = s_scale2 + N2;                             // [N2] ... and shift (0 when absent or per cloud)
 
@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(kM2Threads, 1)
     for (int i = 0; i < 4; ++i) {
       tc::mbar_init(&xland[i], 1);
       tc::mbar_init(&xready[i], 2);
-      tc::mbar_init(&hready[i], 4);
     }
+    for (int i = 0; i < 8; ++i) tc::mbar_init(&hready[i], 4);
     tc::mbar_init(xfree, 1);
     for (int i = 0; i < kM2Stages; ++i) {
       tc::mbar_init(&wfull[i], 1);
@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(kM2Threads, 1)
         const bool first = (j % cpc) == 0;
         for (int h = 0; h < NH; ++h)
           for (int kb = 0; kb < 4; ++kb) {
-            if (h == 0 && (kb & 1) == 0) {
-              M2_WAIT(1, tc::mbar_wait(&hready[buf * 2 + (kb >> 1)], (c2 / NB) & 1));
+            if (h == 0) {                       // K-block kb of this chunk = 32-column block kb of the converted accumulator
+              M2_WAIT(1, tc::mbar_wait(&hready[buf * 4 + kb], (c2 / NB) & 1));
               tc::tc_fence_after();
             }
             M2_WAIT(0, tc::mbar_wait(&wfull[s], ph));
@@ -323,12 +323,18 @@ __global__ void __launch_bounds__(kM2Threads, 1)
             tc::tc_fence_after();
           }
           tc::tmem_st32(lo_t + c0, v);
+          // each 32-column block is published on its own: the second product starts on K-block 0 while the rest converts
+          tc::tmem_st_wait();
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&hready[buf * 4 + half * 2 + r]);
         }
-        else if (LA && cc > 0) tc::mbar_wait(g2done, (cc - 1) & 1);
-        tc::tmem_st_wait();
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&hready[buf * 2 + half]);
+        else {
+          if (LA && cc > 0) tc::mbar_wait(g2done, (cc - 1) & 1);
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&hready[buf * 4 + half * 2]), tc::mbar_arrive(&hready[buf * 4 + half * 2 + 1]);
+        }
       }
       // ---- output epilogue: this warp's 32 rows x N2/2 columns.  Scale / shift come from shared memory; the residual
       //      block of the NEXT 32 columns is requested before the current one is finished (the first before the wait).
