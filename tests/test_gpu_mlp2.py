@@ -45,7 +45,9 @@ def _fp64(x, w1, w2, s1, h1, s2, h2, res, res_first, lrelu2):
     return y
 
 
-@pytest.mark.parametrize("B,P,K1,Hd", [(2, 2048, 128, 512), (3, 300, 128, 512), (1, 130, 64, 256), (16, 1024, 128, 512), (2, 128, 128, 128)])
+@pytest.mark.parametrize("B,P,K1,Hd", [(2, 2048, 128, 512), (3, 300, 128, 512), (1, 130, 64, 256), (16, 1024, 128, 512), (2, 128, 128, 128),
+                                        (2, 10000, 100, 384),      # odd chunk count, several tiles per CTA: the acc1 buffers alternate across tiles
+                                        (1, 19100, 36, 128)])     # one chunk per tile, 150 tiles
 def test_mlp2_feed_forward_matches_two_linear_launches(B, P, K1, Hd):
     """N2 = 128: the same products as the two launches; the second layer accumulates in one chain instead of 8-K-block
     chains, so the results agree to fp32 rounding (and are identical when Hd <= 256 = one chain either way)."""
@@ -66,7 +68,7 @@ def test_mlp2_feed_forward_matches_two_linear_launches(B, P, K1, Hd):
         assert torch.equal(y, ref2)
 
 
-@pytest.mark.parametrize("B,P,Hd,per_cloud", [(2, 2048, 1024, True), (3, 384, 1024, True), (2, 200, 512, False)])
+@pytest.mark.parametrize("B,P,Hd,per_cloud", [(2, 2048, 1024, True), (3, 384, 1024, True), (2, 200, 512, False), (2, 9728, 384, True)])
 def test_mlp2_head_256_wide(B, P, Hd, per_cloud):
     """N2 = 256 (seg head conv2 -> conv3): one 32-K-block accumulation chain; fp32-class against fp64."""
     args = _case(B, P, 128, Hd, 256, seed=P, per_cloud_shift1=per_cloud, residual=False, lrelu2=True)
