@@ -65,6 +65,11 @@ int samble_selftest_tc_gemm(const float* A, const float* B, int K, float* D, con
 int samble_selftest_tc_gemm_ts(const float* A, const float* B, int K, float* D, int iters, int ctas, long long* cycles_out,
                                samble_stream_t stream);
 
+/* ... and with bf16 operands (kind::f16): A, B are rounded to bf16; A sits in tensor memory two K elements per 32-bit column (the form
+ * the feature kNN uses for its query tile), or in shared memory when a_in_smem != 0 (for the rate comparison).  K % 64 == 0, K <= 256. */
+int samble_selftest_tc_gemm_ts_bf16(const float* A, const float* B, int K, float* D, int iters, int ctas, long long* cycles_out,
+                                    int a_in_smem, samble_stream_t stream);
+
 /* issue-rate probe: `ctas` CTAs each issue iters*4 back-to-back kind::tf32 128 x n_tile x 8 MMAs on resident smem tiles;
  * cycles_out[cta] = SM cycles from first issue to completion (measured tensor-pipe ceiling of the SS form). */
 int samble_selftest_mma_rate(int n_tile, int iters, int ctas, long long* cycles_out, samble_stream_t stream);
@@ -240,6 +245,9 @@ int samble_n2p_attend(const float* q, const float* k, const float* v, long long 
 /* measurement only (tools/probe_knn.py): low byte: disable phases of knn_tc_kernel (1 MMAs, 2 epilogue; results are garbage
  * while set); bits 8..: CTAs per cluster forced to 1, 2 or 4 (0 = automatic). */
 void samble_set_knn_debug(int bits);
+/* while non-NULL the tensor-core kNN launches write 8 cycle counters per CTA (device memory, 8 * CTAs entries): MMA thread total,
+ * its waits for operands / accumulator drain / query tile, the epilogue's wait for accumulators, producer total, its wait for free stages */
+void samble_set_knn_probe(long long* cycles);
 
 /* measurement only (tools/probe_linear.py): disable phases of linear_tma_kernel (1 operand split, 2 epilogue, 4 MMAs);
  * results are garbage while any bit is set.  0 = normal. */

@@ -30,6 +30,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_profile_report": (_i, (C.c_char_p, _sz)),
     "samble_selftest_tc_gemm": (_i, (_p, _p, _i, _p, _p, _p, _p)),
     "samble_selftest_tc_gemm_ts": (_i, (_p, _p, _i, _p, _i, _i, _p, _p)),
+    "samble_selftest_tc_gemm_ts_bf16": (_i, (_p, _p, _i, _p, _i, _i, _p, _i, _p)),
     "samble_selftest_mma_rate": (_i, (_i, _i, _i, _p, _p)),
     "samble_selftest_mma_rate_ex": (_i, (_i, _i, _i, _i, _i, _i, _p, _p)),
     "samble_set_knn_mode": (None, (_i,)),
@@ -63,6 +64,7 @@ PROTOTYPES: Dict[str, Tuple[object, tuple]] = {
     "samble_set_gather_mode": (None, (_i,)),
     "samble_set_linear_debug": (None, (_i,)),
     "samble_set_knn_debug": (None, (_i,)),
+    "samble_set_knn_probe": (None, (_p,)),
     "samble_ds_row_stats": (_i, (_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _p, _p, _p, _p)),
     "samble_digits_bytes": (_sz, (_i, _i, _i)),
     "samble_digits": (_i, (_p, _ll, _ll, _i, _i, _i, _p, _i, _p, _p, _p, _p)),

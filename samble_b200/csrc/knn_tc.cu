@@ -99,13 +99,16 @@ __device__ __forceinline__ void sort64(float (&v)[64]) {
 // alone taking 27 of 37 us (threshold) and 37 of 71 us (collect) at N = 2048, C = 128 -- the kernel is bound by that stream.
 // In a cluster each stage of the candidate ring is fetched by ONE CTA (round robin) and multicast into all of them; a stage
 // is released when the MMAs of every CTA have retired (multicast tcgen05.commit onto every CTA's empty[] barrier).
-template <bool PASS_B, int CS>
+template <bool PASS_B, int CS, bool PROF = false>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
     knn_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                   const float* __restrict__ anorm, const float* __restrict__ bext, const unsigned* __restrict__ bbmax_bits,
                   int Nq, int Nr, int Cp, int k, float* __restrict__ thr, uint32_t* __restrict__ cand_out,
-                  int* __restrict__ cnt_out, int dbg) {
+                  int* __restrict__ cnt_out, int dbg, long long* __restrict__ prof_out) {
+  // cycle counters of the warp roles exist only in the PROF instantiation (tools/probe_knn_roles.py): even a predicated-off clock read per
+  // stage in the MMA-issuing thread slowed the production kernels by 7-13 %
+  long long* const prof = PROF ? prof_out : nullptr;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = tc::smem_align1024(smem_raw);
   const int nkt = (Cp + 63) / 64;                           // K-tiles of 64 bf16 (128-byte rows) per plane
@@ -174,10 +177,14 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
       const float* ext_g = bext + (size_t)b * ntiles * (kExt / 4);
       int s = 0, ph = 0;
       uint32_t seq = 0;                                     // stage sequence number: CTA (seq mod CS) fetches it for the cluster
+      long long w_empty = 0;                                // (measurement, tools/probe_knn_roles.py)
+      const long long p_t0 = PROF ? clock64() : 0;
       for (int t = 0; t < ntiles; ++t) {
         for (int g = 0; g < kPlanes * nkt; ++g, ++seq) {    // stage order per tile: (kt 0: hi[, lo]), (kt 1: hi[, lo]), ...
           const int kt = PASS_B ? g >> 1 : g;
+          const long long p_t = (PROF && prof) ? clock64() : 0;
           tc::mbar_wait(&empty[s], ph ^ 1);                 // the MMAs of EVERY CTA of the cluster have retired from stage s
+          if (PROF && prof) w_empty += clock64() - p_t;
           if (g == 0) {
             // the tile's norm slice rides on the barrier of its first stage; buffer t&1 is free once the norm
             // MMA of tile t-2 retired
@@ -195,6 +202,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
+      if (PROF && prof) {
+        long long* o = prof + 8 * (blockIdx.y * gridDim.x + blockIdx.x);
+        o[5] = clock64() - p_t0, o[6] = w_empty;
+      }
     }
     __syncwarp();
   } else if (warp == 4) {
@@ -202,15 +213,22 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
     if (tc::elect_one()) {
       const uint32_t idesc = tc::instr_desc(1, kTcRows, kTcTile);          // bf16 x bf16 -> fp32
       const uint64_t axd = tc::smem_desc_nosw(tc::smem_u32(sAx), 128);
+      long long w_full = 0, w_tempty = 0, w_a = 0;          // (measurement, tools/probe_knn_roles.py)
+      const long long m_t0 = PROF ? clock64() : 0;
       tc::mbar_wait(afull, 0);
+      if (PROF && prof) w_a = clock64() - m_t0;
       int s = 0, ph = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int acc = t & 1;
+        long long m_t = (PROF && prof) ? clock64() : 0;
         tc::mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1);
+        if (PROF && prof) w_tempty += clock64() - m_t;
         tc::tc_fence_after();
         for (int g = 0; g < kPlanes * nkt; ++g) {
           const int kt = PASS_B ? g >> 1 : g;
+          m_t = (PROF && prof) ? clock64() : 0;
           tc::mbar_wait(&full[s], ph);
+          if (PROF && prof) w_full += clock64() - m_t;
           tc::tc_fence_after();
           const uint64_t ah = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)kt * 16384));
           const uint64_t al = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)(nkt + kt) * 16384));
@@ -239,6 +257,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
         }
         tc::mma_commit(&tfull[acc]);                // accumulator complete
       }
+      if (PROF && prof) {
+        long long* o = prof + 8 * (blockIdx.y * gridDim.x + blockIdx.x);
+        o[0] = clock64() - m_t0, o[1] = w_full, o[2] = w_tempty, o[3] = w_a;
+      }
     }
     __syncwarp();
   } else {
@@ -256,9 +278,12 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
     } else {
       my_thr = q < Nq ? thr[(size_t)b * Nq + q] : INFINITY;
     }
+    long long w_tfull = 0;
     for (int t = 0; t < ntiles; ++t) {
       const int acc = t & 1;
+      const long long e_t = (PROF && prof) ? clock64() : 0;
       tc::mbar_wait(&tfull[acc], (t >> 1) & 1);
+      if (PROF && prof) w_tfull += clock64() - e_t;
       tc::tc_fence_after();
       if (!(dbg & 2))
 #pragma unroll
@@ -284,6 +309,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
       tc::tc_fence_before();
       tc::mbar_arrive(&tempty[acc]);
     }
+    if (PROF && prof && tid == 0) prof[8 * (blockIdx.y * gridDim.x + blockIdx.x) + 4] = w_tfull;
     if (!PASS_B) {
       if (q < Nq) {
         sort64(gmax);
@@ -602,6 +628,9 @@ __global__ void __launch_bounds__(256, 5) knn_select_kernel(const float* __restr
 int g_knn_tc_debug = 0;
 // CTAs per cluster: -1 = automatic (2 when the number of query tiles is even), 1 / 2 / 4 forced (4 needs a multiple of 4 tiles)
 int g_knn_cluster = -1;
+// measurement (tools/probe_knn_roles.py): per CTA [MMA thread total, wait operands, wait accumulator drain, wait query tile, epilogue thread's wait for
+// accumulators, producer total, producer's wait for free stages, -] cycles; written by the NEXT tensor-core launches while non-null
+long long* g_knn_prof = nullptr;
 
 // ---- host side ----
 size_t knn_tc_ext_floats(int B, int Nr);
@@ -633,20 +662,20 @@ int launch_knn_tc(const float* an, const float* anorm, const float* bn, const fl
   const int cs = g_knn_cluster > 0 ? g_knn_cluster : 1;     // clusters sharing the candidate stream: measured no gain (the stream is latency-, not bandwidth-bound), kept switchable
   {
     size_t smem = tc_smem_bytes(nkb, false);
-    auto kern = cs == 2 ? knn_tc_kernel<false, 2> : (cs == 4 ? knn_tc_kernel<false, 4> : knn_tc_kernel<false, 1>);
+    auto kern = cs == 2 ? knn_tc_kernel<false, 2> : (cs == 4 ? knn_tc_kernel<false, 4> : (g_knn_prof ? knn_tc_kernel<false, 1, true> : knn_tc_kernel<false, 1>));
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("knn_tc pass A smem attribute");
     SAMBLE_PRE(st);
-    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_al, map_b, map_bl, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt, g_knn_tc_debug);
+    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_al, map_b, map_bl, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt, g_knn_tc_debug, g_knn_prof);
     SAMBLE_LAUNCHED("knn_tc_threshold_kernel");
   }
   {
     size_t smem = tc_smem_bytes(nkb, true);
-    auto kern = cs == 2 ? knn_tc_kernel<true, 2> : (cs == 4 ? knn_tc_kernel<true, 4> : knn_tc_kernel<true, 1>);
+    auto kern = cs == 2 ? knn_tc_kernel<true, 2> : (cs == 4 ? knn_tc_kernel<true, 4> : (g_knn_prof ? knn_tc_kernel<true, 1, true> : knn_tc_kernel<true, 1>));
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("knn_tc pass B smem attribute");
     SAMBLE_PRE(st);
-    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_al, map_b, map_bl, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt, g_knn_tc_debug);
+    kern<<<grid, kTcThreads, smem, st>>>(map_a, map_al, map_b, map_bl, anorm, bext, bbmax, Nq, Nr, Cp, k, thr, cand, cnt, g_knn_tc_debug, g_knn_prof);
     SAMBLE_LAUNCHED("knn_tc_collect_kernel");
   }
   SAMBLE_PRE(st);
@@ -670,4 +699,5 @@ template int launch_knn_tc<long long>(const float*, const float*, const float*, 
 
 }  // namespace samble
 
+extern "C" void samble_set_knn_probe(long long* cycles) { samble::g_knn_prof = cycles; }
 extern "C" void samble_set_knn_debug(int bits) { samble::g_knn_tc_debug = bits & 0xff; samble::g_knn_cluster = (bits >> 8) ? (bits >> 8) : -1; }

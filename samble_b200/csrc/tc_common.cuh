@@ -276,6 +276,22 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
+// the same with bf16 operands (kind::f16): A in tensor memory holds TWO K elements per 32-bit column (low half = the even one),
+// 8 columns per 128 x N x 16 instruction.  Without the A tile the MMA reads half the shared-memory bytes: a 128 x 128 x 16
+// product runs at the tensor pipe's ~66 cycles instead of the ~100 of the smem-smem form (tools/probe_tmem_a.py).
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .b64 db;\n setp.ne.b32 p, %4, 0;\n mov.b64 db, {%2, %5};\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescSw128Hi)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32u(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr), "r"(r[0]),"r"(r[1]),"r"(r[2]),"r"(r[3]),"r"(r[4]),"r"(r[5]),"r"(r[6]),"r"(r[7]),"r"(r[8]),"r"(r[9]),"r"(r[10]),"r"(r[11]),"r"(r[12]),"r"(r[13]),"r"(r[14]),"r"(r[15]),"r"(r[16]),"r"(r[17]),"r"(r[18]),"r"(r[19]),"r"(r[20]),"r"(r[21]),"r"(r[22]),"r"(r[23]),"r"(r[24]),"r"(r[25]),"r"(r[26]),"r"(r[27]),"r"(r[28]),"r"(r[29]),"r"(r[30]),"r"(r[31])
+      : "memory");
+}
+
 }  // namespace tc
 
 // host: rank-3 fp32 tensor map over a (batch, rows, inner) array with row pitch `ld` floats (16-byte multiple) and

@@ -300,3 +300,102 @@ extern "C" int samble_selftest_tc_gemm_ts(const float* A, const float* B, int K,
   SAMBLE_LAUNCHED("tc_gemm_ts_selftest_kernel");
   return SAMBLE_OK;
 }
+
+// ---- bf16 (kind::f16) with the A operand in tensor memory: two K elements per 32-bit column.  A, B arrive as fp32 and are rounded to
+// bf16 here; B goes to shared memory as [128 x 64 bf16] SW128 K-tiles, A to TMEM columns [128, 128 + K/2). ----
+#include <cuda_bf16.h>
+namespace samble {
+template <bool A_SMEM>
+__global__ void __launch_bounds__(128) tc_gemm_ts_bf16_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, int K,
+                                                                       float* __restrict__ D, int iters, long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = tc::smem_align1024(smem_raw);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkt = K / 64;
+  uint8_t* sB = base;
+  uint8_t* sA = base + (size_t)nkt * 16384;
+  auto pack = [](float lo, float hi) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
+  };
+  for (int kt = 0; kt < nkt; ++kt)
+    for (int p = tid; p < 1024; p += 128) {
+      const int row = p >> 3, ch = p & 7;                                // 16-byte chunk = 8 bf16
+      const float* src = B + (size_t)row * K + kt * 64 + ch * 8;
+      *reinterpret_cast<uint4*>(sB + (size_t)kt * 16384 + tc::sw128_offset(row, ch)) =
+          make_uint4(pack(src[0], src[1]), pack(src[2], src[3]), pack(src[4], src[5]), pack(src[6], src[7]));
+      const float* sa = A + (size_t)row * K + kt * 64 + ch * 8;
+      *reinterpret_cast<uint4*>(sA + (size_t)kt * 16384 + tc::sw128_offset(row, ch)) =
+          make_uint4(pack(sa[0], sa[1]), pack(sa[2], sa[3]), pack(sa[4], sa[5]), pack(sa[6], sa[7]));
+    }
+  tc::fence_proxy_async();
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < K / 2; c0 += 32) {
+    uint32_t v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = pack(A[(size_t)row * K + 2 * (c0 + i)], A[(size_t)row * K + 2 * (c0 + i) + 1]);
+    tc::tmem_st32u(tmem + lane_base + 128 + c0, v);
+  }
+  tc::tmem_st_wait();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = tc::instr_desc(1, 128, 128);
+    const long long t0 = clock64();
+    for (int it = 0; it < (iters > 0 ? iters : 1); ++it)
+      for (int kt = 0; kt < nkt; ++kt) {
+        const uint32_t bl = tc::smem_desc_sw128_lo(tc::smem_u32(sB + (size_t)kt * 16384));
+        const uint32_t al = tc::smem_desc_sw128_lo(tc::smem_u32(sA + (size_t)kt * 16384));
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) {
+          if (A_SMEM) tc::mma_bf16_lo(tmem, al + 2 * k16, bl + 2 * k16, idesc, (it | kt | k16) != 0);
+          else tc::mma_bf16_ts(tmem, tmem + 128 + kt * 32 + k16 * 8, bl + 2 * k16, idesc, (it | kt | k16) != 0);
+        }
+      }
+    tc::mma_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    if (cycles_out) cycles_out[blockIdx.x] = clock64() - t0;
+  }
+  __syncthreads();
+  tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  if (blockIdx.x == 0)
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      float v[32];
+      tc::tmem_ld32(tmem + lane_base + c0, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) D[(size_t)row * 128 + c0 + i] = v[i];
+    }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace samble
+
+extern "C" int samble_selftest_tc_gemm_ts_bf16(const float* A, const float* B, int K, float* D, int iters, int ctas, long long* cycles_out,
+                                               int a_in_smem, samble_stream_t stream) {
+  SAMBLE_REQUIRE(A && B && D, "samble_selftest_tc_gemm_ts_bf16: null pointer");
+  SAMBLE_REQUIRE(K > 0 && K % 64 == 0 && K <= 256, "samble_selftest_tc_gemm_ts_bf16: K=%d must be a multiple of 64, <= 256", K);
+  SAMBLE_REQUIRE(ctas >= 1 && iters >= 0, "samble_selftest_tc_gemm_ts_bf16: bad iters / ctas");
+  size_t smem = (size_t)(K / 64) * 2 * 16384 + 1024;
+  auto kern = a_in_smem ? tc_gemm_ts_bf16_selftest_kernel<true> : tc_gemm_ts_bf16_selftest_kernel<false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("tc_gemm_ts_bf16_selftest smem attribute");
+  cudaStream_t st = (cudaStream_t)stream;
+  SAMBLE_PRE(st);
+  kern<<<ctas, 128, smem, st>>>(A, B, K, D, iters, cycles_out);
+  SAMBLE_LAUNCHED("tc_gemm_ts_bf16_selftest_kernel");
+  return SAMBLE_OK;
+}
