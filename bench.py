@@ -423,9 +423,9 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION, set on some boxes) goes there too
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line: NCCL's own diagnostics (the "NCCL version ..." banner of NCCL_DEBUG=VERSION / WARN, set on
+        # some boxes) go to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = False          # stock GEMMs stay true fp32
     torch.backends.cudnn.allow_tf32 = False
