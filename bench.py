@@ -366,7 +366,7 @@ def linear_roofline(ms, census, pk, workload="seg"):
             "algorithmic_gb_per_step": census["bytes"] / 1e9, "hbm_gbs": census["bytes"] / sec / 1e9,
             "flop_per_byte": census["flops"] / census["bytes"],
             "traffic": (tr["dram_bytes_per_step"] / tr["launches_per_step"]) if tr else None,
-            "traffic_note": "DRAM read+write bytes per launch (ncu --set full, profiles/r2k_final_full.md), average over the two families' "
+            "traffic_note": "DRAM read+write bytes per launch (ncu --set full, profiles/r2r_final_full.md), average over the two families' "
                             f"{tr['launches_per_step']} launches of the seg step; algorithmic bytes per launch: "
                             f"{census['bytes'] / max(census['calls'], 1):.0f}" if tr else None,
             "note": "3 kind::tf32 MMAs per fp32-class product: peak = (bf16 sustained / 2) / 3; the layers sit above the 3xTF32 ridge "

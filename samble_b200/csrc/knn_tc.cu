@@ -213,7 +213,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
     if (tc::elect_one()) {
       const uint32_t idesc = tc::instr_desc(1, kTcRows, kTcTile);          // bf16 x bf16 -> fp32
       const uint64_t axd = tc::smem_desc_nosw(tc::smem_u32(sAx), 128);
-      long long w_full = 0, w_tempty = 0, w_a = 0;          // (measurement, tools/probe_knn_roles.py)
+      long long w_full = 0, w_tempty = 0, w_a = 0, w_issue = 0;          // (measurement, tools/probe_knn_roles.py)
       const long long m_t0 = PROF ? clock64() : 0;
       tc::mbar_wait(afull, 0);
       if (PROF && prof) w_a = clock64() - m_t0;
@@ -230,6 +230,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
           tc::mbar_wait(&full[s], ph);
           if (PROF && prof) w_full += clock64() - m_t;
           tc::tc_fence_after();
+          const long long i_t = (PROF && prof) ? clock64() : 0;
           const uint64_t ah = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)kt * 16384));
           const uint64_t al = tc::smem_desc_sw128(tc::smem_u32(sA + (size_t)(nkt + kt) * 16384));
           const uint64_t bd = tc::smem_desc_sw128(tc::smem_u32(sB + (size_t)s * 16384));
@@ -246,6 +247,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) tc::mma_bf16(tmem + acc * kTcTile, ah + 2 * k16, bd + 2 * k16, idesc, 1);
           }
+          if (PROF && prof) w_issue += clock64() - i_t;
           if (g == kPlanes * nkt - 1) {
             // norm slice of tile t: landed with full[] of the tile's first stage, which this thread waited on
             if (!(dbg & 1)) tc::mma_bf16(tmem + acc * kTcTile, axd, tc::smem_desc_nosw(tc::smem_u32(sBx + (size_t)(t & 1) * kExt), 128), idesc, 1);
@@ -259,7 +261,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
       }
       if (PROF && prof) {
         long long* o = prof + 8 * (blockIdx.y * gridDim.x + blockIdx.x);
-        o[0] = clock64() - m_t0, o[1] = w_full, o[2] = w_tempty, o[3] = w_a;
+        o[0] = clock64() - m_t0, o[1] = w_full, o[2] = w_tempty, o[3] = w_a, o[7] = w_issue;
       }
     }
     __syncwarp();
@@ -629,7 +631,7 @@ int g_knn_tc_debug = 0;
 // CTAs per cluster: -1 = automatic (2 when the number of query tiles is even), 1 / 2 / 4 forced (4 needs a multiple of 4 tiles)
 int g_knn_cluster = -1;
 // measurement (tools/probe_knn_roles.py): per CTA [MMA thread total, wait operands, wait accumulator drain, wait query tile, epilogue thread's wait for
-// accumulators, producer total, producer's wait for free stages, -] cycles; written by the NEXT tensor-core launches while non-null
+// accumulators, producer total, producer's wait for free stages, MMA thread's descriptor + MMA issue time] cycles; written by the NEXT tensor-core launches while non-null
 long long* g_knn_prof = nullptr;
 
 // ---- host side ----

@@ -23,7 +23,7 @@ for (B, N, C), bits in itertools.product(((16, 2048, 128), (16, 2048, 64)), (0, 
     w = buf.view(ctas, 8).double() / 1e3
     tiles = N // 128
     print(f"B={B} N={N} C={C} [{('full', 'no MMAs', 'idle epilogue', 'no MMAs, idle epilogue')[bits]}]: collect pass, {ctas} CTAs, {tiles} candidate tiles each; k cycles, mean over CTAs (max)")
-    for name, col in (("MMA thread total", 0), ("  wait operand stages", 1), ("  wait accumulator drain (epilogue)", 2), ("  wait query tile", 3),
+    for name, col in (("MMA thread total", 0), ("  wait operand stages", 1), ("  wait accumulator drain (epilogue)", 2), ("  wait query tile", 3), ("  descriptors + MMA issue (rest: commits, loop)", 7),
                       ("epilogue: wait for accumulators", 4), ("producer total", 5), ("  wait free stages", 6)):
         print(f"   {name:38s} {w[:, col].mean().item():7.1f} ({w[:, col].max().item():7.1f})")
     nkt = (C + 63) // 64
