@@ -125,8 +125,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
   uint64_t* empty = bars + kStages;           // [kStages]
   uint64_t* tfull = bars + 2 * kStages;       // [2]
   uint64_t* tempty = tfull + 2;               // [2]
-  uint64_t* xempty = tempty + 2;              // [2]  norm slice of tile t may be overwritten (its MMA retired)
-  uint64_t* afull = xempty + 2;               // query tile landed
+  uint64_t* afull = tempty + 2;               // query tile landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -150,7 +149,6 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(&tfull[a], 1);
       tc::mbar_init(&tempty[a], 128);
-      tc::mbar_init(&xempty[a], 1);
     }
     tc::mbar_init(afull, 1);
     tc::mbar_init_fence();
@@ -186,9 +184,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
           tc::mbar_wait(&empty[s], ph ^ 1);                 // the MMAs of EVERY CTA of the cluster have retired from stage s
           if (PROF && prof) w_empty += clock64() - p_t;
           if (g == 0) {
-            // the tile's norm slice rides on the barrier of its first stage; buffer t&1 is free once the norm
-            // MMA of tile t-2 retired
-            tc::mbar_wait(&xempty[t & 1], ((t >> 1) & 1) ^ 1);
+            // the tile's norm slice rides on the barrier of its first stage; buffer t&1 is free once the norm MMA of tile t-2
+            // retired -- which is what tfull[t&1] of that tile announces (a tcgen05.commit costs the issuing thread ~300 cycles,
+            // tools/probe_knn_roles.py: 96 of them were 30 k of the MMA thread's 55 k cycles, so the slice has no barrier of its
+            // own any more; tile t's own completion of tfull[t&1] cannot precede this wait, it needs the loads issued below)
+            if (t >= 2) tc::mbar_wait(&tfull[t & 1], ((t - 2) >> 1) & 1);
             tc::mbar_arrive_expect_tx(&full[s], 16384u + kExt);
             tc::bulk_load_1d(sBx + (size_t)(t & 1) * kExt, ext_g + (size_t)t * (kExt / 4), kExt, &full[s]);
           } else {
@@ -251,7 +251,6 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kTcThreads, 1)
           if (g == kPlanes * nkt - 1) {
             // norm slice of tile t: landed with full[] of the tile's first stage, which this thread waited on
             if (!(dbg & 1)) tc::mma_bf16(tmem + acc * kTcTile, axd, tc::smem_desc_nosw(tc::smem_u32(sBx + (size_t)(t & 1) * kExt), 128), idesc, 1);
-            tc::mma_commit(&xempty[t & 1]);
           }
           if (CS == 1) tc::mma_commit(&empty[s]);   // smem stage reusable once these MMAs retire ...
           else tc::mma_commit_multicast(&empty[s], kMask);          // ... in every CTA of the cluster
