@@ -423,9 +423,6 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own diagnostics (the "NCCL version ..." banner of NCCL_DEBUG=VERSION / WARN, set on
-        # some boxes) go to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = False          # stock GEMMs stay true fp32
     torch.backends.cudnn.allow_tf32 = False
@@ -596,6 +593,22 @@ def run_native(args):
 
 if __name__ == "__main__":
     a = parse()
+    # stdout carries exactly ONE JSON line.  Native libraries write banners there on some boxes (NCCL prints "NCCL version ..." at communicator
+    # creation whatever NCCL_DEBUG_FILE says): file descriptor 1 points at stderr while the benchmark runs and is restored for the result line.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*args, **kw):          # noqa: A001  (the result lines below go to the real stdout)
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        try:
+            _print(*args, **kw)
+            sys.stdout.flush()
+        finally:
+            os.dup2(2, 1)
+
     if a.impl == "reference":
         run_reference(a)
     else:
