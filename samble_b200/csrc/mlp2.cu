@@ -18,7 +18,8 @@
 // Y is ONE accumulation chain (Hd / 32 K-blocks) in both layouts.
 //
 // Warps 0-7 conversion + output epilogue (warp & 3 = TMEM lane quadrant, warp >> 2 = column half), 8 MMA issuer, 9 weight
-// producer, 10-11 X loader / splitters (X_lo = X - trunc_tf32(X)).  12 warps: 168 registers per thread, no spills.
+// producer, 10-11 X loader / splitters (X_lo = X - trunc_tf32(X)).  12 warps: 168 registers per thread (no spills without first-layer
+// scale / shift; ~0.5 KB of spill traffic in the CONSTS instantiations, whose 64 constants are prefetched across the accumulator wait).
 #include "linear_common.cuh"
 
 namespace samble {

@@ -60,6 +60,17 @@ def test_no_cpu_fallback():
         m(torch.randn(1, 3, 16), torch.zeros(1, 16, 1))
 
 
+def test_mlp2_host_side_contract():
+    """the fused two-layer kernel's host wrapper: shape gate, and no CPU path (csrc/mlp2.cu behind ops.mlp2)."""
+    assert ops.mlp2_eligible(128, 512, 128) and ops.mlp2_eligible(128, 1024, 256) and ops.mlp2_eligible(64, 256, 128)
+    assert not ops.mlp2_eligible(256, 512, 128)          # input wider than one resident X tile
+    assert not ops.mlp2_eligible(128, 500, 128)          # hidden width not a whole number of 128-wide chunks
+    assert not ops.mlp2_eligible(128, 512, 64)           # output tile must be 128 or 256 wide
+    x, w1, w2 = torch.randn(1, 128, 128), torch.randn(512, 128), torch.randn(128, 512)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.mlp2(x, w1, w2)
+
+
 def test_host_build_of_k_allocation_matches_oracle():
     """csrc/kalloc.h is compiled for the host too; the CUDA sampler runs the same source."""
     from oracle import samble_oracle as O
